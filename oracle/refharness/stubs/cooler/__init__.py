@@ -1,0 +1,158 @@
+"""Fake ``cooler`` package: just enough of ``cooler.Cooler`` for the UNMODIFIED reference
+drivers ``stripenn.compute`` / ``score.getScore`` to run on the ``.npz`` contact maps of
+``stripenn_b200.contactmap`` (cooler, h5py and libhdf5 are not installed; no network).
+
+This file DEFINES the ``matrix(balance).fetch`` semantics the whole project is tested against
+(cooler/api.py ``matrix``/``RangeSelector2D`` restated from its documented
+behaviour):
+
+* region ``"chr:start-end"`` is a half-open bp interval -> bins ``[start // r, ceil(end / r))``;
+  a bare ``"chr"`` is the whole chromosome; ``end < start`` or ``end > chromsize`` raise
+  ``ValueError`` (that is why the reference clamps, getStripe.py:187-190,317-322,805-806);
+* ``balance=False`` -> raw int32 counts; ``True`` -> column ``weight``; a name -> that bins
+  column, inverted first when it is one of cooler's divisive names (KR, VC, VC_SQRT);
+* dense balanced window = ``counts * np.outer(w_rows, w_cols)`` (outer product first), so a
+  bin with NaN weight yields a whole NaN row and column — zeros included;
+* the matrix is symmetric: the stored upper triangle is mirrored.
+
+TEST INFRASTRUCTURE ONLY (oracle/refharness) — never imported by the product.
+"""
+import math
+import re
+
+import numpy as np
+import scipy.sparse as sp
+
+__version__ = "0.0-fake"
+
+_DIVISIVE = ("KR", "VC", "VC_SQRT", "SQRT_VC")
+_CACHE = {}
+
+
+class _SizeArray(np.ndarray):
+    """chromsizes: a numpy array (positional indexing, fancy indexing, arithmetic — what the
+    reference does at stripenn.py:95-116 and getStripe.py:33,242,805) that also answers
+    ``.keys()`` like the pandas Series real cooler returns (getStripe.py:164)."""
+
+    def __new__(cls, values, names):
+        obj = np.asarray(values, dtype=np.int64).view(cls)
+        obj._names = list(names)
+        return obj
+
+    def __array_finalize__(self, obj):
+        self._names = getattr(obj, "_names", None)
+
+    def keys(self):
+        return list(self._names)
+
+
+class _Columns(list):
+    pass
+
+
+class _Bins:
+    def __init__(self, cols):
+        self.columns = _Columns(cols)
+
+
+def _load(path):
+    if path in _CACHE:
+        return _CACHE[path]
+    z = np.load(path, allow_pickle=False)
+    names = [str(x) for x in z["chromnames"]]
+    sizes = z["chromsizes"].astype(np.int64)
+    binsize = int(z["binsize"])
+    wcols = [str(x) for x in z["weight_columns"]]
+    mats, weights = {}, {c: {} for c in wcols}
+    for i, name in enumerate(names):
+        if "c%d_bin1" % i not in z:
+            continue
+        nb = int(math.ceil(int(sizes[i]) / binsize))
+        b1 = z["c%d_bin1" % i].astype(np.int64)
+        b2 = z["c%d_bin2" % i].astype(np.int64)
+        cnt = z["c%d_count" % i].astype(np.int32)
+        off = b1 != b2
+        rows = np.concatenate([b1, b2[off]])
+        cols = np.concatenate([b2, b1[off]])
+        vals = np.concatenate([cnt, cnt[off]])
+        mats[name] = sp.csr_matrix((vals, (rows, cols)), shape=(nb, nb), dtype=np.int32)
+        for c in wcols:
+            weights[c][name] = z["c%d_w_%s" % (i, c)].astype(np.float64)
+    data = dict(names=names, sizes=sizes, binsize=binsize, wcols=wcols, mats=mats,
+                weights=weights)
+    _CACHE[path] = data
+    return data
+
+
+_REGION = re.compile(r"^(.+?)(?::([0-9,]+)-([0-9,]+))?$")
+
+
+class _Selector:
+    """``Cooler.matrix(balance=...)`` — only ``fetch`` is used by the reference."""
+
+    def __init__(self, path, balance):
+        self._path = path
+        self._balance = balance
+        self.nfetch = 0
+
+    def __reduce__(self):  # pickle by reference: loky/cloudpickle copies stay cheap
+        return (_Selector, (self._path, self._balance))
+
+    def _parse(self, region):
+        d = _load(self._path)
+        region = str(region)
+        chrom, start, end = None, None, None
+        if ":" in region:
+            chrom, rest = region.rsplit(":", 1)
+            s, e = rest.split("-")
+            start, end = int(s.replace(",", "")), int(e.replace(",", ""))
+        else:
+            chrom = region
+        if chrom not in d["names"]:
+            raise ValueError("Unknown sequence label: %s" % chrom)
+        size = int(d["sizes"][d["names"].index(chrom)])
+        if start is None:
+            start, end = 0, size
+        if end < start:
+            raise ValueError("End cannot be less than start")
+        if start < 0 or end > size:
+            raise ValueError("Genomic region out of bounds: [%d, %d)" % (start, end))
+        r = d["binsize"]
+        return chrom, start // r, int(math.ceil(end / r))
+
+    def fetch(self, region, region2=None):
+        d = _load(self._path)
+        if region2 is None:
+            region2 = region
+        c1, i0, i1 = self._parse(region)
+        c2, j0, j1 = self._parse(region2)
+        if c1 != c2:
+            raise NotImplementedError("trans windows are never requested by stripenn")
+        self.nfetch += 1
+        arr = d["mats"][c1][i0:i1, j0:j1].toarray()
+        bal = self._balance
+        if bal is False or bal is None:
+            return arr
+        col = "weight" if bal is True else str(bal)
+        w = d["weights"][col][c1]
+        if col in _DIVISIVE:
+            with np.errstate(divide="ignore", invalid="ignore"):
+                w = 1.0 / w
+        with np.errstate(invalid="ignore"):
+            return arr * np.outer(w[i0:i1], w[j0:j1])
+
+
+class Cooler:
+    def __init__(self, path):
+        self._path = str(path)
+        d = _load(self._path)
+        self.chromnames = list(d["names"])
+        self.chromsizes = _SizeArray(d["sizes"], d["names"])
+        self.binsize = d["binsize"]
+        self._info = {"bin-size": d["binsize"]}
+
+    def bins(self):
+        return _Bins(["chrom", "start", "end"] + list(_load(self._path)["wcols"]))
+
+    def matrix(self, balance=True, **_kw):
+        return _Selector(self._path, balance)
