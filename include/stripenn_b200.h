@@ -1,0 +1,161 @@
+/* stripenn_b200 — C ABI of the B200-native `stripenn compute` / `score` hot path.
+ *
+ * The reference (ysora/stripenn 1.1.65.22) has no FFI: its hot path is the Python class
+ * `getStripe` (src/stripenn/getStripe.py:17-33) on top of `cooler.matrix(balance).fetch`.
+ * Every entry point below replaces one method of that class (cited per function); the
+ * Python host in stripenn_b200/ binds them with ctypes (see INTEGRATION.md for the stub a
+ * maintainer of the reference would add).
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative SNN_E* code on failure; the message is
+ *    available from snn_last_error(ctx) (ctx may be NULL for errors of snn_create);
+ *  - the caller owns every host buffer; the library owns device memory behind `snn_ctx`;
+ *  - one context per GPU, used from one host thread at a time; all work of a context is
+ *    issued on one CUDA stream (its own, or the one given to snn_set_stream) and every
+ *    function that returns data to host memory synchronises that stream before returning;
+ *  - there is NO CPU fallback: without a CUDA device snn_create fails with SNN_ENODEV.
+ */
+#ifndef STRIPENN_B200_H
+#define STRIPENN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SNN_VERSION 100
+
+#define SNN_OK 0
+#define SNN_EINVAL (-1)   /* bad argument                                  */
+#define SNN_ENODEV (-2)   /* no usable CUDA device / wrong architecture     */
+#define SNN_ECUDA (-3)    /* CUDA runtime error (message has the details)   */
+#define SNN_ENOMEM (-4)   /* device or host allocation failed               */
+#define SNN_ECAP (-5)     /* caller's output buffer too small (n_out = need) */
+#define SNN_ESTATE (-6)   /* call order violated (e.g. chromosome not loaded) */
+#define SNN_ERANGE (-7)   /* a window needs matrix entries outside the band  */
+
+#define SNN_NDIST 400     /* distances 0..399 (framesize of getStripe.py:794) */
+#define SNN_NBRIGHT 6     /* np.arange(0.5, 1.01, 0.1) (getStripe.py:898)      */
+
+/* cv.cvtColor float32 RGB2GRAY rounding variants */
+#define SNN_GRAY_IPP 0    /* fmaf(B,cb, fl(fl(R*cr) + fl(G*cg)))  — OpenCV with IPP (default wheels) */
+#define SNN_GRAY_FMA2 1   /* fmaf(B,cb, fmaf(G,cg, fl(R*cr)))     — universal intrinsics, FMA3        */
+#define SNN_GRAY_PLAIN 2  /* fl(fl(fl(R*cr)+fl(G*cg)) + fl(B*cb)) — cv.setUseOptimized(False)          */
+
+typedef struct snn_ctx snn_ctx;
+
+/* One candidate stripe as emitted by StripeSearch (getStripe.py:1081-1110), before any
+ * RemoveRedundant.  Records come back ordered exactly like the reference emits them:
+ * maxpixel index, window id, brightness pass, direction (up then down), pair index. */
+typedef struct snn_candidate {
+    int32_t q;        /* index into the maxpixel list                          */
+    int32_t frame;    /* window id `num` (getStripe.py:842)                    */
+    int32_t bright;   /* brightness pass 0..5                                  */
+    int32_t ud;       /* 1 = up, 2 = down (getStripe.py:937-940)               */
+    int32_t k;        /* emission index inside (q, frame, bright, ud)          */
+    int32_t x, y, w, h;   /* window-local, after zero-column compaction        */
+    int32_t start, end;   /* first/last bin of the window (getStripe.py:794-801) */
+    int32_t S;        /* compacted window size                                 */
+    int64_t pos1, pos2, pos3, pos4;   /* bp, 1-based inclusive                 */
+    double total;     /* submat[y:y+h, x:x+w].sum() (getStripe.py:1095)         */
+} snn_candidate;
+
+/* ---- life cycle ------------------------------------------------------------------- */
+int snn_version(void);
+int snn_create(int device, snn_ctx** out);
+void snn_destroy(snn_ctx* ctx);
+const char* snn_last_error(const snn_ctx* ctx);
+/* Issue all work on an existing CUDA stream (cudaStream_t passed as void*); NULL restores
+ * the context's own stream.  Lets a host that times with its own events see the kernels. */
+int snn_set_stream(snn_ctx* ctx, void* cuda_stream);
+int snn_synchronize(snn_ctx* ctx);
+
+/* ---- a1: the data boundary — replaces cooler.Cooler.matrix(balance).fetch
+ * (stripenn.py:118; call sites getStripe.py:172,193,266,326,432,518,560,684,690,696,808).
+ * Upper-triangle COO pixels (bin1 <= bin2, chromosome-local bin ids) and the per-bin
+ * MULTIPLICATIVE weight vector (NULL = raw counts; NaN = masked bin; a divisive column such
+ * as KR is inverted by the host) are uploaded once and turned into a diagonal band
+ * band[i][d] = count(i,i+d) * (w[i]*w[i+d]), d in [0, band_width), resident in HBM.
+ * Entries with d >= band_width stay in the COO arrays (used by the quantiles and the row
+ * flags) but are not addressable as windows (SNN_ERANGE). */
+int snn_load_chrom(snn_ctx* ctx, int chrom_id, int64_t nbins, int64_t binsize,
+                   int64_t chromsize_bp, int64_t nnz, const int32_t* bin1, const int32_t* bin2,
+                   const int32_t* count, const double* weight, int band_width);
+int snn_unload_chrom(snn_ctx* ctx, int chrom_id);
+/* Same, but the four arrays are DEVICE pointers already resident in HBM (zero-copy: the
+ * library keeps using them, the caller must keep them alive until snn_unload_chrom). */
+int snn_load_chrom_device(snn_ctx* ctx, int chrom_id, int64_t nbins, int64_t binsize,
+                          int64_t chromsize_bp, int64_t nnz, const int32_t* d_bin1,
+                          const int32_t* d_bin2, const int32_t* d_count, const double* d_weight,
+                          int band_width);
+/* Dense window rows [i0,i1) x cols [j0,j1) in bins (NaN kept) — debugging / tests only. */
+int snn_fetch(snn_ctx* ctx, int chrom_id, int64_t i0, int64_t i1, int64_t j0, int64_t j1,
+              double* out);
+
+/* ---- a2: getStripe.getQuantile_original (getStripe.py:160-176):
+ * np.quantile(mat[mat > 0], q) over the full symmetric matrix (off-diagonal pixels count
+ * twice), numpy 'linear' interpolation reproduced bit-exactly. */
+int snn_quantiles(snn_ctx* ctx, int chrom_id, int nq, const double* q, double* out);
+
+/* ---- a3: getStripe.mpmean (getStripe.py:178-235): expected value per diagonal. */
+int snn_expected(snn_ctx* ctx, int chrom_id, double* out /* [SNN_NDIST] */);
+
+/* ---- a4: getStripe.nulldist (getStripe.py:238-499).  The host owns the sampling plan (it
+ * draws with Python's random.Random like the reference); the device answers the two
+ * questions the plan needs and then evaluates the planned samples.
+ * snn_row_flags: geom = nunits x 6 int64 {i0, i1, wi0, wi1, wj0, wj1}: rows [i0,i1) with a
+ * non-zero sum inside their own square block [i0,i1) -> avail (available_cols, :249-273);
+ * rows [wi0,wi1) with a non-zero sum over columns [wj0,wj1) -> live (pool, :328-335). */
+int snn_row_flags(snn_ctx* ctx, int chrom_id, int nunits, const int64_t* geom,
+                  uint8_t* avail /* [nbins] */, uint8_t* live /* [nbins] */);
+/* spec = nsamp x 6 int32 {i0, i1, j0, j1, x, shift}: fetched window extent in bins, local
+ * row, column offset (:358-360).  out = 4 x SNN_NDIST x nsamp doubles in the order
+ * bgleft_up, bgright_up, bgleft_down, bgright_down (row-major [table][distance][sample]). */
+int snn_background(snn_ctx* ctx, int chrom_id, int64_t nsamp, const int32_t* spec, double* out);
+/* Install the genome-wide tables (all chromosomes concatenated by the host, same layout)
+ * used by snn_score's p-values; they are sorted per distance on the device. */
+int snn_set_background(snn_ctx* ctx, int64_t ncol, const double* tables);
+
+/* ---- a5-a14: getStripe.extract/search_frame/StripeSearch (getStripe.py:790-1114) for the
+ * windows [frame_lo, frame_hi) of one chromosome and ALL maxpixel values at once.
+ * gauss_w = the 2*radius+1 weights of scipy's _gaussian_kernel1d(sigma) (computed by the
+ * host with numpy so they are the bits the reference would use).  Returns candidates before
+ * any RemoveRedundant; if more than `cap` were found returns SNN_ECAP with *n_out = need. */
+int snn_extract(snn_ctx* ctx, int chrom_id, int nq, const double* maxpixel_values,
+                const double* gauss_w, int radius, int minH, int maxW, int bfilter,
+                int gray_variant, int frame_lo, int frame_hi, snn_candidate* out, int64_t cap,
+                int64_t* n_out);
+/* Per-pass intermediates of one window (tests): any pointer may be NULL.
+ * gray/smoothed/mag: float[S*S]; low/edges/vert: uint8[S*S]; nz: int32[400]. */
+int snn_debug_stages(snn_ctx* ctx, int chrom_id, double maxpixel_value, const double* gauss_w,
+                     int radius, int bfilter, int gray_variant, int frame, int bright, int32_t* S,
+                     int32_t* nz, float* gray, float* smoothed, float* mag, uint8_t* low,
+                     uint8_t* edges, uint8_t* vert);
+
+/* ---- a16-a18: getStripe.pvalue (:536-606), scoringstripes (:608-788), getMean (:501-534)
+ * fused: one pass over each stripe's window.  pos = n x 4 int64 {pos1,pos2,pos3,pos4}.
+ * expected = mpmean output of this chromosome (NULL: skip stripiness / O/E outputs).
+ * Any output pointer may be NULL.  p-values need snn_set_background first. */
+int snn_score(snn_ctx* ctx, int chrom_id, int64_t n, const int64_t* pos, const double* expected,
+              double* pvalue, double* stripiness, double* oe_mean, double* oe_total,
+              double* o_mean, double* o_sum);
+
+/* ---- a15: getStripe.RemoveRedundant (:1116-1196) — host code (C++), no device work.
+ * group = chromosome index per row, num = window id, pos = n x 4, h/w = the size columns,
+ * key = pvalue or Stripiness (unused for by = 0).  by: 0 size, 1 pvalue, 2 score.
+ * keep[i] = 1 for surviving rows (original order is kept by the caller). */
+int snn_remove_redundant(int64_t n, const int32_t* group, const int64_t* num, const int64_t* pos,
+                         const double* h, const double* w, const double* key, int by,
+                         uint8_t* keep);
+
+/* ---- measurement: accumulated CUDA-event time per kernel family since the last reset.
+ * names[i] is a static string; returns the number of stages written (<= cap). */
+int snn_stage_times(snn_ctx* ctx, int cap, const char** names, double* ms, int64_t* launches);
+int snn_reset_stage_times(snn_ctx* ctx);
+int snn_enable_stage_timing(snn_ctx* ctx, int on);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,359 @@
+// C ABI entry points (include/stripenn_b200.h): context life cycle, error reporting, stage
+// timers, argument checking.  The numerical work lives in band.cu, quantile.cu,
+// background.cu, image.cu, search.cu and score.cu; dedup.cpp is host-only.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "snn_internal.cuh"
+
+static thread_local std::string g_last_error;
+
+int snn_fail(const snn_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    if (ctx) ctx->err = buf;
+    return code;
+}
+
+int snn_cuda_fail(const snn_ctx* ctx, cudaError_t e, const char* what) {
+    int code = (e == cudaErrorMemoryAllocation) ? SNN_ENOMEM : SNN_ECUDA;
+    return snn_fail(ctx, code, "CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+}
+
+SnnChrom* snn_find_chrom(snn_ctx* ctx, int chrom_id) {
+    auto it = ctx->chroms.find(chrom_id);
+    return it == ctx->chroms.end() ? nullptr : &it->second;
+}
+
+int snn_scratch(snn_ctx* ctx, size_t bytes, void** out) {
+    if (bytes > ctx->scratch_bytes) {
+        if (ctx->scratch) cudaFree(ctx->scratch);
+        ctx->scratch = nullptr;
+        ctx->scratch_bytes = 0;
+        SNN_CUDA(cudaMalloc(&ctx->scratch, bytes));
+        ctx->scratch_bytes = bytes;
+    }
+    *out = ctx->scratch;
+    return SNN_OK;
+}
+
+// ---- timers ------------------------------------------------------------------------------
+static cudaEvent_t take_event(snn_ctx* ctx) {
+    if (!ctx->event_pool.empty()) {
+        cudaEvent_t e = ctx->event_pool.back();
+        ctx->event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+SnnScope::SnnScope(snn_ctx* c, int s, int launches) : ctx(c), stage(s), n(launches) {
+    if (!ctx->timing) return;
+    a = take_event(ctx);
+    b = take_event(ctx);
+    cudaEventRecord(a, ctx->stream);
+}
+
+SnnScope::~SnnScope() {
+    if (!a) return;
+    cudaEventRecord(b, ctx->stream);
+    ctx->timers[stage].pending.push_back({a, b, n});
+}
+
+static void drain_timers(snn_ctx* ctx) {
+    for (int s = 0; s < ST_COUNT; ++s) {
+        SnnTimer& t = ctx->timers[s];
+        for (auto& p : t.pending) {
+            float ms = 0.f;
+            if (cudaEventSynchronize(p.second) == cudaSuccess &&
+                cudaEventElapsedTime(&ms, p.first, p.second) == cudaSuccess) {
+                t.ms += ms;
+                t.launches += p.n;
+            }
+            ctx->event_pool.push_back(p.first);
+            ctx->event_pool.push_back(p.second);
+        }
+        t.pending.clear();
+    }
+}
+
+static const char* kStageNames[ST_COUNT] = {"band_build", "quantile_select", "expected",   "row_flags",
+                                            "background", "background_sort", "frame_prepare", "gray",
+                                            "gaussian",   "sobel_nms",       "search",     "finish",
+                                            "score"};
+
+extern "C" {
+
+int snn_version(void) { return SNN_VERSION; }
+
+const char* snn_last_error(const snn_ctx* ctx) {
+    if (ctx) return ctx->err.c_str();
+    return g_last_error.c_str();
+}
+
+int snn_create(int device, snn_ctx** out) {
+    if (!out) return snn_fail(nullptr, SNN_EINVAL, "snn_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0)
+        return snn_fail(nullptr, SNN_ENODEV,
+                        "snn_create: no CUDA device (%s); stripenn_b200 has no CPU fallback",
+                        e != cudaSuccess ? cudaGetErrorString(e) : "count = 0");
+    if (device < 0 || device >= n)
+        return snn_fail(nullptr, SNN_EINVAL, "snn_create: device %d out of range [0,%d)", device, n);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+        return snn_cuda_fail(nullptr, e, "cudaGetDeviceProperties");
+    if (prop.major != 10)
+        return snn_fail(nullptr, SNN_ENODEV,
+                        "snn_create: device %d is sm_%d%d; this library is built for sm_100a only",
+                        device, prop.major, prop.minor);
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return snn_cuda_fail(nullptr, e, "cudaSetDevice");
+    snn_ctx* ctx = new snn_ctx();
+    ctx->device = device;
+    if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        delete ctx;
+        return snn_cuda_fail(nullptr, e, "cudaStreamCreate");
+    }
+    ctx->stream = ctx->own_stream;
+    *out = ctx;
+    return SNN_OK;
+}
+
+static void free_chrom(SnnChrom& c) {
+    if (c.own_coo) {
+        cudaFree(c.bin1);
+        cudaFree(c.bin2);
+        cudaFree(c.count);
+        cudaFree(c.weight);
+    }
+    cudaFree(c.band);
+}
+
+void snn_destroy(snn_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    drain_timers(ctx);
+    for (auto& kv : ctx->chroms) free_chrom(kv.second);
+    for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
+    cudaFree(ctx->bg_sorted);
+    cudaFree(ctx->bg_valid);
+    cudaFree(ctx->scratch);
+    cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+int snn_set_stream(snn_ctx* ctx, void* s) {
+    if (!ctx) return snn_fail(nullptr, SNN_EINVAL, "ctx is NULL");
+    cudaStreamSynchronize(ctx->stream);
+    ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+    return SNN_OK;
+}
+
+int snn_synchronize(snn_ctx* ctx) {
+    if (!ctx) return snn_fail(nullptr, SNN_EINVAL, "ctx is NULL");
+    SNN_CUDA(cudaSetDevice(ctx->device));
+    SNN_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SNN_OK;
+}
+
+static int load_common(snn_ctx* ctx, int chrom_id, int64_t nbins, int64_t binsize, int64_t chromsize,
+                       int64_t nnz, const int32_t* b1, const int32_t* b2, const int32_t* cnt,
+                       const double* w, int bw, bool device_ptrs) {
+    if (!ctx) return snn_fail(nullptr, SNN_EINVAL, "ctx is NULL");
+    if (nbins <= 0 || binsize <= 0 || chromsize <= 0 || nnz < 0 || bw < 1)
+        return snn_fail(ctx, SNN_EINVAL, "snn_load_chrom: bad sizes (nbins=%lld binsize=%lld nnz=%lld bw=%d)",
+                        (long long)nbins, (long long)binsize, (long long)nnz, bw);
+    if ((chromsize + binsize - 1) / binsize != nbins)
+        return snn_fail(ctx, SNN_EINVAL, "snn_load_chrom: nbins %lld != ceil(%lld / %lld)", (long long)nbins,
+                        (long long)chromsize, (long long)binsize);
+    if (nnz > 0 && (!b1 || !b2 || !cnt)) return snn_fail(ctx, SNN_EINVAL, "snn_load_chrom: NULL pixel arrays");
+    SNN_CUDA(cudaSetDevice(ctx->device));
+    if (snn_find_chrom(ctx, chrom_id)) snn_unload_chrom(ctx, chrom_id);
+    SnnChrom c;
+    c.id = chrom_id;
+    c.nbins = nbins;
+    c.binsize = binsize;
+    c.chromsize = chromsize;
+    c.nnz = nnz;
+    c.bw = (int)(bw < nbins ? bw : nbins);
+    c.own_coo = !device_ptrs;
+    if (device_ptrs) {
+        c.bin1 = const_cast<int32_t*>(b1);
+        c.bin2 = const_cast<int32_t*>(b2);
+        c.count = const_cast<int32_t*>(cnt);
+        c.weight = const_cast<double*>(w);
+    } else {
+        size_t nb = (size_t)(nnz > 0 ? nnz : 1) * sizeof(int32_t);
+        SNN_CUDA(cudaMalloc(&c.bin1, nb));
+        SNN_CUDA(cudaMalloc(&c.bin2, nb));
+        SNN_CUDA(cudaMalloc(&c.count, nb));
+        if (nnz > 0) {
+            SNN_CUDA(cudaMemcpyAsync(c.bin1, b1, nb, cudaMemcpyHostToDevice, ctx->stream));
+            SNN_CUDA(cudaMemcpyAsync(c.bin2, b2, nb, cudaMemcpyHostToDevice, ctx->stream));
+            SNN_CUDA(cudaMemcpyAsync(c.count, cnt, nb, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        if (w) {
+            SNN_CUDA(cudaMalloc(&c.weight, (size_t)nbins * sizeof(double)));
+            SNN_CUDA(cudaMemcpyAsync(c.weight, w, (size_t)nbins * sizeof(double), cudaMemcpyHostToDevice,
+                                     ctx->stream));
+        }
+    }
+    SNN_CUDA(cudaMalloc(&c.band, (size_t)nbins * c.bw * sizeof(double)));
+    int rc = snn_band_build(ctx, &c);
+    if (rc != SNN_OK) {
+        free_chrom(c);
+        return rc;
+    }
+    if (!device_ptrs) SNN_CUDA(cudaStreamSynchronize(ctx->stream));  // host buffers may go away
+    ctx->chroms[chrom_id] = c;
+    return SNN_OK;
+}
+
+int snn_load_chrom(snn_ctx* ctx, int chrom_id, int64_t nbins, int64_t binsize, int64_t chromsize,
+                   int64_t nnz, const int32_t* b1, const int32_t* b2, const int32_t* cnt, const double* w,
+                   int bw) {
+    return load_common(ctx, chrom_id, nbins, binsize, chromsize, nnz, b1, b2, cnt, w, bw, false);
+}
+
+int snn_load_chrom_device(snn_ctx* ctx, int chrom_id, int64_t nbins, int64_t binsize, int64_t chromsize,
+                          int64_t nnz, const int32_t* b1, const int32_t* b2, const int32_t* cnt,
+                          const double* w, int bw) {
+    return load_common(ctx, chrom_id, nbins, binsize, chromsize, nnz, b1, b2, cnt, w, bw, true);
+}
+
+int snn_unload_chrom(snn_ctx* ctx, int chrom_id) {
+    if (!ctx) return snn_fail(nullptr, SNN_EINVAL, "ctx is NULL");
+    SnnChrom* c = snn_find_chrom(ctx, chrom_id);
+    if (!c) return snn_fail(ctx, SNN_ESTATE, "chromosome %d is not loaded", chrom_id);
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    free_chrom(*c);
+    ctx->chroms.erase(chrom_id);
+    return SNN_OK;
+}
+
+#define GET_CHROM(name)                                                                  \
+    if (!ctx) return snn_fail(nullptr, SNN_EINVAL, "ctx is NULL");                       \
+    SnnChrom* name = snn_find_chrom(ctx, chrom_id);                                      \
+    if (!name) return snn_fail(ctx, SNN_ESTATE, "chromosome %d is not loaded", chrom_id); \
+    SNN_CUDA(cudaSetDevice(ctx->device));
+
+int snn_quantiles(snn_ctx* ctx, int chrom_id, int nq, const double* q, double* out) {
+    GET_CHROM(c);
+    if (nq < 1 || nq > 64 || !q || !out) return snn_fail(ctx, SNN_EINVAL, "snn_quantiles: bad arguments");
+    for (int i = 0; i < nq; ++i)
+        if (!(q[i] >= 0.0 && q[i] <= 1.0))
+            return snn_fail(ctx, SNN_EINVAL, "Quantiles must be in the range [0, 1]");
+    return snn_quantiles_impl(ctx, c, nq, q, out);
+}
+
+int snn_expected(snn_ctx* ctx, int chrom_id, double* out) {
+    GET_CHROM(c);
+    if (!out) return snn_fail(ctx, SNN_EINVAL, "snn_expected: out is NULL");
+    return snn_expected_impl(ctx, c, out);
+}
+
+int snn_row_flags(snn_ctx* ctx, int chrom_id, int nunits, const int64_t* geom, uint8_t* avail,
+                  uint8_t* live) {
+    GET_CHROM(c);
+    if (nunits < 0 || (nunits > 0 && !geom) || !avail || !live)
+        return snn_fail(ctx, SNN_EINVAL, "snn_row_flags: bad arguments");
+    return snn_row_flags_impl(ctx, c, nunits, geom, avail, live);
+}
+
+int snn_background(snn_ctx* ctx, int chrom_id, int64_t nsamp, const int32_t* spec, double* out) {
+    GET_CHROM(c);
+    if (nsamp < 0 || (nsamp > 0 && (!spec || !out)))
+        return snn_fail(ctx, SNN_EINVAL, "snn_background: bad arguments");
+    if (nsamp == 0) return SNN_OK;
+    return snn_background_impl(ctx, c, nsamp, spec, out);
+}
+
+int snn_set_background(snn_ctx* ctx, int64_t ncol, const double* tables) {
+    if (!ctx) return snn_fail(nullptr, SNN_EINVAL, "ctx is NULL");
+    if (ncol < 0 || (ncol > 0 && !tables)) return snn_fail(ctx, SNN_EINVAL, "snn_set_background: bad arguments");
+    SNN_CUDA(cudaSetDevice(ctx->device));
+    return snn_set_background_impl(ctx, ncol, tables);
+}
+
+int snn_extract(snn_ctx* ctx, int chrom_id, int nq, const double* mp, const double* gw, int radius,
+                int minH, int maxW, int bfilter, int gray_variant, int frame_lo, int frame_hi,
+                snn_candidate* out, int64_t cap, int64_t* n_out) {
+    GET_CHROM(c);
+    if (nq < 1 || nq > 64 || !mp || !gw || radius < 0 || radius > 32 || bfilter < 1 || bfilter > 15 ||
+        gray_variant < 0 || gray_variant > 2 || !n_out || cap < 0 || (cap > 0 && !out))
+        return snn_fail(ctx, SNN_EINVAL, "snn_extract: bad arguments");
+    int nframes = (int)((c->nbins + 199) / 200);
+    if (frame_lo < 0 || frame_hi > nframes || frame_lo > frame_hi)
+        return snn_fail(ctx, SNN_EINVAL, "snn_extract: frame range [%d,%d) outside [0,%d)", frame_lo,
+                        frame_hi, nframes);
+    if (c->bw < (c->nbins < SNN_SMAX ? c->nbins : SNN_SMAX))
+        return snn_fail(ctx, SNN_ERANGE, "snn_extract: band width %d < %d", c->bw, SNN_SMAX);
+    return snn_extract_impl(ctx, c, nq, mp, gw, radius, minH, maxW, bfilter, gray_variant, frame_lo,
+                            frame_hi, out, cap, n_out);
+}
+
+int snn_debug_stages(snn_ctx* ctx, int chrom_id, double mp, const double* gw, int radius, int bfilter,
+                     int gray_variant, int frame, int bright, int32_t* S, int32_t* nz, float* gray,
+                     float* smoothed, float* mag, uint8_t* low, uint8_t* edges, uint8_t* vert) {
+    GET_CHROM(c);
+    int nframes = (int)((c->nbins + 199) / 200);
+    if (!gw || radius < 0 || radius > 32 || frame < 0 || frame >= nframes || bright < 0 ||
+        bright >= SNN_NBRIGHT || !S || bfilter < 1 || bfilter > 15)
+        return snn_fail(ctx, SNN_EINVAL, "snn_debug_stages: bad arguments");
+    return snn_debug_stages_impl(ctx, c, mp, gw, radius, bfilter, gray_variant, frame, bright, S, nz, gray,
+                                 smoothed, mag, low, edges, vert);
+}
+
+int snn_score(snn_ctx* ctx, int chrom_id, int64_t n, const int64_t* pos, const double* expected,
+              double* pvalue, double* stripiness, double* oe_mean, double* oe_total, double* o_mean,
+              double* o_sum) {
+    GET_CHROM(c);
+    if (n < 0 || (n > 0 && !pos)) return snn_fail(ctx, SNN_EINVAL, "snn_score: bad arguments");
+    if (n == 0) return SNN_OK;
+    if (pvalue && !ctx->bg_sorted)
+        return snn_fail(ctx, SNN_ESTATE, "snn_score: p-values requested before snn_set_background");
+    return snn_score_impl(ctx, c, n, pos, expected, pvalue, stripiness, oe_mean, oe_total, o_mean, o_sum);
+}
+
+int snn_stage_times(snn_ctx* ctx, int cap, const char** names, double* ms, int64_t* launches) {
+    if (!ctx) return snn_fail(nullptr, SNN_EINVAL, "ctx is NULL");
+    cudaSetDevice(ctx->device);
+    drain_timers(ctx);
+    int n = 0;
+    for (int s = 0; s < ST_COUNT && n < cap; ++s, ++n) {
+        if (names) names[n] = kStageNames[s];
+        if (ms) ms[n] = ctx->timers[s].ms;
+        if (launches) launches[n] = ctx->timers[s].launches;
+    }
+    return n;
+}
+
+int snn_reset_stage_times(snn_ctx* ctx) {
+    if (!ctx) return snn_fail(nullptr, SNN_EINVAL, "ctx is NULL");
+    cudaSetDevice(ctx->device);
+    drain_timers(ctx);
+    for (int s = 0; s < ST_COUNT; ++s) {
+        ctx->timers[s].ms = 0;
+        ctx->timers[s].launches = 0;
+    }
+    return SNN_OK;
+}
+
+int snn_enable_stage_timing(snn_ctx* ctx, int on) {
+    if (!ctx) return snn_fail(nullptr, SNN_EINVAL, "ctx is NULL");
+    ctx->timing = on != 0;
+    return SNN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,144 @@
+// Internal declarations shared by the translation units of libstripenn_b200.so.
+// Everything here is device-side plumbing for the C ABI in include/stripenn_b200.h.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/stripenn_b200.h"
+
+#define SNN_SMAX 400  // largest search window (getStripe.py:794-801)
+#define SNN_WPR 13    // 32-bit words per bit-packed window row (13*32 = 416 >= 400)
+
+// ---- stage ids for the CUDA-event timers (snn_stage_times) -------------------------------
+enum SnnStage {
+    ST_BAND = 0,
+    ST_QUANTILE,
+    ST_EXPECTED,
+    ST_FLAGS,
+    ST_BACKGROUND,
+    ST_BGSORT,
+    ST_FRAME,
+    ST_GRAY,
+    ST_GAUSS,
+    ST_NMS,
+    ST_SEARCH,
+    ST_FINISH,
+    ST_SCORE,
+    ST_COUNT
+};
+
+struct SnnChrom {
+    int id = -1;
+    int64_t nbins = 0, binsize = 0, chromsize = 0, nnz = 0;
+    int bw = 0;
+    bool own_coo = true;
+    int32_t* bin1 = nullptr;   // device
+    int32_t* bin2 = nullptr;   // device
+    int32_t* count = nullptr;  // device
+    double* weight = nullptr;  // device or null
+    double* band = nullptr;    // device, nbins * bw
+};
+
+struct SnnPending {
+    cudaEvent_t first, second;
+    int n;
+};
+struct SnnTimer {
+    std::vector<SnnPending> pending;
+    double ms = 0.0;
+    int64_t launches = 0;
+};
+
+struct snn_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
+    std::map<int, SnnChrom> chroms;
+    mutable std::string err;
+    // background tables, sorted per (table, distance): 4 * 400 rows of `bg_ncol` doubles,
+    // NaNs moved to the end; bg_valid[row] = number of non-NaN entries.
+    double* bg_sorted = nullptr;
+    int32_t* bg_valid = nullptr;
+    int64_t bg_ncol = 0;
+    // scratch of snn_extract, grown on demand
+    void* scratch = nullptr;
+    size_t scratch_bytes = 0;
+    // timers
+    bool timing = false;
+    SnnTimer timers[ST_COUNT];
+    std::vector<cudaEvent_t> event_pool;
+};
+
+int snn_fail(const snn_ctx* ctx, int code, const char* fmt, ...);
+int snn_cuda_fail(const snn_ctx* ctx, cudaError_t e, const char* what);
+SnnChrom* snn_find_chrom(snn_ctx* ctx, int chrom_id);
+int snn_scratch(snn_ctx* ctx, size_t bytes, void** out);
+
+#define SNN_CUDA(call)                                                   \
+    do {                                                                 \
+        cudaError_t e__ = (call);                                        \
+        if (e__ != cudaSuccess) return snn_cuda_fail(ctx, e__, #call);   \
+    } while (0)
+
+#define SNN_LAUNCH_CHECK(what)                                             \
+    do {                                                                   \
+        cudaError_t e__ = cudaGetLastError();                              \
+        if (e__ != cudaSuccess) return snn_cuda_fail(ctx, e__, what);      \
+    } while (0)
+
+// RAII stage timer: records two events around the launches issued in its scope.
+struct SnnScope {
+    snn_ctx* ctx;
+    int stage;
+    int n;  // kernel launches issued inside the scope
+    cudaEvent_t a = nullptr, b = nullptr;
+    SnnScope(snn_ctx* c, int s, int launches = 1);
+    ~SnnScope();
+};
+
+// ---- device helpers ---------------------------------------------------------------------
+__device__ __forceinline__ double snn_nan0(double v) { return (v != v) ? 0.0 : v; }
+
+// Symmetric matrix element from the band; (i, j) chromosome-local bins, must satisfy
+// |i - j| < bw (callers guarantee it; out-of-chromosome reads return 0).
+__device__ __forceinline__ double snn_band_at(const double* __restrict__ band, int64_t nbins, int bw,
+                                               int64_t i, int64_t j) {
+    if (i < 0 || j < 0 || i >= nbins || j >= nbins) return 0.0;
+    int64_t lo = i < j ? i : j;
+    int64_t d = i < j ? j - i : i - j;
+    if (d >= bw) return 0.0;
+    return band[lo * bw + d];
+}
+
+// Python slice(a, b) on an axis of length n -> [lo, hi) (hi <= lo means empty).
+__host__ __device__ __forceinline__ void snn_pyslice(int64_t a, int64_t b, int64_t n, int64_t* lo,
+                                                      int64_t* hi) {
+    if (a < 0) { a += n; if (a < 0) a = 0; } else if (a > n) a = n;
+    if (b < 0) { b += n; if (b < 0) b = 0; } else if (b > n) b = n;
+    *lo = a;
+    *hi = b;
+}
+
+// ---- per-TU entry points used by api.cu ---------------------------------------------------
+int snn_band_build(snn_ctx* ctx, SnnChrom* c);
+int snn_quantiles_impl(snn_ctx* ctx, SnnChrom* c, int nq, const double* q, double* out);
+int snn_expected_impl(snn_ctx* ctx, SnnChrom* c, double* out);
+int snn_row_flags_impl(snn_ctx* ctx, SnnChrom* c, int nunits, const int64_t* geom, uint8_t* avail,
+                       uint8_t* live);
+int snn_background_impl(snn_ctx* ctx, SnnChrom* c, int64_t nsamp, const int32_t* spec, double* out);
+int snn_set_background_impl(snn_ctx* ctx, int64_t ncol, const double* tables);
+int snn_extract_impl(snn_ctx* ctx, SnnChrom* c, int nq, const double* mp, const double* gw, int radius,
+                     int minH, int maxW, int bfilter, int gray_variant, int frame_lo, int frame_hi,
+                     snn_candidate* out, int64_t cap, int64_t* n_out);
+int snn_debug_stages_impl(snn_ctx* ctx, SnnChrom* c, double mp, const double* gw, int radius,
+                          int bfilter, int gray_variant, int frame, int bright, int32_t* S, int32_t* nz,
+                          float* gray, float* smoothed, float* mag, uint8_t* low, uint8_t* edges,
+                          uint8_t* vert);
+int snn_score_impl(snn_ctx* ctx, SnnChrom* c, int64_t n, const int64_t* pos, const double* expected,
+                   double* pvalue, double* stripiness, double* oe_mean, double* oe_total,
+                   double* o_mean, double* o_sum);
