@@ -136,8 +136,14 @@ int snn_debug_stages(snn_ctx* ctx, int chrom_id, double maxpixel_value, const do
 /* ---- a16-a18: getStripe.pvalue (:536-606), scoringstripes (:608-788), getMean (:501-534)
  * fused: one pass over each stripe's window.  pos = n x 4 int64 {pos1,pos2,pos3,pos4}.
  * expected = mpmean output of this chromosome (NULL: skip stripiness / O/E outputs).
- * Any output pointer may be NULL.  p-values need snn_set_background first. */
-int snn_score(snn_ctx* ctx, int chrom_id, int64_t n, const int64_t* pos, const double* expected,
+ * stale = NULL or n x 2 int32 {table (0 down / 1 up), distance}: the background row a stripe
+ * that is neither on (x1 == y1) nor under (x2 == y2) the diagonal inherits from the rows
+ * processed before it (the reference's loop variables persist, getStripe.py:583-597); the
+ * host derives it from the table order.  Without it such stripes get NaN.
+ * Rows the reference would crash on (window outside the chromosome, shape mismatch at the
+ * last bin) get NaN.  Any output pointer may be NULL.  p-values need snn_set_background. */
+int snn_score(snn_ctx* ctx, int chrom_id, int64_t n, const int64_t* pos, const int32_t* stale,
+              const double* expected,
               double* pvalue, double* stripiness, double* oe_mean, double* oe_total,
               double* o_mean, double* o_sum);
 

@@ -136,6 +136,7 @@ static void free_chrom(SnnChrom& c) {
         cudaFree(c.weight);
     }
     cudaFree(c.band);
+    cudaFree(c.rowptr);
 }
 
 void snn_destroy(snn_ctx* ctx) {
@@ -315,7 +316,8 @@ int snn_debug_stages(snn_ctx* ctx, int chrom_id, double mp, const double* gw, in
                                  smoothed, mag, low, edges, vert);
 }
 
-int snn_score(snn_ctx* ctx, int chrom_id, int64_t n, const int64_t* pos, const double* expected,
+int snn_score(snn_ctx* ctx, int chrom_id, int64_t n, const int64_t* pos, const int32_t* stale,
+              const double* expected,
               double* pvalue, double* stripiness, double* oe_mean, double* oe_total, double* o_mean,
               double* o_sum) {
     GET_CHROM(c);
@@ -323,7 +325,7 @@ int snn_score(snn_ctx* ctx, int chrom_id, int64_t n, const int64_t* pos, const d
     if (n == 0) return SNN_OK;
     if (pvalue && !ctx->bg_sorted)
         return snn_fail(ctx, SNN_ESTATE, "snn_score: p-values requested before snn_set_background");
-    return snn_score_impl(ctx, c, n, pos, expected, pvalue, stripiness, oe_mean, oe_total, o_mean, o_sum);
+    return snn_score_impl(ctx, c, n, pos, stale, expected, pvalue, stripiness, oe_mean, oe_total, o_mean, o_sum);
 }
 
 int snn_stage_times(snn_ctx* ctx, int cap, const char** names, double* ms, int64_t* launches) {

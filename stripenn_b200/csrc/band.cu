@@ -38,7 +38,48 @@ __global__ void k_band_scatter(double* __restrict__ band, const int32_t* __restr
     }
 }
 
+// CSR row pointers of the (bin1, bin2)-sorted pixel table + sortedness check.
+__global__ void k_rowptr(const int32_t* __restrict__ b1, const int32_t* __restrict__ b2, int64_t nnz,
+                         int64_t nbins, int64_t* __restrict__ rowptr, int* __restrict__ bad) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t <= nnz; t += stride) {
+        int64_t prev = (t > 0) ? b1[t - 1] : -1;
+        int64_t cur = (t < nnz) ? b1[t] : nbins;
+        if (t < nnz) {
+            int64_t c2 = b2[t];
+            if (cur < 0 || cur >= nbins || c2 < cur || c2 >= nbins) *bad = 1;       // upper triangle, in range
+            if (t > 0 && (prev > cur || (prev == cur && b2[t - 1] >= c2))) *bad = 2;  // sorted, unique
+        }
+        if (cur > nbins) cur = nbins;
+        for (int64_t r = prev + 1; r <= cur && r <= nbins; ++r) rowptr[r] = t;
+    }
+}
+
 int snn_band_build(snn_ctx* ctx, SnnChrom* c) {
+    {
+        void* scratch = nullptr;
+        int rc0 = snn_scratch(ctx, 64, &scratch);
+        if (rc0) return rc0;
+        int* d_bad = (int*)scratch;
+        SNN_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream));
+        SNN_CUDA(cudaMalloc(&c->rowptr, (size_t)(c->nbins + 1) * sizeof(int64_t)));
+        int blocks0 = (int)((c->nnz + 256) / 256);
+        if (blocks0 > 148 * 16) blocks0 = 148 * 16;
+        {
+            SnnScope scope(ctx, ST_BAND, 1);
+            k_rowptr<<<blocks0, 256, 0, ctx->stream>>>(c->bin1, c->bin2, c->nnz, c->nbins, c->rowptr, d_bad);
+            SNN_LAUNCH_CHECK("k_rowptr");
+        }
+        int bad = 0;
+        SNN_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost, ctx->stream));
+        SNN_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (bad == 1)
+            return snn_fail(ctx, SNN_EINVAL, "snn_load_chrom: pixels must satisfy 0 <= bin1 <= bin2 < nbins");
+        if (bad == 2)
+            return snn_fail(ctx, SNN_EINVAL,
+                            "snn_load_chrom: pixels must be sorted by (bin1, bin2) without duplicates, like a "
+                            "cooler pixel table");
+    }
     SnnScope scope(ctx, ST_BAND, 2);
     int threads = 256;
     int64_t total = c->nbins * c->bw;

@@ -1,0 +1,405 @@
+// K9: fused scoring of candidate stripes — getStripe.pvalue (getStripe.py:536-606),
+// getStripe.scoringstripes / iterate_idx (:608-788, stats.elementwise_product_sum
+// stats.py:184-199) and getStripe.getMean (:501-534) in one pass over each stripe's window.
+//
+// One CTA (4 warps) per stripe; a warp owns a row of the window and its lanes run along the
+// columns (contiguous in the band for rows above the diagonal), so every window byte is
+// requested once; per-row results live in shared memory, the background rows are pre-sorted
+// (background.cu) so #(bg >= v) is a binary search in L2-resident tables.
+//
+// Roofline: HBM.  Algorithmic bytes per stripe: 8 * h * (w + 2*bs) window bytes + 48 B out;
+// the 12.8 MB background tables are read once per launch (L2-resident afterwards).
+#include "snn_internal.cuh"
+
+#define SCORE_THREADS 128
+#define SCORE_MAXCOLS 512
+
+struct ScoreParams {
+    int64_t binsize, chromsize, nbins;
+    int bs;
+    int hmax;  // shared-memory capacity in rows
+    int64_t bg_ncol;
+};
+
+__device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
+
+// number of entries >= v among the first n (sorted ascending) entries of row
+__device__ __forceinline__ int count_ge(const double* __restrict__ row, int n, double v) {
+    if (v != v) return 0;
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (row[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    return n - lo;
+}
+
+// k-th smallest (0-based) of a[0..n) by rank counting; all threads of the CTA call it and get the
+// same answer through `slot` (shared).
+__device__ double select_kth(const double* a, int n, int k, double* slot) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double v = a[i];
+        int less = 0, leq = 0;
+        for (int j = 0; j < n; ++j) {
+            const double u = a[j];
+            less += (u < v);
+            leq += (u <= v);
+        }
+        if (less <= k && k < leq) *slot = v;  // every writer writes the same value
+    }
+    __syncthreads();
+    return *slot;
+}
+
+__global__ void __launch_bounds__(SCORE_THREADS) k_score(MatView m, const int64_t* __restrict__ pos,
+                                                         const int32_t* __restrict__ stale,
+                                                         const double* __restrict__ expected,
+                                                         const double* __restrict__ bg,
+                                                         const int32_t* __restrict__ bg_valid, ScoreParams P,
+                                                         int want_p, int want_s, double* __restrict__ out) {
+    extern __shared__ double sh[];
+    double* cm = sh;               // centre row means (O/E)         [hmax]
+    double* lm = cm + P.hmax;      // left                            [hmax]
+    double* rm = lm + P.hmax;      // right                           [hmax]
+    double* pv = rm + P.hmax;      // per-row p-values / scratch      [hmax]
+    int* ridx = (int*)(pv + P.hmax);                 // compacted row index [hmax]
+    unsigned char* rdel = (unsigned char*)(ridx + P.hmax);  // row deleted  [hmax]
+    __shared__ double ex[SNN_NDIST];
+    __shared__ unsigned char dead[SCORE_MAXCOLS];
+    __shared__ double slot;
+    __shared__ double red[8];
+    __shared__ int redi[4];
+    __shared__ int bad_flag;
+
+    const int64_t s = blockIdx.x;
+    const int64_t p1 = pos[s * 4 + 0], p2 = pos[s * 4 + 1], p3 = pos[s * 4 + 2], p4 = pos[s * 4 + 3];
+    const int64_t r = P.binsize;
+    const int bs = P.bs;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = SCORE_THREADS / 32;
+    double* o = out + s * 6;
+    if (threadIdx.x == 0) {
+        bad_flag = 0;
+        for (int t = 0; t < 6; ++t) o[t] = qnan();
+    }
+    if (want_s)
+        for (int t = threadIdx.x; t < SNN_NDIST; t += SCORE_THREADS) ex[t] = expected[t];
+    __syncthreads();
+    // cooler region checks (fake/real cooler raise; we answer NaN)
+    if (p1 < 1 || p3 < 1 || p2 < p1 || p4 < p3 || p2 > P.chromsize || p4 > P.chromsize) return;
+    // rows of the window: bins [p3 // r, ceil(p4 / r))
+    const int64_t R0 = p3 / r, R1 = (p4 + r - 1) / r;
+    const int h = (int)(R1 - R0);
+    if (h <= 0 || h > P.hmax) return;
+
+    // ================================ p-value (getStripe.py:552-605) ================================
+    if (want_p) {
+        int64_t lmost = p1 - (int64_t)bs * r;
+        if (lmost < 1) lmost = 1;
+        int64_t rmost = p2 + (int64_t)bs * r;
+        if (rmost > P.chromsize) rmost = P.chromsize;
+        const int64_t C0 = lmost / r, C1 = (rmost + r - 1) / r;
+        const int64_t ncol = C1 - C0;
+        int64_t ca, cb, la, lb, ra, rb;
+        snn_pyslice(bs, -(int64_t)bs, ncol, &ca, &cb);   // mat[:, bs:-bs]
+        snn_pyslice(0, bs, ncol, &la, &lb);              // mat[:, :bs]
+        snn_pyslice(-(int64_t)bs, ncol, ncol, &ra, &rb); // mat[:, -bs:]
+        if (bs == 0) { ra = 0; rb = ncol; }
+        const int64_t x1 = (p1 - 1) / r, x2 = p2 / r, y1 = (p3 - 1) / r, y2 = p4 / r;
+        int mode;  // 0: down tables, row j ; 1: up tables, row y2-y1-j-1 ; 2: stale ; 3: undefined
+        if (x1 == y1) mode = 0;
+        else if (x2 == y2) mode = 1;
+        else if (stale && stale[s * 2] >= 0) mode = 2;
+        else mode = 3;
+        for (int j = warp; j < h; j += nwarp) {
+            const int64_t row = R0 + j;
+            double sc = 0.0, sl = 0.0, sr = 0.0;
+            for (int64_t c = lane; c < ncol; c += 32) {
+                const double v = snn_nan0(snn_mat_at(m, row, C0 + c));
+                if (c >= ca && c < cb) sc += v;
+                if (c >= la && c < lb) sl += v;
+                if (c >= ra && c < rb) sr += v;
+            }
+            for (int off = 16; off > 0; off >>= 1) {
+                sc += __shfl_xor_sync(0xffffffffu, sc, off);
+                sl += __shfl_xor_sync(0xffffffffu, sl, off);
+                sr += __shfl_xor_sync(0xffffffffu, sr, off);
+            }
+            if (lane == 0) {
+                const double mc = (cb > ca) ? sc / (double)(cb - ca) : qnan();
+                const double ml = (lb > la) ? sl / (double)(lb - la) : qnan();
+                const double mr = (rb > ra) ? sr / (double)(rb - ra) : qnan();
+                const double dl = mc - ml, dr = mc - mr;
+                double p = qnan();
+                if (mode != 3) {
+                    int table, d;
+                    if (mode == 0) { table = 1; d = j < 399 ? j : 399; }
+                    else if (mode == 1) {
+                        int64_t dd = y2 - y1 - j - 1;
+                        if (dd > 399) dd = 399;
+                        if (dd < 0) dd += SNN_NDIST;   // numpy negative index
+                        d = (int)dd;
+                        table = 0;
+                    } else { table = stale[s * 2] ? 0 : 1; d = stale[s * 2 + 1]; }
+                    if (d >= 0 && d < SNN_NDIST) {
+                        // table order in memory: 0 bgleft_up, 1 bgright_up, 2 bgleft_down, 3 bgright_down
+                        const int tl = table == 0 ? 0 : 2, tr = table == 0 ? 1 : 3;
+                        const int64_t rl = (int64_t)tl * SNN_NDIST + d, rr = (int64_t)tr * SNN_NDIST + d;
+                        const int nl = bg_valid[rl], nr = bg_valid[rr];
+                        const double a = (double)count_ge(bg + rl * P.bg_ncol, nl, dl) / (double)nl;
+                        const double b = (double)count_ge(bg + rr * P.bg_ncol, nr, dr) / (double)nr;
+                        p = a;                // Python max(a, b)
+                        if (b > p) p = b;
+                        if (p == 0.0) p = 1.0 / (double)P.bg_ncol;
+                    }
+                }
+                pv[j] = p;
+            }
+        }
+        __syncthreads();
+        // np.median: NaN if any NaN, else mean of the middle pair
+        int anynan = 0;
+        for (int j = threadIdx.x; j < h; j += SCORE_THREADS) anynan |= (pv[j] != pv[j]);
+        anynan = __syncthreads_or(anynan);
+        double med;
+        if (anynan) med = qnan();
+        else if (h & 1) med = select_kth(pv, h, h / 2, &slot);
+        else {
+            const double a = select_kth(pv, h, h / 2 - 1, &slot);
+            const double b = select_kth(pv, h, h / 2, &slot);
+            med = (a + b) / 2.0;
+        }
+        if (threadIdx.x == 0) o[0] = med;
+        __syncthreads();
+    }
+    if (!want_s) return;
+
+    // ============================ stripiness (getStripe.py:661-759) ================================
+    const int64_t xsi = p1 / r, xei = p2 / r, ysi = p3 / r, yei = p4 / r;
+    int64_t lmb = xsi - bs, rmb = xei + bs;
+    if (lmb < 1) lmb = 1;
+    if (rmb >= P.nbins) rmb = P.nbins - 1;
+    // fetched column ranges (bins) and the first expected-value column of each part
+    const int64_t cC0 = p1 / r, cC1 = (p2 + r - 1) / r;  // centre: "chr:xs-xe"
+    const int64_t lC0 = lmb, lC1 = xsi;                   // left:   "chr:lm*r - xsi*r"
+    const int64_t rC0 = xei, rC1 = rmb;                   // right:  "chr:xei*r - rm*r"
+    const int wc = (int)(cC1 - cC0), wl = (int)(lC1 - lC0), wr = (int)(rC1 - rC0);
+    // shapes must agree with expecMatrix (else numpy raises in the reference) and the regions
+    // must be valid for cooler (end >= start)
+    if (wc != (int)(xei - xsi) || h != (int)(yei - ysi) || wc <= 0 || wl < 0 || wr < 0 ||
+        wc + wl + wr > SCORE_MAXCOLS || R0 != ysi)
+        return;
+    const int ncols = wc + wl + wr;  // column order: centre | left | right
+    // ---- pass 1: all-NaN columns of the O/E parts (division keeps NaN of the observed value)
+    for (int c = threadIdx.x; c < ncols; c += SCORE_THREADS) {
+        int64_t gc = c < wc ? cC0 + c : (c < wc + wl ? lC0 + (c - wc) : rC0 + (c - wc - wl));
+        bool all = true;
+        for (int j = 0; j < h && all; ++j) {
+            const double v = snn_mat_at(m, R0 + j, gc);
+            if (v == v) all = false;  // observed finite or inf -> O/E not NaN (expected + 1e-8 is finite)
+        }
+        dead[c] = all ? 1 : 0;
+    }
+    for (int j = threadIdx.x; j < h; j += SCORE_THREADS) rdel[j] = 0;
+    __syncthreads();
+    // rows deleted together with dead columns: index x (column index inside its part) when
+    // xs == ys, else shape[0]-1-x  (getStripe.py:713-731); np.delete wraps negatives
+    if (threadIdx.x == 0) {
+        const bool diag = (p1 == p3);
+        for (int part = 0; part < 3; ++part) {
+            const int w0 = part == 0 ? 0 : (part == 1 ? wc : wc + wl);
+            const int wn = part == 0 ? wc : (part == 1 ? wl : wr);
+            for (int x = 0; x < wn; ++x) {
+                if (!dead[w0 + x]) continue;
+                int idx = diag ? x : h - 1 - x;
+                if (idx < 0) idx += h;
+                if (idx < 0 || idx >= h) { bad_flag = 1; continue; }  // IndexError in the reference
+                rdel[idx] = 1;
+            }
+        }
+        int k = 0;
+        for (int j = 0; j < h; ++j)
+            if (!rdel[j]) ridx[k++] = j;
+        redi[0] = k;
+    }
+    __syncthreads();
+    if (bad_flag) return;
+    const int hk = redi[0];
+    int lc = 0, ll = 0, lr = 0;  // live columns per part
+    for (int c = 0; c < ncols; ++c) {
+        if (dead[c]) continue;
+        if (c < wc) ++lc; else if (c < wc + wl) ++ll; else ++lr;
+    }
+    // ---- pass 2: row means of nan0(O/E) over the live columns; observed sums for getMean
+    double tot_oe = 0.0, tot_obs = 0.0;
+    int n_obs = 0;
+    for (int k = warp; k < hk; k += nwarp) {
+        const int j = ridx[k];
+        const int64_t row = R0 + j;
+        double sc = 0.0, sl = 0.0, sr = 0.0;
+        for (int c = lane; c < ncols; c += 32) {
+            if (dead[c]) continue;
+            int64_t gc, ecol;
+            if (c < wc) { gc = cC0 + c; ecol = xsi + c; }
+            else if (c < wc + wl) { gc = lC0 + (c - wc); ecol = lmb + (c - wc); }
+            else { gc = rC0 + (c - wc - wl); ecol = xei + 1 + (c - wc - wl); }  // right: shifted by one
+            int64_t dd = ecol - row;
+            if (dd < 0) dd = -dd;
+            if (dd > 399) dd = 399;
+            const double obs = snn_mat_at(m, row, gc);
+            const double v = snn_nan0(obs / (ex[dd] + .00000001));
+            if (c < wc) sc += v; else if (c < wc + wl) sl += v; else sr += v;
+        }
+        for (int off = 16; off > 0; off >>= 1) {
+            sc += __shfl_xor_sync(0xffffffffu, sc, off);
+            sl += __shfl_xor_sync(0xffffffffu, sl, off);
+            sr += __shfl_xor_sync(0xffffffffu, sr, off);
+        }
+        if (lane == 0) {
+            cm[k] = lc ? sc / (double)lc : qnan();
+            lm[k] = ll ? sl / (double)ll : qnan();
+            rm[k] = lr ? sr / (double)lr : qnan();
+            tot_oe += sc;
+        }
+    }
+    // getMean: nanmean / nansum of the observed centre window (all rows, all columns)
+    for (int j = warp; j < h; j += nwarp) {
+        double so = 0.0;
+        int no = 0;
+        for (int c = lane; c < wc; c += 32) {
+            const double obs = snn_mat_at(m, R0 + j, cC0 + c);
+            if (obs == obs) { so += obs; ++no; }
+        }
+        for (int off = 16; off > 0; off >>= 1) {
+            so += __shfl_xor_sync(0xffffffffu, so, off);
+            no += __shfl_xor_sync(0xffffffffu, no, off);
+        }
+        if (lane == 0) { tot_obs += so; n_obs += no; }
+    }
+    if (lane == 0) { red[warp] = tot_oe; red[4 + warp] = tot_obs; redi[warp] = n_obs; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+        int n = 0;
+        for (int w = 0; w < nwarp; ++w) { a += red[w]; b += red[4 + w]; n += redi[w]; }
+        // centerMean = mean(center[rows_rep]) = sum / (h' * w') ; centerTotal = w' * sum  (quirk :747)
+        o[2] = (hk > 0 && lc > 0) ? a / ((double)hk * (double)lc) : qnan();
+        o[3] = (double)lc * a;
+        o[4] = n ? b / (double)n : qnan();
+        o[5] = b;
+    }
+    __syncthreads();
+    // ---- pass 3: Sobel-like sums (stats.elementwise_product_sum) and the score
+    double acc = 0.0;
+    int nacc = 0;
+    for (int i = 1 + threadIdx.x; i + 1 < hk; i += SCORE_THREADS) {
+        const double l0 = lm[i - 1], l1 = lm[i], l2 = lm[i + 1];
+        const double c0 = cm[i - 1], c1 = cm[i], c2 = cm[i + 1];
+        const double r0 = rm[i - 1], r1 = rm[i], r2 = rm[i + 1];
+        const double gxl = ((-1.0 * l0 + -2.0 * l1) + -1.0 * l2) + ((1.0 * c0 + 2.0 * c1) + 1.0 * c2);
+        const double gxr = ((1.0 * c0 + 2.0 * c1) + 1.0 * c2) + ((-1.0 * r0 + -2.0 * r1) + -1.0 * r2);
+        double gy = (((1.0 * l0 + 0.0 * l1) + -1.0 * l2) + ((2.0 * c0 + 0.0 * c1) + -2.0 * c2)) +
+                    ((1.0 * r0 + 0.0 * r1) + -1.0 * r2);
+        if (gy < 0) gy *= -1.0;
+        const double gx = (gxl != gxl || gxr != gxr) ? qnan() : fmin(gxl, gxr);  // np.minimum propagates NaN
+        const double d = gx - gy;
+        if (d == d) { acc += d; ++nacc; }
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        nacc += __shfl_xor_sync(0xffffffffu, nacc, off);
+    }
+    __syncthreads();
+    if (lane == 0) { red[warp] = acc; redi[warp] = nacc; }
+    __syncthreads();
+    double avgdiff;
+    {
+        double a = 0.0;
+        int n = 0;
+        for (int w = 0; w < nwarp; ++w) { a += red[w]; n += redi[w]; }
+        avgdiff = n ? a / (double)n : qnan();
+    }
+    // nanmedian(centerm): compact the non-NaN values into pv
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int n = 0;
+        for (int k = 0; k < hk; ++k)
+            if (cm[k] == cm[k]) pv[n++] = cm[k];
+        redi[0] = n;
+    }
+    __syncthreads();
+    const int nm = redi[0];
+    double med;
+    if (nm == 0) med = qnan();
+    else if (nm & 1) med = select_kth(pv, nm, nm / 2, &slot);
+    else {
+        const double a = select_kth(pv, nm, nm / 2 - 1, &slot);
+        const double b = select_kth(pv, nm, nm / 2, &slot);
+        med = (a + b) / 2.0;
+    }
+    if (threadIdx.x == 0) o[1] = med * avgdiff;
+}
+
+int snn_score_impl(snn_ctx* ctx, SnnChrom* c, int64_t n, const int64_t* pos, const int32_t* stale,
+                   const double* expected, double* pvalue, double* stripiness, double* oe_mean, double* oe_total,
+                   double* o_mean, double* o_sum) {
+    const int want_p = pvalue != nullptr;
+    const int want_s = expected != nullptr && (stripiness || oe_mean || oe_total || o_mean || o_sum);
+    if (!want_p && !want_s) return SNN_OK;
+    // shared-memory rows needed: the tallest stripe of the batch
+    int64_t hmax = 1;
+    for (int64_t i = 0; i < n; ++i) {
+        int64_t p3 = pos[i * 4 + 2], p4 = pos[i * 4 + 3];
+        if (p3 < 1 || p4 < p3 || p4 > c->chromsize) continue;
+        int64_t h = (p4 + c->binsize - 1) / c->binsize - p3 / c->binsize;
+        if (h > hmax) hmax = h;
+    }
+    hmax = (hmax + 31) & ~(int64_t)31;
+    const size_t per_row = 4 * sizeof(double) + sizeof(int) + 1;
+    if (hmax * per_row > 200 * 1024) hmax = (200 * 1024 / per_row) & ~(size_t)31;  // taller stripes -> NaN
+    const size_t smem = (size_t)hmax * per_row + 64;
+    SNN_CUDA(cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+
+    size_t pbytes = ((size_t)n * 4 * sizeof(int64_t) + 255) & ~(size_t)255;
+    size_t sbytes = stale ? (((size_t)n * 2 * sizeof(int32_t) + 255) & ~(size_t)255) : 0;
+    size_t ebytes = 4096;
+    size_t obytes = (size_t)n * 6 * sizeof(double);
+    void* scratch = nullptr;
+    int rc = snn_scratch(ctx, pbytes + sbytes + ebytes + obytes, &scratch);
+    if (rc) return rc;
+    char* b = (char*)scratch;
+    int64_t* dpos = (int64_t*)b;
+    int32_t* dstale = stale ? (int32_t*)(b + pbytes) : nullptr;
+    double* dex = (double*)(b + pbytes + sbytes);
+    double* dout = (double*)(b + pbytes + sbytes + ebytes);
+    SNN_CUDA(cudaMemcpyAsync(dpos, pos, (size_t)n * 4 * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    if (stale)
+        SNN_CUDA(cudaMemcpyAsync(dstale, stale, (size_t)n * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    if (want_s)
+        SNN_CUDA(cudaMemcpyAsync(dex, expected, SNN_NDIST * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    ScoreParams P;
+    P.binsize = c->binsize;
+    P.chromsize = c->chromsize;
+    P.nbins = c->nbins;
+    P.bs = (int)(50000.0 / (double)c->binsize);
+    P.hmax = (int)hmax;
+    P.bg_ncol = ctx->bg_ncol;
+    {
+        SnnScope scope(ctx, ST_SCORE, 1);
+        k_score<<<(unsigned)n, SCORE_THREADS, smem, ctx->stream>>>(snn_view(c), dpos, dstale, dex, ctx->bg_sorted,
+                                                                   ctx->bg_valid, P, want_p, want_s, dout);
+        SNN_LAUNCH_CHECK("k_score");
+    }
+    std::vector<double> host((size_t)n * 6);
+    SNN_CUDA(cudaMemcpyAsync(host.data(), dout, obytes, cudaMemcpyDeviceToHost, ctx->stream));
+    SNN_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int64_t i = 0; i < n; ++i) {
+        if (pvalue) pvalue[i] = host[i * 6 + 0];
+        if (stripiness) stripiness[i] = host[i * 6 + 1];
+        if (oe_mean) oe_mean[i] = host[i * 6 + 2];
+        if (oe_total) oe_total[i] = host[i * 6 + 3];
+        if (o_mean) o_mean[i] = host[i * 6 + 4];
+        if (o_sum) o_sum[i] = host[i * 6 + 5];
+    }
+    return SNN_OK;
+}

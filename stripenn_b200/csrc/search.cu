@@ -1,0 +1,679 @@
+// Hysteresis, verticalLine, block scan, segment refinement, grouping, pairing and candidate
+// emission of getStripe.StripeSearch, one CTA per brightness pass with
+// the whole 400 x 400 window held as bit masks in shared memory (4 masks x 20.8 KB):
+//   E  edges  : low mask -> after hysteresis the Canny edge map (skimage canny, ndi.label)
+//   C  current: high mask, grown to the connected components of E that contain a high pixel
+//   V  vert   : ImageProcessing.verticalLine(edges, 60, 120)            (ImageProcessing.py:61-83)
+//   T  testmat: painted candidate segments, refined per row               (getStripe.py:945-978)
+// All of this is integer / bit work; the only floating point is the count-weighted mean
+// column of the grouping step (float64, sequential, round-half-even).
+#include <string.h>
+
+#include <algorithm>
+
+#include "image.cuh"
+
+#define NTHR 416
+
+__device__ __forceinline__ int getbit(const uint32_t* M, int S, int r, int c) {
+    if (r < 0 || c < 0 || r >= S || c >= S) return 0;
+    return (M[r * SNN_WPR + (c >> 5)] >> (c & 31)) & 1;
+}
+
+// bits [s, e) of a 13-word row: apply dst = (dst & ~mask) | (src & mask)
+__device__ __forceinline__ void row_assign(uint32_t* dst, const uint32_t* src, int s, int e) {
+    if (e <= s) return;
+    for (int w = s >> 5; w <= (e - 1) >> 5; ++w) {
+        int lo = max(s, w * 32) - w * 32, hi = min(e, w * 32 + 32) - w * 32;  // [lo, hi) within the word
+        uint32_t mask = (hi == 32 ? 0xffffffffu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
+        uint32_t sv = src ? src[w] : 0u;
+        dst[w] = (dst[w] & ~mask) | (sv & mask);
+    }
+}
+
+__device__ __forceinline__ bool row_any(const uint32_t* row, int s, int e) {  // any bit in [s, e)
+    if (e <= s) return false;
+    for (int w = s >> 5; w <= (e - 1) >> 5; ++w) {
+        int lo = max(s, w * 32) - w * 32, hi = min(e, w * 32 + 32) - w * 32;
+        uint32_t mask = (hi == 32 ? 0xffffffffu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
+        if (row[w] & mask) return true;
+    }
+    return false;
+}
+
+// next set bit at position >= p in a 13-word row, or -1
+__device__ __forceinline__ int next_set(const uint32_t* row, int p, int S) {
+    while (p < S) {
+        uint32_t w = row[p >> 5] >> (p & 31);
+        if (w) {
+            int r = p + __ffs(w) - 1;
+            return r < S ? r : -1;
+        }
+        p = (p | 31) + 1;
+    }
+    return -1;
+}
+
+// next clear bit at position >= p (returns S if none below S)
+__device__ __forceinline__ int next_clear(const uint32_t* row, int p, int S) {
+    while (p < S) {
+        uint32_t w = (~row[p >> 5]) >> (p & 31);
+        if (w) {
+            int r = p + __ffs(w) - 1;
+            return r < S ? r : S;
+        }
+        p = (p | 31) + 1;
+    }
+    return S;
+}
+
+struct SearchParams {
+    int nq, minH, maxW;
+    int raw_cap;
+};
+
+__global__ void __launch_bounds__(NTHR) k_search(const uint32_t* __restrict__ low_all,
+                                                 const uint32_t* __restrict__ high_all,
+                                                 const FrameInfo* __restrict__ info, SearchParams P,
+                                                 int* __restrict__ counter, RawCand* __restrict__ raw,
+                                                 uint32_t* __restrict__ dbg_edges, uint32_t* __restrict__ dbg_vert) {
+    extern __shared__ uint32_t smem[];
+    uint32_t* E = smem;
+    uint32_t* C = E + SNN_SMAX * SNN_WPR;
+    uint32_t* V = C + SNN_SMAX * SNN_WPR;
+    uint32_t* T = V + SNN_SMAX * SNN_WPR;
+    __shared__ uint32_t colV[SNN_WPR], colT[SNN_WPR];
+    __shared__ short cEnd[SNN_SMAX];
+    __shared__ unsigned char cUd[SNN_SMAX];
+    __shared__ short cnt[SNN_SMAX];
+    __shared__ int X[SNN_SMAX + 8];
+    __shared__ int nX;
+    __shared__ int rmin, rmax;
+    __shared__ RawCand pend[SNN_SMAX];
+    __shared__ int npend;
+    __shared__ int base_sh;
+
+    const int pass = blockIdx.x;
+    const int S = info[pass / (P.nq * SNN_NBRIGHT)].S;
+    if (S == 0) return;
+    const int tid = threadIdx.x;
+    const uint32_t* low = low_all + (int64_t)pass * SNN_SMAX * SNN_WPR;
+    const uint32_t* high = high_all + (int64_t)pass * SNN_SMAX * SNN_WPR;
+    for (int t = tid; t < S * SNN_WPR; t += NTHR) {
+        E[t] = low[t];
+        C[t] = high[t];
+    }
+    if (tid < SNN_WPR) colV[tid] = 0;
+    if (tid == 0) npend = 0;
+    __syncthreads();
+
+    // ---- hysteresis: grow C inside E to the fixed point (8-connectivity).  Per iteration a
+    // thread owns one row: 3x3 dilation from the rows above/below, then a full horizontal
+    // flood inside the row (Kogge-Stone fill with carries across the 13 words).
+    {
+        const int r = tid;
+        for (;;) {
+            bool changed = false;
+            uint32_t nw[SNN_WPR];
+            if (r < S) {
+                const uint32_t* cu = (r > 0) ? C + (r - 1) * SNN_WPR : nullptr;
+                const uint32_t* cc = C + r * SNN_WPR;
+                const uint32_t* cd = (r < S - 1) ? C + (r + 1) * SNN_WPR : nullptr;
+                const uint32_t* er = E + r * SNN_WPR;
+                uint32_t v[SNN_WPR];
+#pragma unroll
+                for (int w = 0; w < SNN_WPR; ++w) v[w] = cc[w] | (cu ? cu[w] : 0u) | (cd ? cd[w] : 0u);
+#pragma unroll
+                for (int w = 0; w < SNN_WPR; ++w) {
+                    uint32_t sp = v[w] | (v[w] << 1) | (v[w] >> 1);
+                    if (w > 0) sp |= v[w - 1] >> 31;
+                    if (w < SNN_WPR - 1) sp |= v[w + 1] << 31;
+                    nw[w] = (sp & er[w]) | cc[w];
+                }
+                // flood towards higher bits
+                uint32_t carry = 0;
+#pragma unroll
+                for (int w = 0; w < SNN_WPR; ++w) {
+                    uint32_t m = er[w];
+                    uint32_t g = nw[w] | (carry & m);
+                    uint32_t p = m;
+                    g |= p & (g << 1); p &= p << 1;
+                    g |= p & (g << 2); p &= p << 2;
+                    g |= p & (g << 4); p &= p << 4;
+                    g |= p & (g << 8); p &= p << 8;
+                    g |= p & (g << 16);
+                    nw[w] = g;
+                    carry = g >> 31;
+                }
+                // flood towards lower bits
+                carry = 0;
+#pragma unroll
+                for (int w = SNN_WPR - 1; w >= 0; --w) {
+                    uint32_t m = er[w];
+                    uint32_t g = nw[w] | ((carry << 31) & m);
+                    uint32_t p = m;
+                    g |= p & (g >> 1); p &= p >> 1;
+                    g |= p & (g >> 2); p &= p >> 2;
+                    g |= p & (g >> 4); p &= p >> 4;
+                    g |= p & (g >> 8); p &= p >> 8;
+                    g |= p & (g >> 16);
+                    nw[w] = g;
+                    carry = g & 1u;
+                }
+#pragma unroll
+                for (int w = 0; w < SNN_WPR; ++w) changed |= (nw[w] != cc[w]);
+            }
+            __syncthreads();  // all reads of C done
+            if (r < S && changed) {
+#pragma unroll
+                for (int w = 0; w < SNN_WPR; ++w) C[r * SNN_WPR + w] = nw[w];
+            }
+            if (!__syncthreads_or(changed)) break;
+        }
+    }
+    // E := edges
+    for (int t = tid; t < S * SNN_WPR; t += NTHR) E[t] = C[t];
+    __syncthreads();
+    if (dbg_edges)
+        for (int t = tid; t < S * SNN_WPR; t += NTHR) dbg_edges[(int64_t)pass * SNN_SMAX * SNN_WPR + t] = E[t];
+
+    // ---- verticalLine: hit(x, y) = Fx > 0 && 3 Fy^2 < Fx^2 ; vert[x][y-1] = hit[x][y].
+    // vert[r][c] can only be set where column c has an edge pixel in rows r-1..r+1.
+    if (tid < S) {
+        const int r = tid;
+        uint32_t any = 0;
+        for (int w = 0; w < SNN_WPR; ++w) {
+            uint32_t d = E[r * SNN_WPR + w];
+            if (r > 0) d |= E[(r - 1) * SNN_WPR + w];
+            if (r < S - 1) d |= E[(r + 1) * SNN_WPR + w];
+            uint32_t out = 0;
+            while (d) {
+                int bit = __ffs(d) - 1;
+                d &= d - 1;
+                int c = w * 32 + bit;
+                if (c > S - 2) continue;
+                // y = c + 1 ; columns y-1 = c, y, y+1 = c + 2
+                int a0 = getbit(E, S, r - 1, c), a1 = getbit(E, S, r - 1, c + 1), a2 = getbit(E, S, r - 1, c + 2);
+                int b0 = getbit(E, S, r, c), b2 = getbit(E, S, r, c + 2);
+                int c0 = getbit(E, S, r + 1, c), c1 = getbit(E, S, r + 1, c + 1), c2 = getbit(E, S, r + 1, c + 2);
+                int fx = (a0 + 2 * b0 + c0) - (a2 + 2 * b2 + c2);
+                int fy = (c0 + 2 * c1 + c2) - (a0 + 2 * a1 + a2);
+                if (fx > 0 && 3 * fy * fy < fx * fx) out |= 1u << bit;
+            }
+            V[r * SNN_WPR + w] = out;
+            any |= out;
+            if (out) atomicOr(&colV[w], out);
+        }
+    }
+    __syncthreads();
+    if (dbg_vert)
+        for (int t = tid; t < S * SNN_WPR; t += NTHR) dbg_vert[(int64_t)pass * SNN_SMAX * SNN_WPR + t] = V[t];
+
+    // ---- block(vert, c) for every column + candidate test (ImageProcessing.py:100-195,
+    // getStripe.py:924-940)
+    if (tid < S) {
+        const int c = tid;
+        int best = 0, end = 0;
+        // does any of the columns c-1, c, c+1 hold a one at all?
+        bool some = false;
+        for (int cc = max(c - 1, 0); cc <= min(c + 1, S - 1); ++cc) some |= (colV[cc >> 5] >> (cc & 31)) & 1;
+        if (some) {
+            int count = 0, buf = 0, last = 0;
+            for (int i = 0; i < S; ++i) {
+                int one = getbit(V, S, i, c - 1) | getbit(V, S, i, c) | getbit(V, S, i, c + 1);
+                if (one) {
+                    ++count;
+                    last = i;
+                } else if (buf < 5) {
+                    ++buf;
+                } else {
+                    if (count > best) { best = count; end = last; }
+                    count = 0;
+                    buf = 0;
+                }
+            }
+            if (count > best) { best = count; end = last; }
+        }
+        if (end < c) end = end - best + 1;
+        int ud = 0;
+        if (best > P.minH) {
+            int lo = min(c, end), hi = max(c, end);
+            bool has = false;
+            for (int i = max(lo, 0); i <= hi && i < S; ++i)
+                if (getbit(V, S, i, c)) { has = true; break; }
+            if (has) ud = (end > c) ? 2 : 1;
+        }
+        cEnd[c] = (short)end;
+        cUd[c] = (unsigned char)ud;
+    }
+    __syncthreads();
+
+    for (int ud = 1; ud <= 2; ++ud) {
+        for (int t = tid; t < S * SNN_WPR; t += NTHR) T[t] = 0;
+        if (tid < SNN_WPR) colT[tid] = 0;
+        if (tid == 0) nX = 0;
+        __syncthreads();
+        // paint the candidate segments (half-open row ranges)
+        if (tid < S && cUd[tid] == ud) {
+            const int c = tid, e = cEnd[c];
+            int st = (ud == 1) ? e : c, en = (ud == 1) ? c : e;
+            if (st < 0) st = 0;
+            for (int r = st; r < en; ++r) atomicOr(&T[r * SNN_WPR + (c >> 5)], 1u << (c & 31));
+        }
+        __syncthreads();
+        // per-row refinement of every horizontal run of ones (getStripe.py:957-978)
+        if (tid < S) {
+            const int r = tid;
+            uint32_t* tr = T + r * SNN_WPR;
+            uint32_t orig[SNN_WPR];
+            uint32_t anyrow = 0;
+            for (int w = 0; w < SNN_WPR; ++w) { orig[w] = tr[w]; anyrow |= orig[w]; }
+            if (anyrow) {
+                int p = 0;
+                for (;;) {
+                    int s = next_set(orig, p, S);
+                    if (s < 0) break;
+                    int e = next_clear(orig, s, S) - 1;  // inclusive end of the run
+                    if (row_any(E + r * SNN_WPR, s, e + 1)) {
+                        row_assign(tr, V + r * SNN_WPR, s, e);  // testmat[r, s:e] = vert[r, s:e]
+                    } else {
+                        row_assign(tr, nullptr, s, e);          // testmat[r, s:e] = 0
+                        int sum = s + e;
+                        int med = sum >> 1;
+                        if ((sum & 1) && (med & 1)) med += 1;   // np.round((s+e)/2): half to even
+                        tr[med >> 5] |= 1u << (med & 31);
+                    }
+                    p = e + 1;
+                }
+                for (int w = 0; w < SNN_WPR; ++w)
+                    if (tr[w]) atomicOr(&colT[w], tr[w]);
+            }
+        }
+        __syncthreads();
+        // ones per column
+        if (tid < S) {
+            const int c = tid;
+            int n = 0;
+            if ((colT[c >> 5] >> (c & 31)) & 1) {
+                const int w = c >> 5, b = c & 31;
+                for (int r = 0; r < S; ++r) n += (T[r * SNN_WPR + w] >> b) & 1;
+            }
+            cnt[c] = (short)n;
+        }
+        __syncthreads();
+        // grouping state machine (getStripe.py:996-1030), sequential
+        if (tid == 0) {
+            int n = 0;
+            // columns with >= 3 ones, ascending; walk consecutive pairs
+            int prev = -1, prevlen = 0;
+            bool open_ = false;
+            bool have_ln = false;
+            double tot = 0.0;   // running description of the open group: we keep the lists
+            int gcol[SNN_SMAX];
+            int glen[SNN_SMAX];
+            int gn = 0;
+            bool unit_len = false;  // the single-column case stores ln = [1.0]
+            int nx = 0;
+            auto flush = [&](void) {
+                // fr = [a / tot] ; round(sum(c * fr))  in float64, sequential, half-even
+                double total = 0.0;
+                if (unit_len) total = 1.0;
+                else {
+                    long long ti = 0;
+                    for (int k = 0; k < gn; ++k) ti += glen[k];
+                    total = (double)ti;
+                }
+                double acc = 0.0;
+                for (int k = 0; k < gn; ++k) {
+                    double fr = (unit_len ? 1.0 : (double)glen[k]) / total;
+                    double term = (double)gcol[k] * fr;
+                    acc = (k == 0) ? term : acc + term;
+                }
+                double rv = rint(acc);
+                X[nx++] = (int)rv;
+            };
+            (void)tot;
+            for (int c = 0; c < S; ++c) {
+                if (cnt[c] < 3) continue;
+                ++n;
+                if (prev >= 0) {
+                    // one step of the loop `for k in range(n-1)` with cur = prev, nxt = c
+                    const bool adjacent = (c - prev) == 1;
+                    if (adjacent && open_) {
+                        gcol[gn] = c; glen[gn] = cnt[c]; ++gn;
+                    } else if (adjacent) {
+                        gcol[0] = prev; glen[0] = prevlen; gcol[1] = c; glen[1] = cnt[c]; gn = 2;
+                        unit_len = false; open_ = true; have_ln = true;
+                    } else if (!open_) {
+                        gcol[0] = prev; glen[0] = 1; gn = 1; unit_len = true; have_ln = true;
+                        flush();
+                    } else {
+                        flush();
+                        gcol[0] = prev; glen[0] = prevlen; gn = 1; unit_len = false; open_ = false;
+                        have_ln = true;
+                    }
+                }
+                prev = c;
+                prevlen = cnt[c];
+            }
+            if (!have_ln) X[nx++] = 0;
+            else flush();
+            // sorted(set(...))
+            for (int a = 1; a < nx; ++a) {
+                int v = X[a], b = a - 1;
+                while (b >= 0 && X[b] > v) { X[b + 1] = X[b]; --b; }
+                X[b + 1] = v;
+            }
+            int u = 0;
+            for (int a = 0; a < nx; ++a)
+                if (a == 0 || X[a] != X[u - 1]) X[u++] = X[a];
+            nX = u;
+        }
+        __syncthreads();
+        // pairing (getStripe.py:1034-1078)
+        const int nx = nX;
+        int kout = 0;
+        for (int k = 0; k + 1 < nx; ++k) {
+            const int n = X[k], m = X[k + 1];
+            const int gap = m - n;
+            if (!(gap > 1 && gap <= P.maxW)) continue;  // uniform across the CTA
+            if (tid == 0) { rmin = 1 << 30; rmax = -1; }
+            __syncthreads();
+            if (tid < S) {
+                const uint32_t* tr = T + tid * SNN_WPR;
+                bool hit = row_any(tr, max(0, n - 1), min(n + 2, S)) || row_any(tr, max(0, m - 1), min(m + 2, S));
+                if (hit) { atomicMin(&rmin, tid); atomicMax(&rmax, tid); }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                const int right = (gap > 4) ? m - 2 : m;
+                int lo = rmin, hi = rmax;
+                if (ud == 1) hi = right; else lo = n;
+                if (npend < SNN_SMAX) {
+                    RawCand rc;
+                    rc.pass = pass; rc.ud = ud; rc.k = kout;
+                    rc.x = n; rc.y = lo; rc.right = right; rc.hi = hi;
+                    pend[npend++] = rc;
+                }
+            }
+            ++kout;
+            __syncthreads();
+        }
+        __syncthreads();
+    }
+    // ---- flush the candidates of this pass
+    if (tid == 0) base_sh = npend ? atomicAdd(&counter[0], npend) : 0;
+    __syncthreads();
+    const int base = base_sh;
+    for (int t = tid; t < npend; t += NTHR) {
+        if (base + t < P.raw_cap) raw[base + t] = pend[t];
+        else counter[1] = 1;
+    }
+}
+
+// ---- finish: bp coordinates and the window sum of each candidate (getStripe.py:1087-1095) --------
+__global__ void k_finish(const RawCand* __restrict__ raw, int n, const FrameInfo* __restrict__ info,
+                         const int32_t* __restrict__ nz_all, const double* __restrict__ Dc_all, int nq,
+                         int64_t binsize, int64_t chromsize, snn_candidate* __restrict__ out) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n) return;
+    const RawCand rc = raw[warp];
+    const int f = rc.pass / (nq * SNN_NBRIGHT);
+    const FrameInfo fi = info[f];
+    const int32_t* nz = nz_all + (int64_t)f * SNN_SMAX;
+    const double* Dc = Dc_all + (int64_t)f * SNN_SMAX * SNN_SMAX;
+    const int w = rc.right - rc.x + 1, h = rc.hi - rc.y + 1;
+    double s = 0.0;
+    if (h > 0 && w > 0) {
+        for (int t = lane; t < h * w; t += 32) {
+            int r = rc.y + t / w, c = rc.x + t % w;
+            if (r >= 0 && r < fi.S && c >= 0 && c < fi.S) s += Dc[r * SNN_SMAX + c];
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+        snn_candidate c;
+        c.q = (rc.pass / SNN_NBRIGHT) % nq;
+        c.frame = fi.idx;
+        c.bright = rc.pass % SNN_NBRIGHT;
+        c.ud = rc.ud;
+        c.k = rc.k;
+        c.x = rc.x; c.y = rc.y; c.w = w; c.h = h;
+        c.start = fi.start; c.end = fi.end; c.S = fi.S;
+        auto sa = [&](int i) -> int64_t {  // start_array[i]
+            int ii = min(max(i, 0), fi.S - 1);
+            return ((int64_t)fi.start + nz[ii]) * binsize + 1;
+        };
+        auto ea = [&](int i) -> int64_t {  // end_array[i]; only the window's last bin is clipped
+            int ii = min(max(i, 0), fi.S - 1);
+            int64_t g = (int64_t)fi.start + nz[ii];
+            int64_t e = (g + 1) * binsize;
+            if (g == fi.end && e >= chromsize) e = chromsize;
+            return e;
+        };
+        c.pos1 = sa(rc.x);
+        c.pos2 = ea(rc.right);
+        c.pos3 = sa(rc.y);
+        c.pos4 = ea(rc.hi);
+        c.total = s;
+        out[warp] = c;
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------
+static size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
+
+static int make_plan(snn_ctx* ctx, ExtractPlan* pl, int nq, const double* mp, const double* gw, int radius,
+                     int minH, int maxW, int bfilter, int variant, int fb, bool dbg, uint32_t** dbgE,
+                     uint32_t** dbgV, float** dbgM) {
+    pl->nq = nq;
+    pl->minH = minH;
+    pl->maxW = maxW;
+    pl->fb = fb;
+    GrayParams& g = pl->gray;
+    g.nq = nq;
+    g.bf = bfilter;
+    g.variant = variant;
+    // np.ones((bf,bf)) / (bf*bf)
+    g.kv = 1.0 / (double)(bfilter * bfilter);
+    {   // what the constant red channel becomes: sequential sum of bf*bf taps, clip, float32
+        volatile double s = 0.0;
+        for (int t = 0; t < bfilter * bfilter; ++t) {
+            volatile double term = g.kv * 1.0;
+            s = s + term;
+        }
+        double cl = s < 0.0 ? 0.0 : (s > 1.0 ? 1.0 : s);
+        g.r32 = (float)cl;
+    }
+    {   // np.arange(0.5, 1.01, 0.1): start + i * delta with delta = (start + step) - start
+        volatile double first = 0.5, second = 0.5 + 0.1;
+        volatile double delta = second - first;
+        for (int i = 0; i < SNN_NBRIGHT; ++i) {
+            volatile double t = (double)i * delta;
+            g.bright[i] = first + t;
+        }
+    }
+    for (int i = 0; i < nq; ++i) g.mp[i] = mp[i];
+    pl->gauss.radius = radius;
+    for (int i = 0; i <= radius; ++i) pl->gauss.w[i] = gw[i];
+
+    const size_t npass = (size_t)fb * nq * SNN_NBRIGHT;
+    const size_t img = (size_t)SNN_SMAX * SNN_SMAX;
+    pl->raw_cap = (int)std::min<size_t>(npass * 24 + 4096, (size_t)16 << 20);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
+    size_t o_info = take(fb * sizeof(FrameInfo));
+    size_t o_nz = take((size_t)fb * SNN_SMAX * sizeof(int32_t));
+    size_t o_Dc = take((size_t)fb * img * sizeof(double));
+    size_t o_bleed = take((size_t)fb * img * sizeof(float));
+    size_t o_A = take(npass * img * sizeof(float));
+    size_t o_B = take(npass * img * sizeof(float));
+    size_t o_C = take(npass * img * sizeof(float));
+    size_t o_low = take(npass * SNN_SMAX * SNN_WPR * sizeof(uint32_t));
+    size_t o_high = take(npass * SNN_SMAX * SNN_WPR * sizeof(uint32_t));
+    size_t o_cnt = take(64);
+    size_t o_raw = take((size_t)pl->raw_cap * sizeof(RawCand));
+    size_t o_cand = take((size_t)pl->raw_cap * sizeof(snn_candidate));
+    size_t o_dE = 0, o_dV = 0, o_dM = 0;
+    if (dbg) {
+        o_dE = take(npass * SNN_SMAX * SNN_WPR * sizeof(uint32_t));
+        o_dV = take(npass * SNN_SMAX * SNN_WPR * sizeof(uint32_t));
+        o_dM = take(npass * img * sizeof(float));
+    }
+    void* base = nullptr;
+    int rc = snn_scratch(ctx, off, &base);
+    if (rc) return rc;
+    char* b = (char*)base;
+    pl->info = (FrameInfo*)(b + o_info);
+    pl->nz = (int32_t*)(b + o_nz);
+    pl->Dc = (double*)(b + o_Dc);
+    pl->bleed = (float*)(b + o_bleed);
+    pl->bufA = (float*)(b + o_A);
+    pl->bufB = (float*)(b + o_B);
+    pl->bufC = (float*)(b + o_C);
+    pl->low = (uint32_t*)(b + o_low);
+    pl->high = (uint32_t*)(b + o_high);
+    pl->counter = (int*)(b + o_cnt);
+    pl->raw = (RawCand*)(b + o_raw);
+    pl->cand = (snn_candidate*)(b + o_cand);
+    if (dbg) {
+        *dbgE = (uint32_t*)(b + o_dE);
+        *dbgV = (uint32_t*)(b + o_dV);
+        *dbgM = (float*)(b + o_dM);
+    }
+    return SNN_OK;
+}
+
+static const size_t kSearchSmem = 4 * (size_t)SNN_SMAX * SNN_WPR * sizeof(uint32_t);
+
+static int run_batch(snn_ctx* ctx, SnnChrom* c, const ExtractPlan& pl, int frame0, int nf, uint32_t* dbgE,
+                     uint32_t* dbgV, float* dbgM, int* n_found) {
+    const int npass = nf * pl.nq * SNN_NBRIGHT;
+    SNN_CUDA(cudaMemsetAsync(pl.counter, 0, 64, ctx->stream));
+    int rc = snn_image_chain(ctx, c, pl, frame0, nf, dbgM);
+    if (rc) return rc;
+    {
+        SnnScope scope(ctx, ST_SEARCH, 1);
+        SearchParams sp;
+        sp.nq = pl.nq;
+        sp.minH = pl.minH;
+        sp.maxW = pl.maxW;
+        sp.raw_cap = pl.raw_cap;
+        k_search<<<npass, NTHR, kSearchSmem, ctx->stream>>>(pl.low, pl.high, pl.info, sp, pl.counter, pl.raw, dbgE,
+                                                            dbgV);
+        SNN_LAUNCH_CHECK("k_search");
+    }
+    int cnt[2] = {0, 0};
+    SNN_CUDA(cudaMemcpyAsync(cnt, pl.counter, sizeof cnt, cudaMemcpyDeviceToHost, ctx->stream));
+    SNN_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (cnt[1] || cnt[0] > pl.raw_cap)
+        return snn_fail(ctx, SNN_ENOMEM, "snn_extract: more than %d raw candidates in one batch", pl.raw_cap);
+    *n_found = cnt[0];
+    if (cnt[0] > 0) {
+        SnnScope scope(ctx, ST_FINISH, 1);
+        int blocks = (cnt[0] * 32 + 255) / 256;
+        k_finish<<<blocks, 256, 0, ctx->stream>>>(pl.raw, cnt[0], pl.info, pl.nz, pl.Dc, pl.nq, c->binsize,
+                                                  c->chromsize, pl.cand);
+        SNN_LAUNCH_CHECK("k_finish");
+    }
+    return SNN_OK;
+}
+
+static int ensure_search_attr(snn_ctx* ctx) {
+    SNN_CUDA(cudaFuncSetAttribute(k_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSearchSmem));
+    return SNN_OK;
+}
+
+int snn_extract_impl(snn_ctx* ctx, SnnChrom* c, int nq, const double* mp, const double* gw, int radius, int minH,
+                     int maxW, int bfilter, int gray_variant, int frame_lo, int frame_hi, snn_candidate* out,
+                     int64_t cap, int64_t* n_out) {
+    *n_out = 0;
+    int rc = ensure_search_attr(ctx);
+    if (rc) return rc;
+    const int total = frame_hi - frame_lo;
+    if (total <= 0) return SNN_OK;
+    // windows per batch: keep the per-pass intermediates (~2 MB each) around 3 GB
+    int fb = 1536 / (nq * SNN_NBRIGHT);
+    if (fb < 1) fb = 1;
+    if (fb > total) fb = total;
+    ExtractPlan pl;
+    rc = make_plan(ctx, &pl, nq, mp, gw, radius, minH, maxW, bfilter, gray_variant, fb, false, nullptr, nullptr,
+                   nullptr);
+    if (rc) return rc;
+    std::vector<snn_candidate> all;
+    for (int f0 = frame_lo; f0 < frame_hi; f0 += fb) {
+        int nf = std::min(fb, frame_hi - f0);
+        int found = 0;
+        rc = run_batch(ctx, c, pl, f0, nf, nullptr, nullptr, nullptr, &found);
+        if (rc) return rc;
+        if (found > 0) {
+            size_t old = all.size();
+            all.resize(old + found);
+            SNN_CUDA(cudaMemcpyAsync(all.data() + old, pl.cand, (size_t)found * sizeof(snn_candidate),
+                                     cudaMemcpyDeviceToHost, ctx->stream));
+            SNN_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    // the reference's emission order: maxpixel, window, brightness pass, up/down, pair index
+    std::sort(all.begin(), all.end(), [](const snn_candidate& a, const snn_candidate& b) {
+        if (a.q != b.q) return a.q < b.q;
+        if (a.frame != b.frame) return a.frame < b.frame;
+        if (a.bright != b.bright) return a.bright < b.bright;
+        if (a.ud != b.ud) return a.ud < b.ud;
+        return a.k < b.k;
+    });
+    *n_out = (int64_t)all.size();
+    if ((int64_t)all.size() > cap)
+        return snn_fail(ctx, SNN_ECAP, "snn_extract: %lld candidates, caller's buffer holds %lld",
+                        (long long)all.size(), (long long)cap);
+    if (!all.empty()) memcpy(out, all.data(), all.size() * sizeof(snn_candidate));
+    return SNN_OK;
+}
+
+static void unpack_bits(const std::vector<uint32_t>& words, int S, uint8_t* out) {
+    for (int r = 0; r < S; ++r)
+        for (int c = 0; c < S; ++c) out[r * S + c] = (words[r * SNN_WPR + (c >> 5)] >> (c & 31)) & 1;
+}
+
+int snn_debug_stages_impl(snn_ctx* ctx, SnnChrom* c, double mp, const double* gw, int radius, int bfilter,
+                          int gray_variant, int frame, int bright, int32_t* S_out, int32_t* nz, float* gray,
+                          float* smoothed, float* mag, uint8_t* low, uint8_t* edges, uint8_t* vert) {
+    int rc = ensure_search_attr(ctx);
+    if (rc) return rc;
+    ExtractPlan pl;
+    uint32_t *dE = nullptr, *dV = nullptr;
+    float* dM = nullptr;
+    rc = make_plan(ctx, &pl, 1, &mp, gw, radius, 10, 8, bfilter, gray_variant, 1, true, &dE, &dV, &dM);
+    if (rc) return rc;
+    int found = 0;
+    rc = run_batch(ctx, c, pl, frame, 1, dE, dV, dM, &found);
+    if (rc) return rc;
+    FrameInfo fi;
+    SNN_CUDA(cudaMemcpyAsync(&fi, pl.info, sizeof fi, cudaMemcpyDeviceToHost, ctx->stream));
+    SNN_CUDA(cudaStreamSynchronize(ctx->stream));
+    const int S = fi.S;
+    *S_out = S;
+    if (nz) SNN_CUDA(cudaMemcpy(nz, pl.nz, SNN_SMAX * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (S == 0) return SNN_OK;
+    const size_t img = (size_t)SNN_SMAX * SNN_SMAX;
+    std::vector<float> tmp(img);
+    auto grab_f = [&](const float* dev, float* dst) -> int {
+        SNN_CUDA(cudaMemcpy(tmp.data(), dev + (size_t)bright * img, img * sizeof(float), cudaMemcpyDeviceToHost));
+        for (int r = 0; r < S; ++r) memcpy(dst + (size_t)r * S, tmp.data() + (size_t)r * SNN_SMAX, S * sizeof(float));
+        return SNN_OK;
+    };
+    if (gray && (rc = grab_f(pl.bufA, gray))) return rc;
+    if (smoothed && (rc = grab_f(pl.bufC, smoothed))) return rc;
+    if (mag && (rc = grab_f(dM, mag))) return rc;
+    std::vector<uint32_t> words((size_t)SNN_SMAX * SNN_WPR);
+    auto grab_b = [&](const uint32_t* dev, uint8_t* dst) -> int {
+        SNN_CUDA(cudaMemcpy(words.data(), dev + (size_t)bright * SNN_SMAX * SNN_WPR, words.size() * 4,
+                            cudaMemcpyDeviceToHost));
+        unpack_bits(words, S, dst);
+        return SNN_OK;
+    };
+    if (low && (rc = grab_b(pl.low, low))) return rc;
+    if (edges && (rc = grab_b(dE, edges))) return rc;
+    if (vert && (rc = grab_b(dV, vert))) return rc;
+    return SNN_OK;
+}

@@ -42,7 +42,32 @@ struct SnnChrom {
     int32_t* count = nullptr;  // device
     double* weight = nullptr;  // device or null
     double* band = nullptr;    // device, nbins * bw
+    int64_t* rowptr = nullptr; // device, nbins + 1: CSR row pointers into the (bin1, bin2)-sorted pixels
 };
+
+// Read-only view of one chromosome's matrix for kernels that may touch ANY pixel: the band
+// answers |i - j| < bw, a binary search in the CSR row answers the (rare) far pixels.
+struct MatView {
+    const double* band;
+    int64_t nbins;
+    int bw;
+    const int64_t* rowptr;
+    const int32_t* bin2;
+    const int32_t* count;
+    const double* weight;
+};
+
+inline MatView snn_view(const SnnChrom* c) {
+    MatView v;
+    v.band = c->band;
+    v.nbins = c->nbins;
+    v.bw = c->bw;
+    v.rowptr = c->rowptr;
+    v.bin2 = c->bin2;
+    v.count = c->count;
+    v.weight = c->weight;
+    return v;
+}
 
 struct SnnPending {
     cudaEvent_t first, second;
@@ -115,6 +140,25 @@ __device__ __forceinline__ double snn_band_at(const double* __restrict__ band, i
     return band[lo * bw + d];
 }
 
+#ifdef __CUDACC__
+// Pixel (i, j) of the symmetric balanced matrix, NaN kept; 0 <= i, j < nbins required.
+__device__ __forceinline__ double snn_mat_at(const MatView& m, int64_t i, int64_t j) {
+    int64_t lo = i < j ? i : j, hi = i < j ? j : i;
+    int64_t d = hi - lo;
+    if (d < m.bw) return m.band[lo * m.bw + d];
+    int64_t a = m.rowptr[lo], b = m.rowptr[lo + 1];
+    double cnt = 0.0;
+    while (a < b) {
+        int64_t mid = (a + b) >> 1;
+        int32_t c = m.bin2[mid];
+        if (c == hi) { cnt = (double)m.count[mid]; break; }
+        if (c < hi) a = mid + 1; else b = mid;
+    }
+    if (m.weight) cnt = cnt * (m.weight[lo] * m.weight[hi]);
+    return cnt;
+}
+#endif
+
 // Python slice(a, b) on an axis of length n -> [lo, hi) (hi <= lo means empty).
 __host__ __device__ __forceinline__ void snn_pyslice(int64_t a, int64_t b, int64_t n, int64_t* lo,
                                                       int64_t* hi) {
@@ -139,6 +183,7 @@ int snn_debug_stages_impl(snn_ctx* ctx, SnnChrom* c, double mp, const double* gw
                           int bfilter, int gray_variant, int frame, int bright, int32_t* S, int32_t* nz,
                           float* gray, float* smoothed, float* mag, uint8_t* low, uint8_t* edges,
                           uint8_t* vert);
-int snn_score_impl(snn_ctx* ctx, SnnChrom* c, int64_t n, const int64_t* pos, const double* expected,
+int snn_score_impl(snn_ctx* ctx, SnnChrom* c, int64_t n, const int64_t* pos, const int32_t* stale,
+                   const double* expected,
                    double* pvalue, double* stripiness, double* oe_mean, double* oe_total,
                    double* o_mean, double* o_sum);

@@ -1,0 +1,376 @@
+"""Host-side mirror of the reference class ``getStripe`` (src/stripenn/getStripe.py:17-33).
+
+Same constructor arguments (the cooler matrix selector is replaced by a :class:`DeviceMatrix`,
+the contact map resident on one B200), same method names, argument meaning and return types,
+so ``compute``/``getScore`` read like the reference drivers.  Every method hands its arithmetic
+to the CUDA library through :class:`stripenn_b200.engine.Device`; what stays on the host is
+exactly what the north star assigns to it: the ``random.Random`` sample draws, the table
+bookkeeping and file I/O.
+"""
+from __future__ import annotations
+
+import math
+import random
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import pandas as pd
+
+from .contactmap import ContactMap
+from .engine import Device, gaussian_weights, remove_redundant_mask
+
+NDIST = 400
+RESULT_COLUMNS = ['chr', 'pos1', 'pos2', 'chr2', 'pos3', 'pos4', 'length', 'width', 'total', 'Mean',
+                  'maxpixel', 'num', 'start', 'end', 'x', 'y', 'h', 'w', 'medpixel']
+
+
+class DeviceMatrix:
+    """What ``Lib.matrix(balance=norm)`` is to the reference (stripenn.py:118): the balanced
+    contact matrix, here resident in HBM.  Chromosomes are uploaded lazily, once."""
+
+    def __init__(self, cm: ContactMap, balance, device: Optional[Device] = None, device_id: int = 0,
+                 band_width: Optional[int] = None):
+        self.cm = cm
+        self.balance = balance
+        self.dev = device if device is not None else Device(device_id)
+        self.band_width = band_width
+        self.binsize = int(cm.binsize)
+
+    def chrom_id(self, chrom: str) -> int:
+        return self.cm.chromnames.index(str(chrom))
+
+    def chromsize(self, chrom: str) -> int:
+        return int(self.cm.chromsizes[self.chrom_id(chrom)])
+
+    def nbins(self, chrom: str) -> int:
+        return int(math.ceil(self.chromsize(chrom) / self.binsize))
+
+    def ensure(self, chrom: str, band_width: Optional[int] = None) -> int:
+        cid = self.chrom_id(chrom)
+        need = band_width or self.band_width
+        have = self.dev.loaded.get(cid)
+        if have is not None and (need is None or have["bw"] >= min(need, have["nbins"])):
+            return cid
+        if str(chrom) not in self.cm.chroms:
+            raise KeyError("chromosome %r has no pixels in the contact map" % chrom)
+        c = self.cm.chroms[str(chrom)]
+        w = self.cm.weight_vector(str(chrom), self.balance)
+        self.dev.load_chrom(cid, c.nbins, self.binsize, c.size_bp, c.bin1, c.bin2, c.count, w, need)
+        return cid
+
+
+def _bins_of(start: int, end: int, size: int, r: int):
+    """cooler region -> bin range, with cooler's range checks."""
+    if end < start:
+        raise ValueError("End cannot be less than start")
+    if start < 0 or end > size:
+        raise ValueError("Genomic region out of bounds: [%d, %d)" % (start, end))
+    return start // r, int(math.ceil(end / r))
+
+
+class getStripe:
+    def __init__(self, unbalLib: DeviceMatrix, resol, minH, maxW, canny, all_chromnames, chromnames,
+                 all_chromsizes, chromsizes, core, bfilter, seed, gray_variant: int = 0):
+        self.unbalLib = unbalLib
+        self.dev = unbalLib.dev
+        self.resol = int(resol)
+        self.minH = minH
+        self.maxW = maxW
+        self.canny = canny
+        self.all_chromnames = list(all_chromnames)
+        self.all_chromsizes = np.asarray(all_chromsizes)
+        self.chromnames = list(chromnames)
+        self.chromsizes = np.asarray(chromsizes)
+        self.core = core          # kept for signature compatibility; the GPU does the work
+        self.bfilter = bfilter
+        self.seed = seed
+        self.gray_variant = gray_variant
+        self.chromnames2sizes = {self.all_chromnames[i]: int(self.all_chromsizes[i])
+                                 for i in range(len(self.all_chromnames))}
+        self._bg_installed = None
+
+    # ------------------------------------------------------------------ a2
+    def getQuantile_original(self, coolinfo, ChrList, quantile):
+        """getStripe.py:160-176 -> {chrom: ndarray[len(quantile)]}."""
+        out = {}
+        for c in ChrList:
+            cid = self.unbalLib.ensure(c)
+            out[c] = self.dev.quantiles(cid, quantile)
+        return out
+
+    def getQuantile_slow(self, coolinfo, ChrList, quantile):
+        raise NotImplementedError(
+            "-s/--slow (getStripe.getQuantile_slow, getStripe.py:107-158) is not built yet: in the "
+            "reference it returns DIFFERENT maxpixel values than the default path (SURVEY.md §8f "
+            "row 2); the B200 path needs no memory-saving mode, run without -s")
+
+    # ------------------------------------------------------------------ a3
+    def mpmean(self):
+        """getStripe.py:178-235 -> {chrom: list[400]} for the selected chromosomes."""
+        out = {}
+        for c in self.chromnames:
+            cid = self.unbalLib.ensure(c)
+            out[c] = self.dev.expected(cid).tolist()
+        return out
+
+    # ------------------------------------------------------------------ a4
+    @staticmethod
+    def _budget(values):
+        v = (np.asarray(values, dtype=np.float64) / np.sum(values)) * 1000
+        v = v.astype(np.uint64)
+        dif = 1000 - int(np.sum(v))
+        nz = np.nonzero(v != 0)[0]
+        v[0] += np.uint64(dif)
+        return v, nz
+
+    def _units(self, chrom):
+        r = self.resol
+        csize = self.chromnames2sizes[chrom]
+        itera = int(min(csize / r / 500, 25))
+        unit = int(np.floor(csize / r / itera))
+        return csize, itera, unit
+
+    def _unit_geometry(self, chrom, it, unit):
+        """Row/column bin ranges of the window main_null_calc fetches (getStripe.py:313-326)."""
+        r = self.resol
+        csize = self.chromnames2sizes[chrom]
+        start1 = int(unit * r * it + 1)
+        start0 = start1 - 400 * r
+        end1 = int(unit * r * (it + 1))
+        end2 = int(unit * r * (it + 1) + 400 * r)
+        if end2 > csize:
+            end2 = csize - 1
+        if end1 > csize - 400 * r:
+            end1 = csize - 400 * r
+        if start0 <= 1:
+            start0 = 1
+        i0, i1 = _bins_of(start1, end1, csize, r)
+        j0, j1 = _bins_of(start0, end2, csize, r)
+        return i0, i1, j0, j1
+
+    def _flags(self, chrom):
+        """Per-bin flags from the device: avail (non-empty row inside the unit's own block,
+        available_cols :249-273) and live (non-empty row of the unit's sampling window :328-331)."""
+        r = self.resol
+        csize, itera, unit = self._units(chrom)
+        geom = []
+        for it in range(itera):
+            a0, a1 = _bins_of(unit * r * it + 1, unit * r * (it + 1), csize, r)
+            i0, i1, j0, j1 = self._unit_geometry(chrom, it, unit)
+            geom.append((a0, a1, i0, i1, j0, j1))
+        cid = self.unbalLib.ensure(chrom)
+        avail, live = self.dev.row_flags(cid, np.array(geom, dtype=np.int64))
+        return geom, avail, live
+
+    def plan_samples(self):
+        """Everything of nulldist that decides WHICH rows are sampled (getStripe.py:242-247,
+        278-283, 296-346, 416-440).  RNG convention: a fresh random.Random(seed) per chromosome —
+        what every loky task of the reference sees with -n >= 2."""
+        v1, nz1 = self._budget(self.all_chromsizes)
+        names2 = [self.all_chromnames[i] for i in nz1]
+        flags = {c: self._flags(c) for c in names2}
+        avail = [int(flags[c][1].sum()) for c in names2]
+        budget, nz2 = self._budget(avail)
+        names2 = [names2[i] for i in nz2]
+        plans = []
+        for chrom in names2:
+            prng = random.Random(self.seed)
+            ss = int(budget[names2.index(chrom)])  # indexes the UNfiltered budget (reference quirk)
+            csize, itera, unit = self._units(chrom)
+            geom, _, live = flags[chrom]
+            specs, n_pool = [], []
+            it = 0
+
+            def pool_of(g, first):
+                _, _, i0, i1, j0, j1 = g
+                x = np.arange(i1 - i0)
+                ok = (live[i0:i1] != 0) & (x > 20) & (x < unit - 20)
+                if first:
+                    ok &= (x > 410) & (x < (j1 - j0))
+                return x[ok].tolist()
+
+            for it in range(itera):
+                sss = int(ss / itera)
+                g = geom[it]
+                pool = pool_of(g, it == 0)
+                n_pool.append(len(pool))
+                if len(pool) == 0:
+                    continue
+                k = len(pool) if len(pool) < sss else sss
+                for x in prng.choices(pool, k=k):
+                    specs.append((g[2], g[3], g[4], g[5], x, 400 if it > 0 else 0))
+            depl = ss - len(specs)
+            if depl > 0:
+                rich = int(np.argmax(n_pool))
+                g = geom[rich]
+                pool = pool_of(g, False)
+                for x in prng.choices(pool, k=depl):
+                    specs.append((g[2], g[3], g[4], g[5], x, 400 if it > 0 else 0))  # stale `it`
+            plans.append(np.array(specs, dtype=np.int32).reshape(-1, 6))
+        return names2, plans
+
+    def nulldist(self):
+        """getStripe.py:238-499 -> bgleft_up, bgright_up, bgleft_down, bgright_down."""
+        names2, plans = self.plan_samples()
+        parts = []
+        for chrom, spec in zip(names2, plans):
+            cid = self.unbalLib.ensure(chrom)
+            parts.append(self.dev.background(cid, spec))
+        if parts:
+            full = np.concatenate(parts, axis=2)
+        else:
+            full = np.zeros((4, NDIST, 0))
+        return full[0], full[1], full[2], full[3]
+
+    # ------------------------------------------------------------------ a5-a15
+    def _candidate_frame(self, cand, chrom, perc):
+        n = len(cand)
+        h = cand["h"].astype(np.int64)
+        w = cand["w"].astype(np.int64)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            mean = cand["total"] / h / w
+        df = pd.DataFrame({
+            'chr': [chrom] * n, 'pos1': cand["pos1"], 'pos2': cand["pos2"], 'chr2': [chrom] * n,
+            'pos3': cand["pos3"], 'pos4': cand["pos4"],
+            'length': cand["pos4"] - cand["pos3"] + 1, 'width': cand["pos2"] - cand["pos1"] + 1,
+            'total': cand["total"], 'Mean': mean, 'maxpixel': [str(perc * 100) + '%'] * n,
+            'num': cand["frame"].astype(np.int64), 'start': cand["start"].astype(np.int64),
+            'end': cand["end"].astype(np.int64), 'x': cand["x"].astype(np.int64),
+            'y': cand["y"].astype(np.int64), 'h': h, 'w': w, 'medpixel': np.full(n, np.nan)})
+        return df
+
+    def extract_all(self, MP, quantiles: Sequence[float], bgleft_up, bgright_up, bgleft_down,
+                    bgright_down, frame_range=None):
+        """``extract`` for every maxpixel value at once: the device builds each search window
+        once and runs all Q x 6 brightness passes on it.  Returns one DataFrame per quantile,
+        identical to what the reference's per-quantile loop (stripenn.py:134-138) collects."""
+        per_q: List[List[pd.DataFrame]] = [[] for _ in quantiles]
+        weights = gaussian_weights(self.canny)
+        for ci, chrom in enumerate(self.chromnames):
+            cid = self.unbalLib.ensure(chrom)
+            lo, hi = (0, None) if frame_range is None else frame_range
+            cand = self.dev.extract(cid, np.asarray(MP[chrom], dtype=np.float64), self.canny, self.minH,
+                                    self.maxW, self.bfilter, self.gray_variant, lo, hi, weights)
+            for qi, perc in enumerate(quantiles):
+                sel = cand[cand["q"] == qi]
+                df = self._candidate_frame(sel, chrom, perc)
+                # per-window RemoveRedundant('size') (getStripe.py:1112): pairs inside one window
+                if len(df):
+                    keep = remove_redundant_mask(df['num'].to_numpy(), df['num'].to_numpy(),
+                                                 df[['pos1', 'pos2', 'pos3', 'pos4']].to_numpy(),
+                                                 df['h'].to_numpy(), df['w'].to_numpy(), None, "size")
+                    df = df[keep]
+                per_q[qi].append(df)
+        out = []
+        for qi, perc in enumerate(quantiles):
+            res = pd.concat(per_q[qi]) if per_q[qi] else pd.DataFrame(columns=RESULT_COLUMNS)
+            res = self.RemoveRedundant(res, 'size')          # getStripe.py:852
+            res = res.reset_index(drop=True)
+            pval = self.pvalue(bgleft_up, bgright_up, bgleft_down, bgright_down, res)
+            res = res.assign(pvalue=pval)
+            out.append(res)
+        return out
+
+    def extract(self, MP, index, perc, bgleft_up, bgright_up, bgleft_down, bgright_down):
+        """getStripe.py:790-862 for one maxpixel value."""
+        MP1 = {c: np.asarray(MP[c], dtype=np.float64)[[index]] for c in self.chromnames}
+        return self.extract_all(MP1, [perc], bgleft_up, bgright_up, bgleft_down, bgright_down)[0]
+
+    def RemoveRedundant(self, df, by):
+        """getStripe.py:1116-1196."""
+        if by not in ('size', 'pvalue', 'score'):
+            raise ValueError('"by" should be one of "size", "pvalue" and "score"')
+        if len(df) == 0:
+            return df
+        codes, _ = pd.factorize(df['chr'].astype(str))
+        key = None
+        if by == 'pvalue':
+            key = df['pvalue'].to_numpy(dtype=np.float64)
+        elif by == 'score':
+            key = df['Stripiness'].to_numpy(dtype=np.float64)
+        keep = remove_redundant_mask(codes, df['num'].to_numpy(dtype=np.int64),
+                                     df[['pos1', 'pos2', 'pos3', 'pos4']].to_numpy(dtype=np.int64),
+                                     df['h'].to_numpy(dtype=np.float64), df['w'].to_numpy(dtype=np.float64),
+                                     key, by)
+        return df[keep]
+
+    # ------------------------------------------------------------------ a16-a18
+    def _install_background(self, tables):
+        ident = tuple(id(t) for t in tables)
+        if self._bg_installed != ident:
+            self.dev.set_background(tables)
+            self._bg_installed = ident
+            self._bg_keepalive = tables
+
+    def _by_chrom(self, df):
+        chrs = df['chr'].astype(str).to_numpy()
+        pos = df[['pos1', 'pos2', 'pos3', 'pos4']].to_numpy(dtype=np.int64)
+        groups = {}
+        for i, c in enumerate(chrs):
+            groups.setdefault(c, []).append(i)
+        return chrs, pos, groups
+
+    def _stale_rows(self, pos):
+        """Background row inherited by stripes that are neither on nor under the diagonal
+        (getStripe.py:583-597: the loop variables persist across stripes)."""
+        r = self.resol
+        n = len(pos)
+        stale = np.full((n, 2), -1, dtype=np.int32)
+        last = (-1, -1)
+        for i in range(n):
+            p1, p2, p3, p4 = (int(v) for v in pos[i])
+            x1, x2, y1, y2 = (p1 - 1) // r, p2 // r, (p3 - 1) // r, p4 // r
+            h = int(math.ceil(p4 / r)) - p3 // r
+            if x1 == y1:
+                last = (0, min(h - 1, 399)) if h > 0 else last
+            elif x2 == y2:
+                last = (1, min(max(y2 - y1 - (h - 1) - 1, -400), 399) % 400) if h > 0 else last
+            else:
+                stale[i] = last
+        return stale
+
+    def pvalue(self, bgleft_up, bgright_up, bgleft_down, bgright_down, df):
+        """getStripe.py:536-606 -> list of p-values in table order."""
+        if len(df) == 0:
+            return []
+        self._install_background((bgleft_up, bgright_up, bgleft_down, bgright_down))
+        chrs, pos, groups = self._by_chrom(df)
+        stale = self._stale_rows(pos)
+        out = np.full(len(pos), np.nan)
+        for c, idx in groups.items():
+            cid = self.unbalLib.ensure(c)
+            idx = np.asarray(idx)
+            st = stale[idx] if (stale[idx, 0] >= 0).any() else None
+            out[idx] = self.dev.score(cid, pos[idx], None, True, st)["pvalue"]
+        return out.tolist()
+
+    def scoringstripes(self, df, expecVal, mask='0'):
+        """getStripe.py:608-788 -> (Stripiness, O/E mean, O/E total) lists."""
+        if mask != '0':
+            raise NotImplementedError("--mask (getStripe.py:612-639) is not built yet (SURVEY.md §8f row 3)")
+        n = len(df)
+        g, m, t = np.zeros(n), np.zeros(n), np.zeros(n)
+        if n == 0:
+            return g.tolist(), m.tolist(), t.tolist()
+        chrs, pos, groups = self._by_chrom(df)
+        for c, idx in groups.items():
+            cid = self.unbalLib.ensure(c)
+            idx = np.asarray(idx)
+            res = self.dev.score(cid, pos[idx], np.asarray(expecVal[c], dtype=np.float64), False)
+            g[idx], m[idx], t[idx] = res["stripiness"], res["oe_mean"], res["oe_total"]
+        return g.tolist(), m.tolist(), t.tolist()
+
+    def getMean(self, df):
+        """getStripe.py:501-534 -> (nanmean, nansum) lists of the stripe bodies."""
+        n = len(df)
+        ms, ss = np.zeros(n), np.zeros(n)
+        if n == 0:
+            return ms.tolist(), ss.tolist()
+        chrs, pos, groups = self._by_chrom(df)
+        dummy = np.zeros(NDIST)
+        for c, idx in groups.items():
+            cid = self.unbalLib.ensure(c)
+            idx = np.asarray(idx)
+            res = self.dev.score(cid, pos[idx], dummy, False)
+            ms[idx], ss[idx] = res["o_mean"], res["o_sum"]
+        return ms.tolist(), ss.tolist()
