@@ -1,0 +1,407 @@
+#!/usr/bin/env python
+"""Benchmark of the `stripenn compute` hot path (BASELINE.json metric: Mpixels/s of banded Hi-C
+scored — extract + score + pvalue — at 1/2/4/8 B200 next to the CPU path).
+
+    python bench.py --gpus N --steps K --warmup W            # the B200 arm (one JSON line)
+    python bench.py --impl reference --gpus N --steps K ...  # the CPU arm (oracle port, all cores)
+
+A step = one pass of stages 1-5 of `compute` (maxpixel quantiles, expected values, background
+sampling, candidate search over every 400-bin window x 5 maxpixel values x 6 brightness passes,
+p-values, dedup, stripiness) over one synthetic genome.  Workload = BASELINE.json configs[1]:
+synthetic mouse whole genome at 10 kb (chr1-19+X, 263,389 bins, 1,329 windows), --norm None,
+-m 0.95,0.96,0.97,0.98,0.99.  Mpixels = Q * sum over windows of (end-start+1)^2 / 1e6
+ = 1,041 Mpixels per genome.
+
+`value`: pixels resident in HBM (COO arrays on the device) when the timed region starts;
+`e2e`: the same step through the public API with pinned HOST buffers, H2D copies of the pixel
+tables and D2H of candidates/results inside the timed region.
+Multi-GPU (`--scaling weak`, default): one genome per rank (independent samples, different
+seeds), no collective.  `--scaling strong`: ONE genome sharded by chromosome (LPT) with the two
+host-side exchanges of the background tables (stripenn_b200.compute.run_pipeline).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "Mpixels/s banded Hi-C scored (extract+score+pvalue)"
+UNIT = "Mpixels/s"
+QS = "0.95,0.96,0.97,0.98,0.99"
+NQ = 5
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--config", default="cfg2")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def env_rank():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def genome_mpixels(cm, names):
+    from stripenn_b200 import synth
+    return NQ * sum(synth.frame_pixels(cm.nbins(c)) for c in names) / 1e6
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in out.strip().splitlines():
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0]))
+                mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------ peaks
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def _cpu_window(args):
+    """One search window x all maxpixel values with the oracle port (worker process)."""
+    idx, = args
+    from snn_oracle import pipeline as pl
+    st = _CPU_STATE
+    fr = pl.load_frame(st["mat"], st["chrom"], idx)
+    out = []
+    for qi, q in enumerate(st["qs"]):
+        if fr is None:
+            out.append(pl.empty_table())
+        else:
+            out.append(pl.stripe_search(fr, st["MP"][qi], q, st["chrom"], 10, 8, 2.0, 3))
+    return idx, out
+
+
+_CPU_STATE = {}
+
+
+def cpu_sample(budget_s, cores=None, chrom_size=61431566, binsize=10000, seed=20240501):
+    """The CPU implementation of the path (numpy oracle port of the reference, oracle/snn_oracle)
+    on a bounded sample of the workload: the first F windows of a chr19-sized synthetic chromosome
+    of the same generator, 5 maxpixel values: search (all cores, one task per window like the
+    reference's joblib loop) + serial p-values + dedup + stripiness.  Quantiles, expected values
+    and the background tables are prepared OUTSIDE the timed region (favours the CPU)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import multiprocessing as mp
+    from snn_oracle import background as bgm, pipeline as pl, scoring as sc
+    from snn_oracle.matrix import OracleMatrix
+    from stripenn_b200 import synth
+    cores = cores or os.cpu_count() or 1
+    cm = synth.make_map([("19", chrom_size)], binsize, seed=seed)
+    mat = OracleMatrix(cm, False)
+    qs = list(map(float, QS.split(",")))
+    MP = pl.quantiles(mat, ["19"], qs)["19"]
+    EV = bgm.expected_by_distance(mat, ["19"])
+    bg = bgm.null_distribution(mat, ["19"], np.array([chrom_size]), 123456789)
+    _CPU_STATE.update(mat=mat, chrom="19", qs=qs, MP=MP)
+    # calibrate: one window on one core
+    t0 = time.time()
+    _cpu_window((3,))
+    per_window = time.time() - t0
+    nfr = pl.n_frames(mat.nbins("19"))
+    F = int(max(cores, min(nfr, budget_s * 0.7 * cores / max(per_window, 1e-3))))
+    F = min(F, nfr)
+    frames = list(range(F))
+    t0 = time.time()
+    if cores > 1:
+        ctx = mp.get_context("fork")
+        with ctx.Pool(cores) as pool:
+            res = dict(pool.map(_cpu_window, [(i,) for i in frames], chunksize=1))
+    else:
+        res = dict(_cpu_window((i,)) for i in frames)
+    per_q = []
+    for qi in range(len(qs)):
+        t = pl.remove_redundant(pl.concat_tables([res[i][qi] for i in frames]), "size")
+        t["pvalue"] = sc.pvalues(mat, bg, t)
+        per_q.append(t)
+    final = pl.remove_redundant(pl.concat_tables(per_q), "pvalue")
+    sc.stripiness(mat, final, EV)
+    dt = time.time() - t0
+    px = NQ * sum((min((i + 1) * 200 + 99, mat.nbins("19") - 1) - (0 if i == 0 else i * 200 - 100) + 1) ** 2
+                  for i in frames) / 1e6
+    return {"value": px / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "oracle port (numpy restatement of the reference), first %d of %d windows of a chr19-sized "
+                      "synthetic chromosome at 10 kb x 5 maxpixel values: search on %d processes + serial pvalue + "
+                      "dedup + stripiness in %.1f s; quantiles/expected/background prepared outside the timed region"
+                      % (F, nfr, cores, dt),
+            "seconds": dt, "mpixels": px, "stripes": len(final["pos1"])}
+
+
+def reference_arm(args):
+    rank, local, world = env_rank()
+    if rank != 0:
+        return
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    per = max(4.0, min(args.cpu_seconds, 150.0 / (steps + warm)))
+    vals = []
+    last = None
+    for i in range(warm + steps):
+        last = cpu_sample(per)
+        if i >= warm:
+            vals.append(last)
+    tot_px = sum(v["mpixels"] for v in vals)
+    tot_s = sum(v["seconds"] for v in vals)
+    value = tot_px / tot_s
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": 1000.0 * tot_s / steps, "higher_is_better": True,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "cfg2 (synthetic mouse genome, 10 kb, norm None, 5 maxpixel values); each step "
+                                   "= a bounded sample of it", "sample": last["sample"]},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": last["cores"], "kind": "port",
+                             "sample": last["sample"]},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ B200 arm
+def native_arm(args):
+    import torch
+    import torch.distributed as dist
+    from stripenn_b200 import compute as cp
+    from stripenn_b200 import getstripe as gs
+    from stripenn_b200 import synth
+    from stripenn_b200.engine import Device, default_band_width
+
+    rank, local, world = env_rank()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the B200 arm has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    strong = args.scaling == "strong" and world > 1
+
+    chroms, binsize, balanced = synth.config_chroms(args.config)
+    names = [c[0] for c in chroms]
+    sizes = [c[1] for c in chroms]
+    if strong:
+        owner = cp.lpt_partition(names, sizes, world)
+        mine = [c for c in names if owner[c] == rank]
+        seed = synth.DEFAULT_SEED
+    else:
+        mine = names
+        seed = synth.DEFAULT_SEED + rank          # one independent sample per rank
+    t0 = time.time()
+    cm = synth.make_config(args.config, seed=seed, only=mine)
+    gen_s = time.time() - t0
+    norm = "KR" if balanced else "None"
+    bal = cp.resolve_norm(cm, norm, "compute", False)
+    all_names, all_sizes, chromnames, chromsizes = cp.compute_chromosomes(cm, ["all"])
+    mpix_rank = genome_mpixels(cm, [c for c in chromnames if c in cm.chroms])
+    nnz_rank = sum(cm.chroms[c].nnz for c in cm.chroms)
+
+    dev = Device(local, timing=True)
+    stream = torch.cuda.current_stream()
+    dev.set_stream(stream.cuda_stream)
+    comm = cp.TorchComm() if strong else None
+
+    # resident copies (HBM) and pinned host copies of the pixel tables
+    resident, pinned = {}, {}
+    for c, px in cm.chroms.items():
+        host = [torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).pin_memory()
+                for a in (px.bin1, px.bin2, px.count)]
+        pinned[c] = host
+        resident[c] = [h.cuda(non_blocking=True) for h in host]
+    torch.cuda.synchronize()
+
+    class ResidentMatrix(gs.DeviceMatrix):
+        """DeviceMatrix whose chromosomes are built from pixel tables already in HBM."""
+        def ensure(self, chrom, band_width=None):
+            cid = self.chrom_id(chrom)
+            if cid in self.dev.loaded:
+                return cid
+            px = self.cm.chroms[str(chrom)]
+            b1, b2, ct = resident[str(chrom)]
+            self.dev.load_chrom_device(cid, px.nbins, self.binsize, px.size_bp, px.nnz, b1.data_ptr(),
+                                       b2.data_ptr(), ct.data_ptr(), None, band_width or self.band_width)
+            return cid
+
+    class PinnedMatrix(gs.DeviceMatrix):
+        """DeviceMatrix fed from pinned host buffers (the H2D copies happen inside ensure)."""
+        def ensure(self, chrom, band_width=None):
+            cid = self.chrom_id(chrom)
+            if cid in self.dev.loaded:
+                return cid
+            px = self.cm.chroms[str(chrom)]
+            b1, b2, ct = (t.numpy() for t in pinned[str(chrom)])
+            self.dev.load_chrom(cid, px.nbins, self.binsize, px.size_bp, b1, b2, ct, None,
+                                band_width or self.band_width)
+            return cid
+
+    qs = list(map(float, QS.split(",")))
+
+    def step(matrix_cls):
+        for cid in list(dev.loaded):
+            dev.unload_chrom(cid)
+        lib = matrix_cls(cm, bal, dev)
+        obj = gs.getStripe(lib, cm.binsize, 10, 8, 2.0, all_names, chromnames, all_sizes, chromsizes, 1, 3,
+                           123456789, 0)
+        unf, fil = cp.run_pipeline(obj, cm, qs, chromnames, 0.1, '0', False, comm)
+        return unf, fil
+
+    def timed(matrix_cls, k, w):
+        for _ in range(w):
+            step(matrix_cls)
+        dev.reset_stage_times()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(k):
+            res = step(matrix_cls)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            dist.barrier()
+        return ms, res
+
+    steps, warm = max(1, args.steps), max(3, args.warmup)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms_dev, (unf, fil) = timed(ResidentMatrix, steps, warm)
+    clocks = sampler.stop()
+    stages = dev.stage_times()
+    dev.h2d_bytes = dev.d2h_bytes = 0
+    ms_e2e, _ = timed(PinnedMatrix, steps, 1)
+    h2d_step, d2h_step = dev.h2d_bytes // (steps + 1), dev.d2h_bytes // (steps + 1)
+
+    if world > 1:
+        t = torch.tensor([mpix_rank, float(nnz_rank)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        mpix_total, nnz_total = float(t[0].item()), float(t[1].item())
+    else:
+        mpix_total, nnz_total = mpix_rank, float(nnz_rank)
+    value = mpix_total * steps / (ms_dev / 1000.0)
+    e2e = mpix_total * steps / (ms_e2e / 1000.0)
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        launches = int(sum(v["launches"] for v in stages.values()))
+        kern_ms = {k: v["ms"] / steps for k, v in stages.items()}
+        # algorithmic bytes per step of each kernel family on THIS rank (DESIGN.md "Kernels")
+        nb = sum(cm.nbins(c) for c in cm.chroms)
+        bw = default_band_width(cm.binsize)
+        fpx = mpix_rank * 1e6 / NQ
+        n_str = max(len(unf), 1)
+        alg = {
+            "band_build": nnz_rank * 12 + nb * bw * 8,
+            "quantile_select": nnz_rank * 12,
+            "expected": nb * 400 * 8,
+            "frame_prepare": fpx * 8,
+            "gray": fpx * NQ * 6 * (8 + 4),
+            "gaussian": fpx * NQ * 6 * 16,
+            "sobel_nms": fpx * NQ * 6 * 4,
+            "search": fpx * NQ * 6 * 2 / 8,
+        }
+        top = max(kern_ms, key=lambda k: kern_ms[k])
+        per_stage = {k: {"ms_per_step": round(kern_ms[k], 4),
+                         "achieved_gbs": (alg[k] / 1e9) / (kern_ms[k] / 1e3) if k in alg and kern_ms[k] > 0 else None}
+                     for k in kern_ms}
+        ach = per_stage[top]["achieved_gbs"]
+        roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                    "frac": (ach / peak) if ach else None, "traffic": None, "peak_source": peak_src,
+                    "share_of_step": kern_ms[top] / (ms_dev / steps), "stages": per_stage,
+                    "gpu_ms_per_step": sum(kern_ms.values())}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                cpu = cpu_sample(args.cpu_seconds)
+                cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            except Exception as e:  # the checker must not break the measurement
+                cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % e}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
+                "ms_per_step": ms_dev / steps, "higher_is_better": True, "scaling": args.scaling,
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "%s: synthetic mouse whole genome at 10 kb (chr1-19+X, %d bins, %.0f Mpixels "
+                                       "per genome), --norm None, -m %s, stages 1-5 of compute" %
+                                       (args.config, sum(int(math.ceil(s / binsize)) for s in sizes),
+                                        mpix_rank if not strong else mpix_total, QS),
+                           "parallelism": ("1 genome per GPU (independent samples)" if not strong else
+                                           "1 genome sharded by chromosome (LPT) over %d GPUs" % world),
+                           "l2": "inputs larger than L2 (pixel tables %.0f MB per genome)" % (nnz_rank * 12 / 1e6),
+                           "stripes_found": int(len(unf)), "stripes_filtered": int(len(fil)),
+                           "generate_s": round(gen_s, 1)},
+                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d_step),
+                        "d2h_bytes_per_step": int(d2h_step), "ms_per_step": ms_e2e / steps},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    dev.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        reference_arm(a)
+    else:
+        native_arm(a)

@@ -119,13 +119,125 @@ def compute_chromosomes(cm: ContactMap, chroms):
     return all_names, all_sizes, chromnames, chromsizes
 
 
+class LocalComm:
+    """Single-process stand-in for the two host-side exchanges of the sharded pipeline."""
+    rank = 0
+    world = 1
+
+    def all_gather(self, obj):
+        return [obj]
+
+
+class TorchComm:
+    """torch.distributed (nccl or gloo) as the exchange: the payloads are the per-chromosome
+    availability counts, the background columns (12.8 MB in total) and the candidate tables —
+    host objects, gathered with all_gather_object.  No data-path collective exists (SURVEY.md
+    §8e): every (chromosome, window) unit is independent."""
+
+    def __init__(self):
+        import torch.distributed as dist
+        self.dist = dist
+        self.rank = dist.get_rank()
+        self.world = dist.get_world_size()
+
+    def all_gather(self, obj):
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj)
+        return out
+
+
+def lpt_partition(names, sizes, world):
+    """Longest-processing-time-first assignment of chromosomes to ranks (work ~ bins).
+    Deterministic: ties keep file order.  Returns {chrom: rank}."""
+    order = sorted(range(len(names)), key=lambda i: (-int(sizes[i]), i))
+    load = [0] * world
+    owner = {}
+    for i in order:
+        r = min(range(world), key=lambda k: (load[k], k))
+        owner[names[i]] = r
+        load[r] += int(sizes[i])
+    return owner
+
+
+def make_object(cm, bal, dev, all_names, all_sizes, chromnames, chromsizes, minL, maxW, canny, numcores,
+                bfilter, seed, gray_variant):
+    lib = gs.DeviceMatrix(cm, bal, dev)
+    return gs.getStripe(lib, cm.binsize, minL, maxW, canny, all_names, chromnames, all_sizes, chromsizes,
+                        numcores, bfilter, seed, gray_variant)
+
+
+def run_pipeline(obj, cm, qs, chromnames, pvalue, mask, slow, comm=None, say=lambda *a, **k: None,
+                 return_stages=False):
+    """Stages 1-5 of compute (stripenn.py:120-152) for the chromosomes this rank owns, with the
+    two host-side exchanges the background needs.  `obj` is a getStripe-shaped object."""
+    comm = comm or LocalComm()
+    all_names = list(obj.all_chromnames)
+    owner = lpt_partition(all_names, obj.all_chromsizes, comm.world)
+    mine = lambda c: owner.get(c, 0) == comm.rank
+    my_sel = [c for c in chromnames if mine(c)]
+    say('1. Maximum pixel value calculation ...')
+    MP = obj.getQuantile_slow(cm, my_sel, qs) if slow else obj.getQuantile_original(cm, my_sel, qs)
+    say('2. Expected value calculation ...')
+    saved = obj.chromnames
+    obj.chromnames = my_sel
+    try:
+        EV = obj.mpmean()
+    finally:
+        obj.chromnames = saved
+    say('3. Background distribution estimation ...')
+    names2 = obj.background_chromosomes()
+    avail = {}
+    for part in comm.all_gather(obj.available_counts([c for c in names2 if mine(c)])):
+        avail.update(part)
+    names2b, budget = obj.sample_budget(names2, avail)
+    cols = {}
+    for c in names2b:
+        if mine(c):
+            cols[c] = obj.background_columns(c, obj.plan_chromosome(c, int(budget[names2b.index(c)])))
+    allcols = {}
+    for part in comm.all_gather(cols):
+        allcols.update(part)
+    full = np.concatenate([allcols[c] for c in names2b], axis=2) if names2b else np.zeros((4, 400, 0))
+    bg = (full[0], full[1], full[2], full[3])
+    say('4. Finding candidate stripes from each chromosome ...')
+    per_q = obj.extract_all(MP, qs, *bg, chroms=my_sel)
+    empty = pd.DataFrame(columns=gs.RESULT_COLUMNS + ['pvalue'])
+    nonempty = [t for t in per_q if len(t)]
+    local = pd.concat(nonempty) if nonempty else empty
+    local = obj.RemoveRedundant(local, 'pvalue')     # pairs never cross chromosomes
+    say('5. Stripiness calculation ...')
+    s = obj.scoringstripes(local, EV, mask)[0]
+    local = local.drop(columns=['total', 'num', 'start', 'end', 'x', 'y', 'h', 'w', 'medpixel'])
+    local.insert(local.shape[1], 'Stripiness', s, True)
+    if comm.world > 1:
+        # reference row order: maxpixel-major, then chromosomes in -k order, then emission order
+        labels = [str(q * 100) + '%' for q in qs]
+        parts = comm.all_gather(local)
+        merged = pd.concat([p for p in parts if len(p)]) if any(len(p) for p in parts) else local
+        if len(merged):
+            qk = merged['maxpixel'].map({l: i for i, l in enumerate(labels)}).to_numpy()
+            ck = merged['chr'].astype(str).map({c: i for i, c in enumerate(chromnames)}).to_numpy()
+            order = np.lexsort((np.arange(len(merged)), ck, qk))
+            merged = merged.iloc[order]
+        result_table = merged
+    else:
+        result_table = local
+    result_table = result_table.reset_index(drop=True)
+    res_filter = result_table[result_table['pvalue'] < pvalue]
+    res_filter = res_filter.sort_values(by=['Stripiness'], ascending=False)
+    if return_stages:
+        return result_table, res_filter, dict(MP=MP, EV=EV, bg=bg, per_q=per_q)
+    return result_table, res_filter
+
+
 def run_stages(cm: ContactMap, norm='KR', chrom='all', canny=2.0, minL=10, maxW=8,
                maxpixel='0.95,0.96,0.97,0.98,0.99', numcores=1, pvalue=0.1, mask='0', slow=False,
                bfilter=3, seed=123456789, device=None, device_id=0, gray_variant=0, verbose=False,
-               return_stages=False):
+               return_stages=False, comm=None):
     """Stages 1-5 of ``compute`` on an in-memory contact map: everything between "matrix
     available" and "result tables on the host" (the span the Mpixels/s metric is defined on).
-    Returns (result_unfiltered, result_filtered) DataFrames [+ the stage products]."""
+    With a multi-rank `comm` every rank processes the chromosomes it owns and all ranks return
+    the same full tables.  Returns (result_unfiltered, result_filtered) [+ the stage products]."""
     say = print if verbose else (lambda *a, **k: None)
     qs = list(map(float, maxpixel.split(','))) if isinstance(maxpixel, str) else list(maxpixel)
     chroms = chrom.split(',') if isinstance(chrom, str) else list(chrom)
@@ -134,35 +246,12 @@ def run_stages(cm: ContactMap, norm='KR', chrom='all', canny=2.0, minL=10, maxW=
     own = device is None
     dev = device if device is not None else Device(device_id)
     try:
-        lib = gs.DeviceMatrix(cm, bal, dev)
-        obj = gs.getStripe(lib, cm.binsize, minL, maxW, canny, all_names, chromnames, all_sizes,
-                           chromsizes, numcores, bfilter, seed, gray_variant)
-        say('1. Maximum pixel value calculation ...')
-        if slow:
-            MP = obj.getQuantile_slow(cm, chromnames, qs)
-        else:
-            MP = obj.getQuantile_original(cm, chromnames, qs)
-        say('2. Expected value calculation ...')
-        EV = obj.mpmean()
-        say('3. Background distribution estimation ...')
-        bg = obj.nulldist()
-        say('4. Finding candidate stripes from each chromosome ...')
-        per_q = obj.extract_all(MP, qs, *bg)
-        result_table = pd.concat([pd.DataFrame(columns=gs.RESULT_COLUMNS + ['pvalue'])] + per_q) \
-            if any(len(t) for t in per_q) else pd.DataFrame(columns=gs.RESULT_COLUMNS + ['pvalue'])
-        result_table = obj.RemoveRedundant(result_table, 'pvalue')
-        say('5. Stripiness calculation ...')
-        s = obj.scoringstripes(result_table, EV, mask)[0]
-        result_table = result_table.drop(columns=['total', 'num', 'start', 'end', 'x', 'y', 'h', 'w', 'medpixel'])
-        result_table.insert(result_table.shape[1], 'Stripiness', s, True)
-        res_filter = result_table[result_table['pvalue'] < pvalue]
-        res_filter = res_filter.sort_values(by=['Stripiness'], ascending=False)
+        obj = make_object(cm, bal, dev, all_names, all_sizes, chromnames, chromsizes, minL, maxW, canny,
+                          numcores, bfilter, seed, gray_variant)
+        return run_pipeline(obj, cm, qs, chromnames, pvalue, mask, slow, comm, say, return_stages)
     finally:
         if own:
             dev.close()
-    if return_stages:
-        return result_table, res_filter, dict(MP=MP, EV=EV, bg=bg, per_q=per_q)
-    return result_table, res_filter
 
 
 def compute(cool, out, norm, chrom, canny, minL, maxW, maxpixel, numcores, pvalue, mask, slow, bfilter,

@@ -46,6 +46,8 @@ class Device:
         self.h = h
         self.device = int(device)
         self.loaded: Dict[int, dict] = {}
+        self.h2d_bytes = 0   # host<->device payload bytes moved by this object's calls
+        self.d2h_bytes = 0
         if timing:
             self.enable_timing(True)
 
@@ -86,6 +88,7 @@ class Device:
             raise ValueError("weight vector has %d entries, chromosome has %d bins" % (w.shape[0], nbins))
         check(self.lib.snn_load_chrom(self.h, int(chrom_id), int(nbins), int(binsize), int(chromsize),
                                       int(b1.shape[0]), ptr(b1), ptr(b2), ptr(ct), ptr(w), bw), self.h)
+        self.h2d_bytes += b1.nbytes * 3 + (0 if w is None else w.nbytes)
         self.loaded[int(chrom_id)] = dict(nbins=int(nbins), binsize=int(binsize),
                                           chromsize=int(chromsize), bw=min(bw, int(nbins)),
                                           nnz=int(b1.shape[0]))
@@ -130,6 +133,7 @@ class Device:
         live = np.zeros(nb, dtype=np.uint8)
         check(self.lib.snn_row_flags(self.h, int(chrom_id), int(g.shape[0]), ptr(g), ptr(avail), ptr(live)),
               self.h)
+        self.d2h_bytes += 2 * nb
         return avail, live
 
     def background(self, chrom_id, spec):
@@ -138,6 +142,8 @@ class Device:
         out = np.empty((4, NDIST, n), dtype=np.float64)
         if n:
             check(self.lib.snn_background(self.h, int(chrom_id), n, ptr(s), ptr(out)), self.h)
+            self.h2d_bytes += s.nbytes
+            self.d2h_bytes += out.nbytes
         return out
 
     def set_background(self, tables):
@@ -145,6 +151,7 @@ class Device:
         t = np.ascontiguousarray(np.stack([np.asarray(x, dtype=np.float64) for x in tables]))
         assert t.shape[0] == 4 and t.shape[1] == NDIST
         check(self.lib.snn_set_background(self.h, int(t.shape[2]), ptr(t)), self.h)
+        self.h2d_bytes += t.nbytes
 
     # ------------------------------------------------------------------ a5-a14
     def extract(self, chrom_id, maxpixel_values, sigma, minH, maxW, bfilter, gray_variant=0,
@@ -166,6 +173,7 @@ class Device:
                 cap = int(n.value)
                 continue
             check(rc, self.h)
+            self.d2h_bytes += int(n.value) * CANDIDATE_DTYPE.itemsize
             return out[:n.value]
 
     def debug_stages(self, chrom_id, maxpixel_value, sigma, bfilter, frame, bright, gray_variant=0):
@@ -203,6 +211,8 @@ class Device:
                                  ptr(res["oe_total"]) if ex is not None else None,
                                  ptr(res["o_mean"]) if ex is not None else None,
                                  ptr(res["o_sum"]) if ex is not None else None), self.h)
+        self.h2d_bytes += p.nbytes + (0 if ex is None else ex.nbytes)
+        self.d2h_bytes += n * 48
         return res
 
     # ------------------------------------------------------------------ timers

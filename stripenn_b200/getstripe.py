@@ -162,60 +162,88 @@ class getStripe:
         avail, live = self.dev.row_flags(cid, np.array(geom, dtype=np.int64))
         return geom, avail, live
 
+    def background_chromosomes(self):
+        """chromnames2 after the size budget (getStripe.py:242-247): chromosomes whose share of
+        1000 samples by size is non-zero."""
+        _, nz1 = self._budget(self.all_chromsizes)
+        return [self.all_chromnames[i] for i in nz1]
+
+    def available_counts(self, chroms):
+        """available_cols (getStripe.py:249-273) for some chromosomes -> {chrom: count}.  The
+        flags stay cached for plan_chromosome."""
+        if not hasattr(self, "_flag_cache"):
+            self._flag_cache = {}
+        out = {}
+        for c in chroms:
+            if c not in self._flag_cache:
+                self._flag_cache[c] = self._flags(c)
+            out[c] = int(self._flag_cache[c][1].sum())
+        return out
+
+    def sample_budget(self, names2, avail: Dict[str, int]):
+        """getStripe.py:278-283 -> (chromnames2 after the availability budget, samplesize)."""
+        budget, nz2 = self._budget([avail[c] for c in names2])
+        return [names2[i] for i in nz2], budget
+
+    def plan_chromosome(self, chrom, ss):
+        """Sample specs of one chromosome (getStripe.py:296-346, 416-440) as an (n, 6) int32
+        array {i0, i1, j0, j1, x, shift}.  RNG convention: a fresh random.Random(seed) per
+        chromosome — what every loky task of the reference sees with -n >= 2."""
+        prng = random.Random(self.seed)
+        csize, itera, unit = self._units(chrom)
+        if not hasattr(self, "_flag_cache"):
+            self._flag_cache = {}
+        if chrom not in self._flag_cache:
+            self._flag_cache[chrom] = self._flags(chrom)
+        geom, _, live = self._flag_cache[chrom]
+        specs, n_pool = [], []
+        it = 0
+
+        def pool_of(g, first):
+            _, _, i0, i1, j0, j1 = g
+            x = np.arange(i1 - i0)
+            ok = (live[i0:i1] != 0) & (x > 20) & (x < unit - 20)
+            if first:
+                ok &= (x > 410) & (x < (j1 - j0))
+            return x[ok].tolist()
+
+        for it in range(itera):
+            sss = int(ss / itera)
+            g = geom[it]
+            pool = pool_of(g, it == 0)
+            n_pool.append(len(pool))
+            if len(pool) == 0:
+                continue
+            k = len(pool) if len(pool) < sss else sss
+            for x in prng.choices(pool, k=k):
+                specs.append((g[2], g[3], g[4], g[5], x, 400 if it > 0 else 0))
+        depl = ss - len(specs)
+        if depl > 0:
+            rich = int(np.argmax(n_pool))
+            g = geom[rich]
+            pool = pool_of(g, False)
+            for x in prng.choices(pool, k=depl):
+                specs.append((g[2], g[3], g[4], g[5], x, 400 if it > 0 else 0))  # stale `it`
+        return np.array(specs, dtype=np.int32).reshape(-1, 6)
+
     def plan_samples(self):
-        """Everything of nulldist that decides WHICH rows are sampled (getStripe.py:242-247,
-        278-283, 296-346, 416-440).  RNG convention: a fresh random.Random(seed) per chromosome —
-        what every loky task of the reference sees with -n >= 2."""
-        v1, nz1 = self._budget(self.all_chromsizes)
-        names2 = [self.all_chromnames[i] for i in nz1]
-        flags = {c: self._flags(c) for c in names2}
-        avail = [int(flags[c][1].sum()) for c in names2]
-        budget, nz2 = self._budget(avail)
-        names2 = [names2[i] for i in nz2]
-        plans = []
-        for chrom in names2:
-            prng = random.Random(self.seed)
-            ss = int(budget[names2.index(chrom)])  # indexes the UNfiltered budget (reference quirk)
-            csize, itera, unit = self._units(chrom)
-            geom, _, live = flags[chrom]
-            specs, n_pool = [], []
-            it = 0
+        """Everything of nulldist that decides WHICH rows are sampled."""
+        names2 = self.background_chromosomes()
+        avail = self.available_counts(names2)
+        names2b, budget = self.sample_budget(names2, avail)
+        # samplesize[c] indexes the UNfiltered budget with the filtered position (reference quirk)
+        plans = [self.plan_chromosome(c, int(budget[names2b.index(c)])) for c in names2b]
+        return names2b, plans
 
-            def pool_of(g, first):
-                _, _, i0, i1, j0, j1 = g
-                x = np.arange(i1 - i0)
-                ok = (live[i0:i1] != 0) & (x > 20) & (x < unit - 20)
-                if first:
-                    ok &= (x > 410) & (x < (j1 - j0))
-                return x[ok].tolist()
-
-            for it in range(itera):
-                sss = int(ss / itera)
-                g = geom[it]
-                pool = pool_of(g, it == 0)
-                n_pool.append(len(pool))
-                if len(pool) == 0:
-                    continue
-                k = len(pool) if len(pool) < sss else sss
-                for x in prng.choices(pool, k=k):
-                    specs.append((g[2], g[3], g[4], g[5], x, 400 if it > 0 else 0))
-            depl = ss - len(specs)
-            if depl > 0:
-                rich = int(np.argmax(n_pool))
-                g = geom[rich]
-                pool = pool_of(g, False)
-                for x in prng.choices(pool, k=depl):
-                    specs.append((g[2], g[3], g[4], g[5], x, 400 if it > 0 else 0))  # stale `it`
-            plans.append(np.array(specs, dtype=np.int32).reshape(-1, 6))
-        return names2, plans
+    def background_columns(self, chrom, spec):
+        """main_null_calc's four tables for one chromosome -> array (4, 400, n)."""
+        cid = self.unbalLib.ensure(chrom)
+        return self.dev.background(cid, spec)
 
     def nulldist(self):
         """getStripe.py:238-499 -> bgleft_up, bgright_up, bgleft_down, bgright_down."""
         names2, plans = self.plan_samples()
-        parts = []
-        for chrom, spec in zip(names2, plans):
-            cid = self.unbalLib.ensure(chrom)
-            parts.append(self.dev.background(cid, spec))
+        parts = [self.background_columns(chrom, spec) for chrom, spec in zip(names2, plans)]
         if parts:
             full = np.concatenate(parts, axis=2)
         else:
@@ -240,13 +268,13 @@ class getStripe:
         return df
 
     def extract_all(self, MP, quantiles: Sequence[float], bgleft_up, bgright_up, bgleft_down,
-                    bgright_down, frame_range=None):
+                    bgright_down, frame_range=None, chroms=None):
         """``extract`` for every maxpixel value at once: the device builds each search window
         once and runs all Q x 6 brightness passes on it.  Returns one DataFrame per quantile,
         identical to what the reference's per-quantile loop (stripenn.py:134-138) collects."""
         per_q: List[List[pd.DataFrame]] = [[] for _ in quantiles]
         weights = gaussian_weights(self.canny)
-        for ci, chrom in enumerate(self.chromnames):
+        for ci, chrom in enumerate(self.chromnames if chroms is None else chroms):
             cid = self.unbalLib.ensure(chrom)
             lo, hi = (0, None) if frame_range is None else frame_range
             cand = self.dev.extract(cid, np.asarray(MP[chrom], dtype=np.float64), self.canny, self.minH,

@@ -41,6 +41,9 @@ def table_arrays(df, prefix, cols=TABLE_COLS):
         v = df[c].to_numpy()
         if c in ("chr", "chr2", "maxpixel"):
             v = v.astype(str)
+        elif v.dtype == object:      # pandas keeps list-built columns as object
+            f = np.array([float(x) for x in v])
+            v = f.astype(np.int64) if np.all(f == np.floor(f)) and c not in ("Mean", "pvalue", "Stripiness") else f
         out[prefix + c] = v
     return out
 

@@ -1,0 +1,273 @@
+"""GPU (-m gpu): parity of the CUDA path, called through the C ABI, against the oracle on the
+same seeded inputs and against the golden fixtures produced by the unmodified reference.
+Bar: coordinates / maxpixel / masks / float32 images bit-exact; Mean, pvalue, Stripiness
+within 1e-5 relative (the north star's tolerance; observed ~1e-15)."""
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from snn_oracle import background as bgm
+from snn_oracle import canny as cn
+from snn_oracle import driver
+from snn_oracle import image as im
+from snn_oracle import pipeline as pl
+from snn_oracle import segments as sg
+from snn_oracle.matrix import OracleMatrix
+from stripenn_b200 import _lib
+from stripenn_b200 import compute as cp
+from stripenn_b200 import getstripe as gs
+from stripenn_b200 import synth
+from stripenn_b200.score import score_table
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+BG = ("blu", "bru", "bld", "brd")
+
+
+def _obj(cm, norm, dev, **kw):
+    bal = cp.resolve_norm(cm, norm, "compute", False)
+    all_names, all_sizes, names, sizes = cp.compute_chromosomes(cm, ["all"])
+    o = cp.make_object(cm, bal, dev, all_names, all_sizes, names, sizes, kw.get("minL", 10), kw.get("maxW", 8),
+                       kw.get("canny", 2.0), 1, kw.get("bfilter", 3), 123456789, kw.get("gray_variant", 0))
+    return o, OracleMatrix(cm, bal), names, all_names, all_sizes
+
+
+def _unload_all(dev):
+    for cid in list(dev.loaded):
+        dev.unload_chrom(cid)
+
+
+@pytest.fixture()
+def dev(device):
+    _unload_all(device)
+    yield device
+    _unload_all(device)
+
+
+@pytest.mark.parametrize("cfg,norm", [("tiny", "None"), ("tiny2", "KR"), ("tiny2", "weight")])
+def test_band_quantiles_expected(dev, cfg, norm):
+    cm = synth.make_config(cfg)
+    obj, mat, names, _, _ = _obj(cm, norm, dev)
+    qs = [0.0, 0.5, 0.95, 0.96, 0.97, 0.98, 0.99, 0.999, 1.0]
+    MP = obj.getQuantile_original(cm, names, qs)
+    EV = obj.mpmean()
+    EVo = bgm.expected_by_distance(mat, names)
+    for c in names:
+        cid = obj.unbalLib.chrom_id(c)
+        a = dev.fetch(cid, 300, 700, 250, 700)
+        assert np.array_equal(a, mat.window(c, 300, 700, 250, 700).astype(float), equal_nan=True)
+        assert np.array_equal(MP[c], np.quantile(mat.positive_population(c), qs)), c
+        np.testing.assert_allclose(EV[c], EVo[c], rtol=1e-12)
+    with pytest.raises(ValueError):
+        dev.quantiles(obj.unbalLib.chrom_id(names[0]), [1.5])
+    with pytest.raises(_lib.StripennB200Error):
+        dev.fetch(obj.unbalLib.chrom_id(names[0]), 0, 10, 1000, 1010)   # outside the band
+
+
+@pytest.mark.parametrize("cfg,norm", [("tiny", "None"), ("tiny2", "KR")])
+def test_background_exact(dev, cfg, norm):
+    cm = synth.make_config(cfg)
+    obj, mat, names, all_names, all_sizes = _obj(cm, norm, dev)
+    n2, plans = obj.plan_samples()
+    n2o, planso = bgm.plan_samples(mat, all_names, all_sizes, 123456789)
+    assert n2 == n2o
+    for a, b in zip(plans, planso):
+        assert np.array_equal(a, np.array(b, dtype=np.int32).reshape(-1, 6))
+    bg = obj.nulldist()
+    bgo = bgm.null_distribution(mat, all_names, all_sizes, 123456789)
+    for a, b in zip(bg, bgo):
+        assert a.shape == b.shape
+        assert np.array_equal(np.isnan(a), np.isnan(b))
+        np.testing.assert_allclose(a, b, rtol=1e-12, atol=1e-12, equal_nan=True)
+
+
+def test_background_far_pixels_use_csr(dev):
+    """A sample whose column offset is stale (+400 on a window that starts at bin 0) reaches
+    offsets ~800 > band width: the kernel must answer from the CSR pixels, not with zeros."""
+    cm = synth.make_config("tiny")
+    obj, mat, names, _, _ = _obj(cm, "None", dev)
+    cid = obj.unbalLib.ensure("T1")
+    assert dev.loaded[cid]["bw"] < 600
+    spec = [(0, 599, 0, 999, x, 400) for x in (30, 200, 450)]
+    got = dev.background(cid, np.array(spec, dtype=np.int32))
+    want = bgm.background_columns(mat, "T1", spec)
+    for t in range(4):
+        np.testing.assert_allclose(got[t], want[t], rtol=1e-12, atol=1e-12, equal_nan=True)
+    assert np.nanmax(np.abs(want[2])) > 0
+
+
+def test_stage_images_match_reference_golden(dev, tiny_cm, golden_dir):
+    g = np.load(os.path.join(golden_dir, "tiny_stages.npz"))
+    obj, mat, names, _, _ = _obj(tiny_cm, "None", dev)
+    cid = obj.unbalLib.ensure("T1")
+    M = float(g["M"])
+    for idx in (0, 5):
+        for b in range(6):
+            d = dev.debug_stages(cid, M, 2.0, 3, idx, b)
+            assert d["S"] == int(g["f%d_S" % idx])
+            assert np.array_equal(d["nz"], g["f%d_nz" % idx])
+            if "f%d_gray%d" % (idx, b) in g:
+                assert np.array_equal(d["gray"], g["f%d_gray%d" % (idx, b)])
+            assert float(d["gray"].astype(np.float64).sum()) == float(g["f%d_graysum%d" % (idx, b)])
+            assert np.array_equal(np.packbits(d["edges"].astype(bool)), g["f%d_edges%d" % (idx, b)])
+            assert np.array_equal(np.packbits(d["vert"].astype(bool)), g["f%d_vert%d" % (idx, b)])
+
+
+@pytest.mark.parametrize("sigma,bf,variant", [(2.0, 3, 0), (2.5, 1, 0), (2.0, 5, 1), (1.5, 3, 2)])
+def test_stage_images_match_oracle(dev, tiny2_cm, sigma, bf, variant):
+    obj, mat, names, _, _ = _obj(tiny2_cm, "KR", dev)
+    c = "chrA"
+    cid = obj.unbalLib.ensure(c)
+    M = float(np.quantile(mat.positive_population(c), 0.96))
+    w = cn.gaussian_weights(sigma)
+    for idx in (1, 4, 11):
+        fr = pl.load_frame(mat, c, idx)
+        G = im.saturate(fr["D"], M)
+        for b in (0, 3, 5):
+            d = dev.debug_stages(cid, M, sigma, bf, idx, b, variant)
+            gray = im.gray_image(G, im.BRIGHTNESS[b], bf, variant)
+            st = cn.canny(gray, sigma, w, None, return_stages=True)
+            assert d["S"] == fr["S"]
+            assert np.array_equal(d["gray"], gray)
+            assert np.array_equal(d["smoothed"], st["smoothed"])
+            assert np.array_equal(d["mag"], st["mag"])
+            assert np.array_equal(d["low"].astype(bool), st["low"])
+            assert np.array_equal(d["edges"].astype(bool), st["edges"])
+            assert np.array_equal(d["vert"], sg.vertical_line(st["edges"]))
+
+
+def _raw_oracle(mat, c, M, minH, maxW, sigma, bf, frames):
+    w = cn.gaussian_weights(sigma)
+    out = {}
+    for idx in frames:
+        fr = pl.load_frame(mat, c, idx)
+        if fr is None:
+            out[idx] = None
+            continue
+        G = im.saturate(fr["D"], M)
+        bleed = cn.bleed_over((fr["S"], fr["S"]), *w)
+        rows = []
+        for bi, b in enumerate(im.BRIGHTNESS):
+            gray = im.gray_image(G, b, bf)
+            edges = cn.canny(gray, sigma, w, bleed)
+            vert = sg.vertical_line(edges)
+            for (x, y, ww, hh) in sg.search_pass(edges, vert, minH, maxW):
+                rows.append((bi, x, y, ww, hh, int(fr["sa"][x]), int(fr["ea"][x + ww - 1]), int(fr["sa"][y]),
+                             int(fr["ea"][y + hh - 1])))
+        out[idx] = rows
+    return out
+
+
+@pytest.mark.parametrize("cfg,norm,minH,maxW", [("tiny", "None", 10, 8), ("tiny2", "KR", 10, 8), ("tiny", "None", 5, 12)])
+def test_raw_candidates_match_oracle(dev, cfg, norm, minH, maxW):
+    cm = synth.make_config(cfg)
+    obj, mat, names, _, _ = _obj(cm, norm, dev)
+    for c in names:
+        cid = obj.unbalLib.ensure(c)
+        mp = np.quantile(mat.positive_population(c), [0.95, 0.99])
+        cand = dev.extract(cid, mp, 2.0, minH, maxW, 3)
+        nfr = pl.n_frames(mat.nbins(c))
+        for qi in range(2):
+            want = _raw_oracle(mat, c, mp[qi], minH, maxW, 2.0, 3, range(nfr))
+            for idx in range(nfr):
+                sel = cand[(cand["q"] == qi) & (cand["frame"] == idx)]
+                got = [(int(r["bright"]), int(r["x"]), int(r["y"]), int(r["w"]), int(r["h"]), int(r["pos1"]),
+                        int(r["pos2"]), int(r["pos3"]), int(r["pos4"])) for r in sel]
+                assert got == (want[idx] or []), (c, qi, idx)
+        # sharding by window range returns the same records
+        a = dev.extract(cid, mp, 2.0, minH, maxW, 3, 0, nfr // 2)
+        b = dev.extract(cid, mp, 2.0, minH, maxW, 3, nfr // 2, nfr)
+        both = np.concatenate([a, b])
+        both = both[np.lexsort((both["k"], both["ud"], both["bright"], both["frame"], both["q"]))]
+        assert np.array_equal(both, cand)
+
+
+def _cmp_golden(unf, fil, g):
+    for df, pre in ((unf, "unf_"), (fil, "fil_")):
+        assert len(df) == len(g[pre + "pos1"])
+        for k in ("pos1", "pos2", "pos3", "pos4", "length", "width"):
+            assert df[k].astype(np.int64).tolist() == g[pre + k].tolist(), (pre, k)
+        assert df["chr"].astype(str).tolist() == g[pre + "chr"].tolist()
+        assert df["maxpixel"].tolist() == g[pre + "maxpixel"].tolist()
+        for k in ("Mean", "pvalue", "Stripiness"):
+            np.testing.assert_allclose(df[k].to_numpy(dtype=float), g[pre + k], rtol=RTOL, atol=0, equal_nan=True)
+
+
+def test_compute_matches_reference_tiny(dev, tiny_cm, golden_dir):
+    g = np.load(os.path.join(golden_dir, "tiny_compute.npz"))
+    unf, fil, st = cp.run_stages(tiny_cm, norm="None", maxpixel="0.95,0.96,0.97,0.98,0.99", device=dev,
+                                 return_stages=True)
+    _cmp_golden(unf, fil, g)
+    assert np.array_equal(st["MP"]["T1"], g["MP_T1"])
+    np.testing.assert_allclose(st["EV"]["T1"], g["EV_T1"], rtol=1e-12)
+    for name, t in zip(BG, st["bg"]):
+        np.testing.assert_allclose(t[:, ::25], g["bg_" + name], rtol=1e-12, atol=1e-12, equal_nan=True)
+    for i, t in enumerate(st["per_q"]):
+        for k in ("pos1", "pos2", "pos3", "pos4", "num", "x", "y", "h", "w"):
+            assert t[k].astype(np.int64).tolist() == g["q%d_%s" % (i, k)].tolist(), (i, k)
+        np.testing.assert_allclose(t["pvalue"].to_numpy(dtype=float), g["q%d_pvalue" % i], rtol=RTOL)
+
+
+def test_compute_matches_reference_tiny2_kr(dev, tiny2_cm, golden_dir):
+    g = np.load(os.path.join(golden_dir, "tiny2_compute.npz"))
+    unf, fil = cp.run_stages(tiny2_cm, norm="KR", maxpixel="0.95,0.98", device=dev)
+    _cmp_golden(unf, fil, g)
+
+
+def test_compute_subset_of_chromosomes(dev, tiny2_cm):
+    """-k chrB: the background still samples every chromosome of the file (getStripe.py:242,276)."""
+    unf, fil = cp.run_stages(tiny2_cm, norm="KR", chrom="chrB", maxpixel="0.97", device=dev)
+    ounf, ofil = driver.compute(tiny2_cm, norm="KR", chrom="chrB", maxpixel="0.97")
+    assert len(unf) == len(ounf["pos1"]) > 0
+    for k in ("pos1", "pos2", "pos3", "pos4"):
+        assert unf[k].astype(np.int64).tolist() == list(ounf[k])
+    for k in ("Mean", "pvalue", "Stripiness"):
+        np.testing.assert_allclose(unf[k].to_numpy(dtype=float), np.array(ounf[k], float), rtol=RTOL, equal_nan=True)
+
+
+def test_score_matches_reference(dev, tiny2_cm, golden_dir):
+    g = np.load(os.path.join(golden_dir, "tiny2_score.npz"))
+    df = pd.DataFrame({"chr": g["chr"], "pos1": g["pos1"], "pos2": g["pos2"], "chr2": g["chr2"],
+                       "pos3": g["pos3"], "pos4": g["pos4"]})
+    res = score_table(tiny2_cm, df, norm="KR", device=dev)
+    for k in ("pvalue_added", "Stripiness_added", "O_Mean_added", "O_Sum_added", "O/E_Mean_added", "O/E_Total_added"):
+        np.testing.assert_allclose(res[k].to_numpy(dtype=float), g[k.replace("/", "_")], rtol=RTOL, atol=0,
+                                   equal_nan=True)
+
+
+def test_small_and_empty_windows(dev):
+    """Ragged inputs: a chromosome shorter than one window, windows inside an all-zero gap
+    (skipped: <= 10 non-empty columns) and a chromosome without pixels."""
+    cm = synth.make_map([("s", 230 * 5000 - 17), ("e", 900 * 5000)], 5000, seed=11, only=["s"])
+    cm.chroms["e"] = type(cm.chroms["s"])("e", 900 * 5000, 900, np.zeros(0, np.int32), np.zeros(0, np.int32),
+                                          np.zeros(0, np.int32))
+    mat = OracleMatrix(cm, False)
+    lib = gs.DeviceMatrix(cm, False, dev)
+    cid = lib.ensure("s")
+    mp = np.quantile(mat.positive_population("s"), [0.95])
+    cand = dev.extract(cid, mp, 2.0, 10, 8, 3)
+    want = _raw_oracle(mat, "s", mp[0], 10, 8, 2.0, 3, range(pl.n_frames(230)))
+    got = {}
+    for r in cand:
+        got.setdefault(int(r["frame"]), []).append((int(r["bright"]), int(r["x"]), int(r["y"]), int(r["w"]),
+                                                    int(r["h"]), int(r["pos1"]), int(r["pos2"]), int(r["pos3"]),
+                                                    int(r["pos4"])))
+    for idx, rows in want.items():
+        assert got.get(idx, []) == (rows or [])
+    cid = lib.ensure("e")
+    assert len(dev.extract(cid, np.array([5.0]), 2.0, 10, 8, 3)) == 0
+    assert np.isnan(dev.quantiles(cid, [0.5])).all()
+    assert np.array_equal(dev.expected(cid), np.zeros(400))
+
+
+def test_load_errors(dev):
+    with pytest.raises(_lib.StripennB200Error) as e:
+        dev.load_chrom(0, 100, 5000, 500000, [5, 3], [6, 4], [1, 1])       # not sorted
+    assert "sorted" in str(e.value)
+    with pytest.raises(_lib.StripennB200Error):
+        dev.load_chrom(0, 100, 5000, 500000, [5], [3], [1])                # lower triangle
+    with pytest.raises(_lib.StripennB200Error) as e:
+        dev.quantiles(7, [0.5])
+    assert e.value.code == _lib.ESTATE
