@@ -56,8 +56,8 @@ def test_band_quantiles_expected(dev, cfg, norm):
     EVo = bgm.expected_by_distance(mat, names)
     for c in names:
         cid = obj.unbalLib.chrom_id(c)
-        a = dev.fetch(cid, 300, 700, 250, 700)
-        assert np.array_equal(a, mat.window(c, 300, 700, 250, 700).astype(float), equal_nan=True)
+        a = dev.fetch(cid, 300, 700, 280, 690)
+        assert np.array_equal(a, mat.window(c, 300, 700, 280, 690).astype(float), equal_nan=True)
         assert np.array_equal(MP[c], np.quantile(mat.positive_population(c), qs)), c
         np.testing.assert_allclose(EV[c], EVo[c], rtol=1e-12)
     with pytest.raises(ValueError):
@@ -177,8 +177,8 @@ def test_raw_candidates_match_oracle(dev, cfg, norm, minH, maxW):
                         int(r["pos2"]), int(r["pos3"]), int(r["pos4"])) for r in sel]
                 assert got == (want[idx] or []), (c, qi, idx)
         # sharding by window range returns the same records
-        a = dev.extract(cid, mp, 2.0, minH, maxW, 3, 0, nfr // 2)
-        b = dev.extract(cid, mp, 2.0, minH, maxW, 3, nfr // 2, nfr)
+        a = dev.extract(cid, mp, 2.0, minH, maxW, 3, frame_lo=0, frame_hi=nfr // 2)
+        b = dev.extract(cid, mp, 2.0, minH, maxW, 3, frame_lo=nfr // 2, frame_hi=nfr)
         both = np.concatenate([a, b])
         both = both[np.lexsort((both["k"], both["ud"], both["bright"], both["frame"], both["q"]))]
         assert np.array_equal(both, cand)

@@ -35,7 +35,7 @@ def test_cfg1_properties(device, cfg1):
     key = np.lexsort((cand["k"], cand["ud"], cand["bright"], cand["frame"], cand["q"]))
     assert np.array_equal(key, np.arange(len(cand)))
     # window-range shards (what a multi-GPU split of one chromosome does) == whole
-    parts = [device.extract(cid, mp, 2.0, 10, 8, 3, lo, hi) for lo, hi in ((0, 13), (13, 50), (50, 99))]
+    parts = [device.extract(cid, mp, 2.0, 10, 8, 3, frame_lo=lo, frame_hi=hi) for lo, hi in ((0, 13), (13, 50), (50, 99))]
     both = np.concatenate(parts)
     both = both[np.lexsort((both["k"], both["ud"], both["bright"], both["frame"], both["q"]))]
     assert np.array_equal(both, cand)
