@@ -3,6 +3,7 @@
 // background.cu, image.cu, search.cu and score.cu; dedup.cpp is host-only.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "snn_internal.cuh"
@@ -124,6 +125,10 @@ int snn_create(int device, snn_ctx** out) {
         return snn_cuda_fail(nullptr, e, "cudaStreamCreate");
     }
     ctx->stream = ctx->own_stream;
+    {
+        const char* g = getenv("SNN_FORCE_GENERIC");
+        ctx->force_generic = g && g[0] == '1';
+    }
     *out = ctx;
     return SNN_OK;
 }

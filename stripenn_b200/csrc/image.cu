@@ -374,26 +374,42 @@ int snn_image_chain(snn_ctx* ctx, SnnChrom* c, const ExtractPlan& pl, int frame0
         k_bleed<<<dim3(13, 13, nf), dim3(32, 8), 0, ctx->stream>>>(pl.info, pl.gauss, pl.bleed);
         SNN_LAUNCH_CHECK("k_bleed");
     }
+    const bool generic = ctx->force_generic;
     {
         SnnScope scope(ctx, ST_GRAY, 1);
-        int T = 32 + pl.gray.bf - 1;
-        k_gray<<<dim3(13, 13, npass), dim3(32, 8), (size_t)T * T * sizeof(double), ctx->stream>>>(pl.Dc, pl.info,
-                                                                                                 pl.gray, pl.bufA);
-        SNN_LAUNCH_CHECK("k_gray");
+        if (!generic && pl.gray.bf == 3) {
+            int rc = snn_launch_gray6(ctx, pl, nf);
+            if (rc) return rc;
+        } else {
+            int T = 32 + pl.gray.bf - 1;
+            k_gray<<<dim3(13, 13, npass), dim3(32, 8), (size_t)T * T * sizeof(double), ctx->stream>>>(
+                pl.Dc, pl.info, pl.gray, pl.bufA);
+            SNN_LAUNCH_CHECK("k_gray");
+        }
     }
     {
         SnnScope scope(ctx, ST_GAUSS, 2);
-        k_gauss_v<<<dim3(13, 13, npass), dim3(32, 8), 0, ctx->stream>>>(pl.bufA, pl.info, ppf, pl.gauss, pl.bufB);
-        SNN_LAUNCH_CHECK("k_gauss_v");
-        k_gauss_h<<<dim3(13, 13, npass), dim3(32, 8), 0, ctx->stream>>>(pl.bufB, pl.info, ppf, pl.gauss, pl.bleed,
-                                                                         pl.bufC);
-        SNN_LAUNCH_CHECK("k_gauss_h");
+        if (!generic && snn_gauss_fast_supported(pl.gauss.radius)) {
+            int rc = snn_launch_gauss_fast(ctx, pl, npass, ppf);
+            if (rc) return rc;
+        } else {
+            k_gauss_v<<<dim3(13, 13, npass), dim3(32, 8), 0, ctx->stream>>>(pl.bufA, pl.info, ppf, pl.gauss, pl.bufB);
+            SNN_LAUNCH_CHECK("k_gauss_v");
+            k_gauss_h<<<dim3(13, 13, npass), dim3(32, 8), 0, ctx->stream>>>(pl.bufB, pl.info, ppf, pl.gauss,
+                                                                             pl.bleed, pl.bufC);
+            SNN_LAUNCH_CHECK("k_gauss_h");
+        }
     }
     {
         SnnScope scope(ctx, ST_NMS, 1);
-        k_sobel_nms<<<dim3(13, 13, npass), dim3(32, 8), 0, ctx->stream>>>(pl.bufC, pl.info, ppf, pl.low, pl.high,
-                                                                           mag_dbg);
-        SNN_LAUNCH_CHECK("k_sobel_nms");
+        if (!generic) {
+            int rc = snn_launch_sobel_nms2(ctx, pl, npass, ppf, mag_dbg);
+            if (rc) return rc;
+        } else {
+            k_sobel_nms<<<dim3(13, 13, npass), dim3(32, 8), 0, ctx->stream>>>(pl.bufC, pl.info, ppf, pl.low, pl.high,
+                                                                               mag_dbg);
+            SNN_LAUNCH_CHECK("k_sobel_nms");
+        }
     }
     return SNN_OK;
 }

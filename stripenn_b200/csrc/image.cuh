@@ -52,4 +52,8 @@ struct ExtractPlan {
     snn_candidate* cand;  // finished candidates (device)
 };
 
+int snn_launch_gray6(snn_ctx* ctx, const ExtractPlan& pl, int nf);
+bool snn_gauss_fast_supported(int radius);
+int snn_launch_gauss_fast(snn_ctx* ctx, const ExtractPlan& pl, int npass, int ppf);
+int snn_launch_sobel_nms2(snn_ctx* ctx, const ExtractPlan& pl, int npass, int ppf, float* mag_dbg);
 int snn_image_chain(snn_ctx* ctx, SnnChrom* c, const ExtractPlan& pl, int frame0, int nf, float* mag_dbg);

@@ -1,0 +1,348 @@
+// Specialised (default-parameter) versions of the image-chain kernels of image.cu.  Same
+// arithmetic, same operation order, bit-identical outputs (tests compare both paths with the
+// oracle); what changes is how often each value is converted and re-read:
+//   k_gray6        one CTA computes saturate(D, M) once per tile and emits all 6 brightness
+//                  passes from shared memory (2 float64 divisions per pixel instead of 12)
+//   k_gauss_v8/h8  every thread produces 8 consecutive outputs along the filter axis from
+//                  8 + 2r inputs held in registers: each float32 input is converted to float64
+//                  once per thread (≈3 conversions per output instead of 17)
+//   k_sobel_nms2   derivative images staged once per tile (float32 subtraction is exact
+//                  here, see the comment), [1 2 1] passes from float64 copies in shared memory
+// ncu (profiles/r01a_*): the generic kernels were bound by the conversion (XU) pipe at 64-68 %
+// and by issue slots at 84 %, not by FP64 or HBM.
+#include "image.cuh"
+
+__device__ __forceinline__ int f_reflect101(int i, int n) {
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * n - 2 - i;
+    return i;
+}
+
+// ---- saturate once, six brightness passes (bf = 3) -------------------------------------------
+#define GT 34  // 32 + bf - 1
+__global__ void __launch_bounds__(256) k_gray6(const double* __restrict__ Dc_all, const FrameInfo* __restrict__ info,
+                                               GrayParams P, float* __restrict__ gray_all) {
+    __shared__ double G[GT * GT];
+    __shared__ double Pk[GT * GT];
+    const int fq = blockIdx.z;  // frame * nq + q
+    const int f = fq / P.nq, q = fq - f * P.nq;
+    const int S = info[f].S;
+    const int ty0 = blockIdx.y * 32, tx0 = blockIdx.x * 32;
+    if (ty0 >= S || tx0 >= S) return;
+    const double M = P.mp[q];
+    const double* Dc = Dc_all + (int64_t)f * SNN_SMAX * SNN_SMAX;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    for (int t = tid; t < GT * GT; t += 256) {
+        const int yy = t / GT, xx = t - yy * GT;
+        int r = f_reflect101(ty0 + yy - 1, S), c = f_reflect101(tx0 + xx - 1, S);
+        double g = 0.0;
+        if (r >= 0 && r < S && c >= 0 && c < S) {
+            const double D = Dc[r * SNN_SMAX + c];
+            double blue = (255.0 * (M - D)) / M;   // getStripe.py:889
+            if (blue < 0.0) blue = 0.0;
+            g = blue / 255.0;
+            g = fmin(fmax(g, 0.0), 1.0);
+        }
+        G[t] = g;
+    }
+    const float CR = 0.299f, CG = 0.587f, CB = 0.114f;
+    const int x = threadIdx.x, y0 = threadIdx.y * 4;
+    for (int bi = 0; bi < SNN_NBRIGHT; ++bi) {
+        const double b = P.bright[bi];
+        const double k = (1.0 - 0.0) / (b - 0.0);
+        __syncthreads();  // G ready / previous pass done with Pk
+        for (int t = tid; t < GT * GT; t += 256) {
+            const double g = G[t];
+            double a;
+            if (g != g || g <= 0.0) a = 0.0;      // ImageProcessing.py:17-23 (NaN cells stay 0)
+            else if (g > b) a = 1.0;
+            else a = k * g;
+            Pk[t] = P.kv * a;                     // the tap product of cv.filter2D
+        }
+        __syncthreads();
+        if (tx0 + x < S) {
+            double p[6][3];
+#pragma unroll
+            for (int i = 0; i < 6; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) p[i][j] = Pk[(y0 + i) * GT + x + j];
+            float* gray = gray_all + ((int64_t)fq * SNN_NBRIGHT + bi) * SNN_SMAX * SNN_SMAX;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (ty0 + y0 + i >= S) break;
+                double acc = 0.0;
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) acc = acc + p[i + ky][kx];
+                acc = fmin(fmax(acc, 0.0), 1.0);
+                const float g = (float)acc;
+                float out;
+                if (P.variant == SNN_GRAY_IPP) {
+                    const float t = (P.r32 * CR) + (g * CG);
+                    out = __fmaf_rn(g, CB, t);
+                } else if (P.variant == SNN_GRAY_FMA2) {
+                    const float t = __fmaf_rn(g, CG, P.r32 * CR);
+                    out = __fmaf_rn(g, CB, t);
+                } else {
+                    out = ((P.r32 * CR) + (g * CG)) + (g * CB);
+                }
+                gray[(ty0 + y0 + i) * SNN_SMAX + tx0 + x] = out;
+            }
+        }
+    }
+}
+
+// ---- Gaussian, 8 outputs per thread ---------------------------------------------------------------
+#define NOUT 8
+
+// axis 0: thread = (column, chunk of 8 rows); loads are coalesced across the warp's columns
+template <int R>
+__global__ void __launch_bounds__(256) k_gauss_v8(const float* __restrict__ in_all, const FrameInfo* __restrict__ info,
+                                                  int passes_per_frame, GaussParams G, float* __restrict__ out_all) {
+    const int pass = blockIdx.z;
+    const int S = info[pass / passes_per_frame].S;
+    const int j = blockIdx.x * 32 + threadIdx.x;
+    const int i0 = (blockIdx.y * 8 + threadIdx.y) * NOUT;
+    if (j >= S || i0 >= S) return;
+    const float* in = in_all + (int64_t)pass * SNN_SMAX * SNN_SMAX + j;
+    float* out = out_all + (int64_t)pass * SNN_SMAX * SNN_SMAX + j;
+    double x[NOUT + 2 * R];
+#pragma unroll
+    for (int t = 0; t < NOUT + 2 * R; ++t) {
+        const int r = i0 - R + t;
+        x[t] = (r >= 0 && r < S) ? (double)in[r * SNN_SMAX] : 0.0;
+    }
+    double w[R + 1];
+#pragma unroll
+    for (int t = 0; t <= R; ++t) w[t] = G.w[t];
+#pragma unroll
+    for (int o = 0; o < NOUT; ++o) {
+        if (i0 + o >= S) break;
+        double t = x[o + R] * w[R];
+#pragma unroll
+        for (int k = R; k >= 1; --k) t = t + (x[o + R - k] + x[o + R + k]) * w[R - k];
+        out[(i0 + o) * SNN_SMAX] = (float)t;
+    }
+}
+
+// axis 1 + bleed-over division: thread = (row, chunk of 8 columns); float4 loads
+template <int R>
+__global__ void __launch_bounds__(256) k_gauss_h8(const float* __restrict__ in_all, const FrameInfo* __restrict__ info,
+                                                  int passes_per_frame, GaussParams G,
+                                                  const float* __restrict__ bleed_all, float* __restrict__ out_all) {
+    static_assert(R % 4 == 0 || R == 6 || R == 10, "R must keep 4-float alignment handling simple");
+    const int pass = blockIdx.z;
+    const int f = pass / passes_per_frame;
+    const int S = info[f].S;
+    const int nchunk = (S + NOUT - 1) / NOUT;
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    const int i = t / nchunk;
+    if (i >= S) return;
+    const int j0 = (t - i * nchunk) * NOUT;
+    const float* in = in_all + (int64_t)pass * SNN_SMAX * SNN_SMAX + i * SNN_SMAX;
+    const float* bleed = bleed_all + (int64_t)f * SNN_SMAX * SNN_SMAX + i * SNN_SMAX;
+    float* out = out_all + (int64_t)pass * SNN_SMAX * SNN_SMAX + i * SNN_SMAX;
+    // inputs j0-R .. j0+NOUT+R-1 ; load as aligned float4 groups covering [j0 - RA, j0 + NOUT + RA)
+    constexpr int RA = (R + 3) / 4 * 4;
+    double x[NOUT + 2 * RA];
+#pragma unroll
+    for (int g = 0; g < (NOUT + 2 * RA) / 4; ++g) {
+        const int c = j0 - RA + 4 * g;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c >= 0 && c < SNN_SMAX) v = *reinterpret_cast<const float4*>(in + c);
+        x[4 * g + 0] = (c + 0 >= 0 && c + 0 < S) ? (double)v.x : 0.0;
+        x[4 * g + 1] = (c + 1 >= 0 && c + 1 < S) ? (double)v.y : 0.0;
+        x[4 * g + 2] = (c + 2 >= 0 && c + 2 < S) ? (double)v.z : 0.0;
+        x[4 * g + 3] = (c + 3 >= 0 && c + 3 < S) ? (double)v.w : 0.0;
+    }
+    double w[R + 1];
+#pragma unroll
+    for (int k = 0; k <= R; ++k) w[k] = G.w[k];
+    float res[NOUT];
+#pragma unroll
+    for (int o = 0; o < NOUT; ++o) {
+        double acc = x[o + RA] * w[R];
+#pragma unroll
+        for (int k = R; k >= 1; --k) acc = acc + (x[o + RA - k] + x[o + RA + k]) * w[R - k];
+        res[o] = (float)acc;
+    }
+    const float4 b0 = *reinterpret_cast<const float4*>(bleed + j0);
+    const float4 b1 = *reinterpret_cast<const float4*>(bleed + j0 + 4);
+    float4 o0, o1;
+    o0.x = res[0] / b0.x; o0.y = res[1] / b0.y; o0.z = res[2] / b0.z; o0.w = res[3] / b0.w;
+    o1.x = res[4] / b1.x; o1.y = res[5] / b1.y; o1.z = res[6] / b1.z; o1.w = res[7] / b1.w;
+    // columns >= S inside the last chunk hold don't-care values (never read: every consumer masks
+    // with S); the row pitch (400) keeps the stores inside the row
+    *reinterpret_cast<float4*>(out + j0) = o0;
+    *reinterpret_cast<float4*>(out + j0 + 4) = o1;
+}
+
+// ---- Sobel + magnitude + NMS ------------------------------------------------------------------------
+__device__ __forceinline__ int f_symm(int i, int n) {
+    if (i < 0) i = -i - 1;
+    if (i >= n) i = 2 * n - 1 - i;
+    return i;
+}
+
+// ndi.sobel's derivative pass computes (x[i-1] - x[i+1]) * -1 in float64 and stores float32.
+// For float32 operands that equals the float32 subtraction: when the exponents are within 2^29
+// the float64 difference is exact (one rounding either way); otherwise the smaller operand is
+// below 2^-29 of the larger, far from any float32 rounding boundary.  So the derivative images
+// are built with __fsub_rn; the [1 2 1] pass keeps the reference's float64 accumulation.
+__global__ void __launch_bounds__(256) k_sobel_nms2(const float* __restrict__ sm_all, const FrameInfo* __restrict__ info,
+                                                    int passes_per_frame, uint32_t* __restrict__ low_all,
+                                                    uint32_t* __restrict__ high_all, float* __restrict__ mag_dbg) {
+    __shared__ float sm[36][37];     // smoothed, tile + halo 2 (reflected)
+    __shared__ double di[34][37];    // d/d(axis 0) at rows r-1..r+32, cols c-2..c+33 (cols 0..35)
+    __shared__ double dj[36][35];    // d/d(axis 1) at rows r-2..r+33 (rows 0..35), cols c-1..c+32
+    __shared__ float si[34][35], sj[34][35], mg[34][35];
+    const int pass = blockIdx.z;
+    const int S = info[pass / passes_per_frame].S;
+    const int ty0 = blockIdx.y * 32, tx0 = blockIdx.x * 32;
+    if (ty0 >= S) return;
+    uint32_t* low = low_all + (int64_t)pass * SNN_SMAX * SNN_WPR;
+    uint32_t* high = high_all + (int64_t)pass * SNN_SMAX * SNN_WPR;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    if (tx0 >= S) {
+        if (tid < 32 && ty0 + tid < S) {
+            low[(ty0 + tid) * SNN_WPR + blockIdx.x] = 0u;
+            high[(ty0 + tid) * SNN_WPR + blockIdx.x] = 0u;
+        }
+        return;
+    }
+    const float* smo = sm_all + (int64_t)pass * SNN_SMAX * SNN_SMAX;
+    for (int t = tid; t < 36 * 36; t += 256) {
+        const int yy = t / 36, xx = t - yy * 36;
+        const int r = f_symm(ty0 + yy - 2, S), c = f_symm(tx0 + xx - 2, S);
+        float v = 0.f;
+        if (r >= 0 && r < S && c >= 0 && c < S) v = smo[r * SNN_SMAX + c];
+        sm[yy][xx] = v;
+    }
+    __syncthreads();
+    // derivative images.  di[a][b]: image row ty0-1+a, image col tx0-2+b  (sm row a+1, col b)
+    for (int t = tid; t < 34 * 36; t += 256) {
+        const int a = t / 36, b = t - a * 36;
+        di[a][b] = (double)(-__fsub_rn(sm[a][b], sm[a + 2][b]));
+    }
+    // dj[a][b]: image row ty0-2+a, image col tx0-1+b  (sm row a, col b+1)
+    for (int t = tid; t < 36 * 34; t += 256) {
+        const int a = t / 34, b = t - a * 34;
+        dj[a][b] = (double)(-__fsub_rn(sm[a][b], sm[a][b + 2]));
+    }
+    __syncthreads();
+    for (int t = tid; t < 34 * 34; t += 256) {
+        const int yy = t / 34, xx = t - yy * 34;
+        const int r = ty0 + yy - 1, c = tx0 + xx - 1;
+        float is = 0.f, js = 0.f, m = 0.f;
+        if (r >= 0 && r < S && c >= 0 && c < S) {
+            // [1 2 1] along axis 1 of the axis-0 derivative; neighbours outside the image reflect
+            // onto the pixel's own column (the derivative image is what scipy pads)
+            const int bc = xx + 1;  // di column of image col c
+            const int bl = (c - 1 < 0) ? bc : bc - 1, br = (c + 1 >= S) ? bc : bc + 1;
+            is = (float)(di[yy][bc] * 2.0 + (di[yy][bl] + di[yy][br]) * 1.0);
+            const int ar = yy + 1;  // dj row of image row r
+            const int au = (r - 1 < 0) ? ar : ar - 1, ad = (r + 1 >= S) ? ar : ar + 1;
+            js = (float)(dj[ar][xx] * 2.0 + (dj[au][xx] + dj[ad][xx]) * 1.0);
+            float mm = is * is;
+            mm = mm + js * js;
+            m = sqrtf(mm);
+        }
+        si[yy][xx] = is;
+        sj[yy][xx] = js;
+        mg[yy][xx] = m;
+    }
+    __syncthreads();
+    const int x = threadIdx.x;
+#pragma unroll
+    for (int yi = 0; yi < 4; ++yi) {
+        const int y = threadIdx.y + 8 * yi;
+        const int r = ty0 + y, c = tx0 + x;
+        bool keep = false, strong = false;
+        if (r < S && c < S) {
+            const int Y = y + 1, X = x + 1;
+            const float m = mg[Y][X];
+            if (mag_dbg) mag_dbg[(int64_t)pass * SNN_SMAX * SNN_SMAX + r * SNN_SMAX + c] = m;
+            if (r >= 1 && r <= S - 2 && c >= 1 && c <= S - 2 && m >= 0.1f) {
+                const float is = si[Y][X], js = sj[Y][X];
+                const bool up = is >= 0.f, down = is <= 0.f, right = js >= 0.f, left = js <= 0.f;
+                const bool cond1 = (up && right) || (down && left);
+                const bool cond2 = (down && right) || (up && left);
+                const float ai = fabsf(is), aj = fabsf(js);
+                float w = 0.f, n11 = 0.f, n12 = 0.f, n21 = 0.f, n22 = 0.f;
+                bool ok = true;
+                if (cond1) {
+                    if (ai > aj) {
+                        w = aj / ai;
+                        n11 = mg[Y + 1][X]; n12 = mg[Y + 1][X + 1]; n21 = mg[Y - 1][X]; n22 = mg[Y - 1][X - 1];
+                    } else {
+                        w = ai / aj;
+                        n11 = mg[Y][X + 1]; n12 = mg[Y + 1][X + 1]; n21 = mg[Y][X - 1]; n22 = mg[Y - 1][X - 1];
+                    }
+                } else if (cond2) {
+                    if (ai < aj) {
+                        w = ai / aj;
+                        n11 = mg[Y][X + 1]; n12 = mg[Y - 1][X + 1]; n21 = mg[Y][X - 1]; n22 = mg[Y + 1][X - 1];
+                    } else {
+                        w = aj / ai;
+                        n11 = mg[Y - 1][X]; n12 = mg[Y - 1][X + 1]; n21 = mg[Y + 1][X]; n22 = mg[Y + 1][X - 1];
+                    }
+                } else {
+                    ok = false;
+                }
+                if (ok) {
+                    const double omw = 1.0 - (double)w;
+                    const double plus = (double)(n12 * w) + (double)n11 * omw;
+                    const double minus = (double)(n22 * w) + (double)n21 * omw;
+                    const double md = (double)m;
+                    keep = (plus <= md) && (minus <= md);
+                    strong = keep && (m >= 0.2f);
+                }
+            }
+        }
+        const unsigned lw = __ballot_sync(0xffffffffu, keep);
+        const unsigned hw = __ballot_sync(0xffffffffu, strong);
+        if (x == 0 && r < S) {
+            low[r * SNN_WPR + blockIdx.x] = lw;
+            high[r * SNN_WPR + blockIdx.x] = hw;
+        }
+    }
+}
+
+// ---- launchers (image.cu picks them when the parameters match) ----------------------------------------
+int snn_launch_gray6(snn_ctx* ctx, const ExtractPlan& pl, int nf) {
+    k_gray6<<<dim3(13, 13, nf * pl.nq), dim3(32, 8), 0, ctx->stream>>>(pl.Dc, pl.info, pl.gray, pl.bufA);
+    SNN_LAUNCH_CHECK("k_gray6");
+    return SNN_OK;
+}
+
+bool snn_gauss_fast_supported(int radius) { return radius == 8 || radius == 10 || radius == 6; }
+
+int snn_launch_gauss_fast(snn_ctx* ctx, const ExtractPlan& pl, int npass, int ppf) {
+    const dim3 gv(13, (SNN_SMAX + 8 * NOUT - 1) / (8 * NOUT), npass), bv(32, 8);
+    const int per_pass = SNN_SMAX * ((SNN_SMAX + NOUT - 1) / NOUT);
+    const dim3 gh((per_pass + 255) / 256, 1, npass), bh(256);
+    switch (pl.gauss.radius) {
+        case 8:
+            k_gauss_v8<8><<<gv, bv, 0, ctx->stream>>>(pl.bufA, pl.info, ppf, pl.gauss, pl.bufB);
+            k_gauss_h8<8><<<gh, bh, 0, ctx->stream>>>(pl.bufB, pl.info, ppf, pl.gauss, pl.bleed, pl.bufC);
+            break;
+        case 10:
+            k_gauss_v8<10><<<gv, bv, 0, ctx->stream>>>(pl.bufA, pl.info, ppf, pl.gauss, pl.bufB);
+            k_gauss_h8<10><<<gh, bh, 0, ctx->stream>>>(pl.bufB, pl.info, ppf, pl.gauss, pl.bleed, pl.bufC);
+            break;
+        default:
+            k_gauss_v8<6><<<gv, bv, 0, ctx->stream>>>(pl.bufA, pl.info, ppf, pl.gauss, pl.bufB);
+            k_gauss_h8<6><<<gh, bh, 0, ctx->stream>>>(pl.bufB, pl.info, ppf, pl.gauss, pl.bleed, pl.bufC);
+            break;
+    }
+    SNN_LAUNCH_CHECK("k_gauss_fast");
+    return SNN_OK;
+}
+
+int snn_launch_sobel_nms2(snn_ctx* ctx, const ExtractPlan& pl, int npass, int ppf, float* mag_dbg) {
+    k_sobel_nms2<<<dim3(13, 13, npass), dim3(32, 8), 0, ctx->stream>>>(pl.bufC, pl.info, ppf, pl.low, pl.high,
+                                                                        mag_dbg);
+    SNN_LAUNCH_CHECK("k_sobel_nms2");
+    return SNN_OK;
+}

@@ -93,6 +93,8 @@ struct snn_ctx {
     // scratch of snn_extract, grown on demand
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
+    // SNN_FORCE_GENERIC=1: run the unspecialised kernels of image.cu (A/B parity tests)
+    bool force_generic = false;
     // timers
     bool timing = false;
     SnnTimer timers[ST_COUNT];

@@ -271,31 +271,50 @@ class getStripe:
                     bgright_down, frame_range=None, chroms=None):
         """``extract`` for every maxpixel value at once: the device builds each search window
         once and runs all Q x 6 brightness passes on it.  Returns one DataFrame per quantile,
-        identical to what the reference's per-quantile loop (stripenn.py:134-138) collects."""
-        per_q: List[List[pd.DataFrame]] = [[] for _ in quantiles]
+        identical to what the reference's per-quantile loop (stripenn.py:134-138) collects.
+
+        Per chromosome: one snn_extract call, the per-window and the cross-window
+        RemoveRedundant('size') of every maxpixel value in one host call each (pairs never cross
+        a maxpixel value or a chromosome), one snn_score call for all p-values."""
+        nq = len(quantiles)
         weights = gaussian_weights(self.canny)
-        for ci, chrom in enumerate(self.chromnames if chroms is None else chroms):
+        self._install_background((bgleft_up, bgright_up, bgleft_down, bgright_down))
+        kept: List[tuple] = []   # (chrom, candidate records, p-values)
+        for chrom in (self.chromnames if chroms is None else chroms):
             cid = self.unbalLib.ensure(chrom)
             lo, hi = (0, None) if frame_range is None else frame_range
             cand = self.dev.extract(cid, np.asarray(MP[chrom], dtype=np.float64), self.canny, self.minH,
                                     self.maxW, self.bfilter, self.gray_variant, lo, hi, weights)
-            for qi, perc in enumerate(quantiles):
-                sel = cand[cand["q"] == qi]
-                df = self._candidate_frame(sel, chrom, perc)
-                # per-window RemoveRedundant('size') (getStripe.py:1112): pairs inside one window
-                if len(df):
-                    keep = remove_redundant_mask(df['num'].to_numpy(), df['num'].to_numpy(),
-                                                 df[['pos1', 'pos2', 'pos3', 'pos4']].to_numpy(),
-                                                 df['h'].to_numpy(), df['w'].to_numpy(), None, "size")
-                    df = df[keep]
-                per_q[qi].append(df)
+            if len(cand):
+                pos = np.stack([cand["pos1"], cand["pos2"], cand["pos3"], cand["pos4"]], axis=1)
+                hh, ww = cand["h"].astype(np.float64), cand["w"].astype(np.float64)
+                frame = cand["frame"].astype(np.int64)
+                nfr = int(frame.max()) + 1
+                # per-window RemoveRedundant('size') (getStripe.py:1112): one group per (q, window)
+                grp = (cand["q"].astype(np.int64) * nfr + frame).astype(np.int32)
+                keep = remove_redundant_mask(grp, np.zeros(len(cand), np.int64), pos, hh, ww, None, "size")
+                cand, pos, hh, ww, frame = cand[keep], pos[keep], hh[keep], ww[keep], frame[keep]
+                # cross-window RemoveRedundant('size') (getStripe.py:852): one group per q
+                keep = remove_redundant_mask(cand["q"], frame, pos, hh, ww, None, "size")
+                cand, pos = cand[keep], pos[keep]
+            if len(cand):
+                pv = self.dev.score(cid, pos, None, True, self._stale_rows(pos))["pvalue"]
+            else:
+                pv = np.zeros(0)
+            kept.append((chrom, cand, pv))
         out = []
         for qi, perc in enumerate(quantiles):
-            res = pd.concat(per_q[qi]) if per_q[qi] else pd.DataFrame(columns=RESULT_COLUMNS)
-            res = self.RemoveRedundant(res, 'size')          # getStripe.py:852
-            res = res.reset_index(drop=True)
-            pval = self.pvalue(bgleft_up, bgright_up, bgleft_down, bgright_down, res)
-            res = res.assign(pvalue=pval)
+            parts, pvs = [], []
+            for chrom, cand, pv in kept:
+                sel = cand["q"] == qi
+                if sel.any():
+                    parts.append(self._candidate_frame(cand[sel], chrom, perc))
+                    pvs.append(pv[sel])
+            if parts:
+                res = pd.concat(parts).reset_index(drop=True)
+                res = res.assign(pvalue=np.concatenate(pvs))
+            else:
+                res = pd.DataFrame(columns=RESULT_COLUMNS + ['pvalue'])
             out.append(res)
         return out
 
@@ -333,27 +352,33 @@ class getStripe:
     def _by_chrom(self, df):
         chrs = df['chr'].astype(str).to_numpy()
         pos = df[['pos1', 'pos2', 'pos3', 'pos4']].to_numpy(dtype=np.int64)
-        groups = {}
-        for i, c in enumerate(chrs):
-            groups.setdefault(c, []).append(i)
+        codes, uniq = pd.factorize(chrs)
+        order = np.argsort(codes, kind="stable")
+        bounds = np.searchsorted(codes[order], np.arange(len(uniq) + 1))
+        groups = {str(uniq[k]): order[bounds[k]:bounds[k + 1]] for k in range(len(uniq))}
         return chrs, pos, groups
 
     def _stale_rows(self, pos):
         """Background row inherited by stripes that are neither on nor under the diagonal
-        (getStripe.py:583-597: the loop variables persist across stripes)."""
+        (getStripe.py:583-597: the loop variables persist across stripes).  None when every
+        stripe is on or under the diagonal (always the case for StripeSearch output)."""
         r = self.resol
+        pos = np.asarray(pos, dtype=np.int64).reshape(-1, 4)
+        x1, x2 = (pos[:, 0] - 1) // r, pos[:, 1] // r
+        y1, y2 = (pos[:, 2] - 1) // r, pos[:, 3] // r
+        down, up = x1 == y1, (x1 != y1) & (x2 == y2)
+        if bool(np.all(down | up)):
+            return None
+        h = -(-pos[:, 3] // r) - pos[:, 2] // r
         n = len(pos)
         stale = np.full((n, 2), -1, dtype=np.int32)
         last = (-1, -1)
         for i in range(n):
-            p1, p2, p3, p4 = (int(v) for v in pos[i])
-            x1, x2, y1, y2 = (p1 - 1) // r, p2 // r, (p3 - 1) // r, p4 // r
-            h = int(math.ceil(p4 / r)) - p3 // r
-            if x1 == y1:
-                last = (0, min(h - 1, 399)) if h > 0 else last
-            elif x2 == y2:
-                last = (1, min(max(y2 - y1 - (h - 1) - 1, -400), 399) % 400) if h > 0 else last
-            else:
+            if h[i] > 0 and down[i]:
+                last = (0, int(min(h[i] - 1, 399)))
+            elif h[i] > 0 and up[i]:
+                last = (1, int(min(max(y2[i] - y1[i] - (h[i] - 1) - 1, -400), 399) % 400))
+            elif not (down[i] or up[i]):
                 stale[i] = last
         return stale
 
@@ -367,8 +392,7 @@ class getStripe:
         out = np.full(len(pos), np.nan)
         for c, idx in groups.items():
             cid = self.unbalLib.ensure(c)
-            idx = np.asarray(idx)
-            st = stale[idx] if (stale[idx, 0] >= 0).any() else None
+            st = None if stale is None else stale[idx]
             out[idx] = self.dev.score(cid, pos[idx], None, True, st)["pvalue"]
         return out.tolist()
 

@@ -115,7 +115,7 @@ def test_stage_images_match_reference_golden(dev, tiny_cm, golden_dir):
             assert np.array_equal(np.packbits(d["vert"].astype(bool)), g["f%d_vert%d" % (idx, b)])
 
 
-@pytest.mark.parametrize("sigma,bf,variant", [(2.0, 3, 0), (2.5, 1, 0), (2.0, 5, 1), (1.5, 3, 2)])
+@pytest.mark.parametrize("sigma,bf,variant", [(2.0, 3, 0), (2.5, 1, 0), (2.0, 5, 1), (1.5, 3, 2), (3.0, 3, 0)])
 def test_stage_images_match_oracle(dev, tiny2_cm, sigma, bf, variant):
     obj, mat, names, _, _ = _obj(tiny2_cm, "KR", dev)
     c = "chrA"
@@ -271,3 +271,31 @@ def test_load_errors(dev):
     with pytest.raises(_lib.StripennB200Error) as e:
         dev.quantiles(7, [0.5])
     assert e.value.code == _lib.ESTATE
+
+
+def test_generic_and_specialised_kernels_agree(dev, tiny2_cm, monkeypatch):
+    """SNN_FORCE_GENERIC=1 selects the unspecialised image kernels (image.cu); the default path
+    uses image_fast.cu.  Both must give the same bits."""
+    from stripenn_b200.engine import Device
+    monkeypatch.setenv("SNN_FORCE_GENERIC", "1")
+    gen = Device(0)
+    monkeypatch.delenv("SNN_FORCE_GENERIC")
+    try:
+        mat = OracleMatrix(tiny2_cm, "KR")
+        c = "chrB"
+        px = tiny2_cm.chroms[c]
+        w = tiny2_cm.weight_vector(c, "KR")
+        for d in (dev, gen):
+            d.load_chrom(1, px.nbins, 5000, px.size_bp, px.bin1, px.bin2, px.count, w)
+        mp = np.quantile(mat.positive_population(c), [0.95, 0.97, 0.99])
+        a = dev.extract(1, mp, 2.0, 10, 8, 3)
+        b = gen.extract(1, mp, 2.0, 10, 8, 3)
+        assert len(a) > 0 and np.array_equal(a, b)
+        for idx in (0, 3):
+            for bi in (1, 4):
+                x = dev.debug_stages(1, mp[1], 2.0, 3, idx, bi)
+                y = gen.debug_stages(1, mp[1], 2.0, 3, idx, bi)
+                for k in ("gray", "smoothed", "mag", "low", "edges", "vert"):
+                    assert np.array_equal(x[k], y[k]), (idx, bi, k)
+    finally:
+        gen.close()
