@@ -293,13 +293,20 @@ def native_arm(args):
 
     qs = list(map(float, QS.split(",")))
 
+    host_ms = {}
+
     def step(matrix_cls):
+        t_in = time.perf_counter()
         for cid in list(dev.loaded):
             dev.unload_chrom(cid)
         lib = matrix_cls(cm, bal, dev)
         obj = gs.getStripe(lib, cm.binsize, 10, 8, 2.0, all_names, chromnames, all_sizes, chromsizes, 1, 3,
                            123456789, 0)
+        t0 = time.perf_counter()
         unf, fil = cp.run_pipeline(obj, cm, qs, chromnames, 0.1, '0', False, comm)
+        host_ms.clear()
+        host_ms.update(obj.last_host_ms)
+        host_ms['unload+setup'] = (t0 - t_in) * 1e3
         return unf, fil
 
     def timed(matrix_cls, k, w):
@@ -329,6 +336,7 @@ def native_arm(args):
     ms_dev, (unf, fil) = timed(ResidentMatrix, steps, warm)
     clocks = sampler.stop()
     stages = dev.stage_times()
+    host_phases = {k: round(v, 2) for k, v in host_ms.items()}
     dev.h2d_bytes = dev.d2h_bytes = 0
     ms_e2e, _ = timed(PinnedMatrix, steps, 1)
     h2d_step, d2h_step = dev.h2d_bytes // (steps + 1), dev.d2h_bytes // (steps + 1)
@@ -391,7 +399,7 @@ def native_arm(args):
                            "generate_s": round(gen_s, 1)},
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d_step),
                         "d2h_bytes_per_step": int(d2h_step), "ms_per_step": ms_e2e / steps},
-                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+                "gpu_launches": launches, "host_phases_ms_last_step": host_phases, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     dev.close()
     if world > 1:

@@ -119,6 +119,19 @@ def compute_chromosomes(cm: ContactMap, chroms):
     return all_names, all_sizes, chromnames, chromsizes
 
 
+class StageClock:
+    """Wall-clock laps of the host pipeline (the reference prints minutes per stage; we keep ms)."""
+
+    def __init__(self):
+        self.t = time.perf_counter()
+        self.ms = {}
+
+    def lap(self, name):
+        now = time.perf_counter()
+        self.ms[name] = self.ms.get(name, 0.0) + (now - self.t) * 1e3
+        self.t = now
+
+
 class LocalComm:
     """Single-process stand-in for the two host-side exchanges of the sharded pipeline."""
     rank = 0
@@ -171,12 +184,14 @@ def run_pipeline(obj, cm, qs, chromnames, pvalue, mask, slow, comm=None, say=lam
     """Stages 1-5 of compute (stripenn.py:120-152) for the chromosomes this rank owns, with the
     two host-side exchanges the background needs.  `obj` is a getStripe-shaped object."""
     comm = comm or LocalComm()
+    clock = StageClock()
     all_names = list(obj.all_chromnames)
     owner = lpt_partition(all_names, obj.all_chromsizes, comm.world)
     mine = lambda c: owner.get(c, 0) == comm.rank
     my_sel = [c for c in chromnames if mine(c)]
     say('1. Maximum pixel value calculation ...')
     MP = obj.getQuantile_slow(cm, my_sel, qs) if slow else obj.getQuantile_original(cm, my_sel, qs)
+    clock.lap('quantiles')
     say('2. Expected value calculation ...')
     saved = obj.chromnames
     obj.chromnames = my_sel
@@ -184,12 +199,14 @@ def run_pipeline(obj, cm, qs, chromnames, pvalue, mask, slow, comm=None, say=lam
         EV = obj.mpmean()
     finally:
         obj.chromnames = saved
+    clock.lap('expected')
     say('3. Background distribution estimation ...')
     names2 = obj.background_chromosomes()
     avail = {}
     for part in comm.all_gather(obj.available_counts([c for c in names2 if mine(c)])):
         avail.update(part)
     names2b, budget = obj.sample_budget(names2, avail)
+    clock.lap('row_flags')
     cols = {}
     for c in names2b:
         if mine(c):
@@ -199,16 +216,20 @@ def run_pipeline(obj, cm, qs, chromnames, pvalue, mask, slow, comm=None, say=lam
         allcols.update(part)
     full = np.concatenate([allcols[c] for c in names2b], axis=2) if names2b else np.zeros((4, 400, 0))
     bg = (full[0], full[1], full[2], full[3])
+    clock.lap('background')
     say('4. Finding candidate stripes from each chromosome ...')
     per_q = obj.extract_all(MP, qs, *bg, chroms=my_sel)
+    clock.lap('extract+pvalue')
     empty = pd.DataFrame(columns=gs.RESULT_COLUMNS + ['pvalue'])
     nonempty = [t for t in per_q if len(t)]
     local = pd.concat(nonempty) if nonempty else empty
     local = obj.RemoveRedundant(local, 'pvalue')     # pairs never cross chromosomes
+    clock.lap('dedup')
     say('5. Stripiness calculation ...')
     s = obj.scoringstripes(local, EV, mask)[0]
     local = local.drop(columns=['total', 'num', 'start', 'end', 'x', 'y', 'h', 'w', 'medpixel'])
     local.insert(local.shape[1], 'Stripiness', s, True)
+    clock.lap('stripiness')
     if comm.world > 1:
         # reference row order: maxpixel-major, then chromosomes in -k order, then emission order
         labels = [str(q * 100) + '%' for q in qs]
@@ -225,6 +246,8 @@ def run_pipeline(obj, cm, qs, chromnames, pvalue, mask, slow, comm=None, say=lam
     result_table = result_table.reset_index(drop=True)
     res_filter = result_table[result_table['pvalue'] < pvalue]
     res_filter = res_filter.sort_values(by=['Stripiness'], ascending=False)
+    clock.lap('tables')
+    obj.last_host_ms = clock.ms
     if return_stages:
         return result_table, res_filter, dict(MP=MP, EV=EV, bg=bg, per_q=per_q)
     return result_table, res_filter
