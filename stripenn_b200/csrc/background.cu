@@ -121,10 +121,12 @@ __global__ void __launch_bounds__(512) k_bg_sort(const double* __restrict__ in, 
 }
 
 int snn_set_background_impl(snn_ctx* ctx, int64_t ncol, const double* tables) {
-    cudaFree(ctx->bg_sorted);
-    cudaFree(ctx->bg_valid);
-    ctx->bg_sorted = nullptr;
-    ctx->bg_valid = nullptr;
+    if (ncol != ctx->bg_ncol) {   // keep the buffers when the shape repeats (every compute step)
+        cudaFree(ctx->bg_sorted);
+        cudaFree(ctx->bg_valid);
+        ctx->bg_sorted = nullptr;
+        ctx->bg_valid = nullptr;
+    }
     ctx->bg_ncol = 0;
     if (ncol == 0) return SNN_OK;
     int npow2 = 1;
@@ -137,8 +139,10 @@ int snn_set_background_impl(snn_ctx* ctx, int64_t ncol, const double* tables) {
     void* scratch = nullptr;
     int rc = snn_scratch(ctx, bytes, &scratch);
     if (rc) return rc;
-    SNN_CUDA(cudaMalloc(&ctx->bg_sorted, bytes));
-    SNN_CUDA(cudaMalloc(&ctx->bg_valid, rows * sizeof(int32_t)));
+    if (!ctx->bg_sorted) {
+        SNN_CUDA(cudaMalloc(&ctx->bg_sorted, bytes));
+        SNN_CUDA(cudaMalloc(&ctx->bg_valid, rows * sizeof(int32_t)));
+    }
     SNN_CUDA(cudaMemcpyAsync(scratch, tables, bytes, cudaMemcpyHostToDevice, ctx->stream));
     size_t smem = (size_t)npow2 * sizeof(double);
     SNN_CUDA(cudaFuncSetAttribute(k_bg_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -62,7 +62,7 @@ int snn_band_build(snn_ctx* ctx, SnnChrom* c) {
         if (rc0) return rc0;
         int* d_bad = (int*)scratch;
         SNN_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream));
-        SNN_CUDA(cudaMalloc(&c->rowptr, (size_t)(c->nbins + 1) * sizeof(int64_t)));
+        SNN_CUDA(cudaMallocAsync(&c->rowptr, (size_t)(c->nbins + 1) * sizeof(int64_t), ctx->stream));
         int blocks0 = (int)((c->nnz + 256) / 256);
         if (blocks0 > 148 * 16) blocks0 = 148 * 16;
         {

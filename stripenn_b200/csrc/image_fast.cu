@@ -309,6 +309,117 @@ __global__ void __launch_bounds__(256) k_sobel_nms2(const float* __restrict__ sm
     }
 }
 
+// ---- Sobel + magnitude + NMS, register-marching version ----------------------------------------------
+// A warp owns a 32-column strip (28 useful columns + 2 halo lanes each side) and marches down
+// the rows keeping s(rho-2..rho), dj(rho-2..rho), mag(rho-3..rho-1) in registers; horizontal
+// neighbours come from warp shuffles.  No shared-memory staging of the images, one conversion
+// per derivative value.  Rows / columns outside the image are LOADED reflected (scipy
+// 'reflect'), which makes every derivative at a reflected position equal to the derivative at
+// its source position — exactly how ndi.sobel pads the derivative image in its second pass.
+#define SN_ROWS 64
+#define SN_WARPS 15
+__global__ void __launch_bounds__(SN_WARPS * 32) k_sobel_nms3(const float* __restrict__ sm_all,
+                                                              const FrameInfo* __restrict__ info,
+                                                              int passes_per_frame, uint32_t* __restrict__ low_all,
+                                                              uint32_t* __restrict__ high_all,
+                                                              float* __restrict__ mag_dbg) {
+    __shared__ uint32_t lowS[SN_ROWS][SNN_WPR], highS[SN_ROWS][SNN_WPR];
+    const int pass = blockIdx.y;
+    const int S = info[pass / passes_per_frame].S;
+    const int r0 = blockIdx.x * SN_ROWS;
+    if (r0 >= S) return;
+    const int r1 = min(r0 + SN_ROWS, S);
+    for (int t = threadIdx.x; t < SN_ROWS * SNN_WPR; t += SN_WARPS * 32) {
+        (&lowS[0][0])[t] = 0u;
+        (&highS[0][0])[t] = 0u;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cbase = warp * 28;
+    if (cbase < S) {
+        const int c = cbase + lane - 2;
+        const int cc = f_symm(c, S);
+        const bool colok = cc >= 0 && cc < S;
+        const float* smo = sm_all + (int64_t)pass * SNN_SMAX * SNN_SMAX + (colok ? cc : 0);
+        const unsigned FULL = 0xffffffffu;
+        float s0 = 0.f, s1 = 0.f;
+        double dj0 = 0.0, dj1 = 0.0;
+        float mA = 0.f, mB = 0.f, isB = 0.f, jsB = 0.f;
+        for (int rho = r0 - 2; rho <= r1 + 1; ++rho) {
+            const int rr = f_symm(rho, S);
+            const float s2 = (colok && rr >= 0 && rr < S) ? smo[rr * SNN_SMAX] : 0.f;
+            // axis-1 derivative of row rho
+            const float sl = __shfl_up_sync(FULL, s2, 1), sr = __shfl_down_sync(FULL, s2, 1);
+            const double djn = (double)(-__fsub_rn(sl, sr));
+            // axis-0 derivative of row rho-1, then the [1 2 1] passes
+            const double di1 = (double)(-__fsub_rn(s0, s2));
+            const double dil = __shfl_up_sync(FULL, di1, 1), dir = __shfl_down_sync(FULL, di1, 1);
+            const float is1 = (float)(di1 * 2.0 + (dil + dir) * 1.0);
+            const float js1 = (float)(dj1 * 2.0 + (dj0 + djn) * 1.0);
+            float mm = is1 * is1;
+            mm = mm + js1 * js1;
+            const float m1 = sqrtf(mm);
+            // NMS of row rho-2 from mag rows rho-3 (mA), rho-2 (mB), rho-1 (m1)
+            const float mAl = __shfl_up_sync(FULL, mA, 1), mAr = __shfl_down_sync(FULL, mA, 1);
+            const float mBl = __shfl_up_sync(FULL, mB, 1), mBr = __shfl_down_sync(FULL, mB, 1);
+            const float m1l = __shfl_up_sync(FULL, m1, 1), m1r = __shfl_down_sync(FULL, m1, 1);
+            const int r = rho - 2;
+            bool keep = false, strong = false;
+            const bool mine = lane >= 2 && lane < 30 && c < S;
+            if (mag_dbg && mine && rho - 1 >= r0 && rho - 1 < r1)
+                mag_dbg[(int64_t)pass * SNN_SMAX * SNN_SMAX + (rho - 1) * SNN_SMAX + c] = m1;
+            if (mine && r >= r0 && r < r1 && r >= 1 && r <= S - 2 && c >= 1 && c <= S - 2 && mB >= 0.1f) {
+                const float is = isB, js = jsB, m = mB;
+                const bool up = is >= 0.f, down = is <= 0.f, right = js >= 0.f, left = js <= 0.f;
+                const bool cond1 = (up && right) || (down && left);
+                const bool cond2 = (down && right) || (up && left);
+                const float ai = fabsf(is), aj = fabsf(js);
+                float w = 0.f, n11 = 0.f, n12 = 0.f, n21 = 0.f, n22 = 0.f;
+                bool ok = true;
+                if (cond1) {
+                    if (ai > aj) { w = aj / ai; n11 = m1;  n12 = m1r; n21 = mA;  n22 = mAl; }
+                    else         { w = ai / aj; n11 = mBr; n12 = m1r; n21 = mBl; n22 = mAl; }
+                } else if (cond2) {
+                    if (ai < aj) { w = ai / aj; n11 = mBr; n12 = mAr; n21 = mBl; n22 = m1l; }
+                    else         { w = aj / ai; n11 = mA;  n12 = mAr; n21 = m1;  n22 = m1l; }
+                } else {
+                    ok = false;
+                }
+                if (ok) {
+                    const double omw = 1.0 - (double)w;
+                    const double plus = (double)(n12 * w) + (double)n11 * omw;
+                    const double minus = (double)(n22 * w) + (double)n21 * omw;
+                    const double md = (double)m;
+                    keep = (plus <= md) && (minus <= md);
+                    strong = keep && (m >= 0.2f);
+                }
+            }
+            const unsigned lw = (__ballot_sync(FULL, keep) >> 2) & 0x0fffffffu;
+            const unsigned hw = (__ballot_sync(FULL, strong) >> 2) & 0x0fffffffu;
+            if (lane == 0 && lw) {
+                const int word = cbase >> 5, off = cbase & 31;
+                atomicOr(&lowS[r - r0][word], lw << off);
+                if (off > 4 && word + 1 < SNN_WPR) atomicOr(&lowS[r - r0][word + 1], lw >> (32 - off));
+                if (hw) {
+                    atomicOr(&highS[r - r0][word], hw << off);
+                    if (off > 4 && word + 1 < SNN_WPR) atomicOr(&highS[r - r0][word + 1], hw >> (32 - off));
+                }
+            }
+            s0 = s1; s1 = s2;
+            dj0 = dj1; dj1 = djn;
+            mA = mB; mB = m1;
+            isB = is1; jsB = js1;
+        }
+    }
+    __syncthreads();
+    uint32_t* low = low_all + (int64_t)pass * SNN_SMAX * SNN_WPR + (int64_t)r0 * SNN_WPR;
+    uint32_t* high = high_all + (int64_t)pass * SNN_SMAX * SNN_WPR + (int64_t)r0 * SNN_WPR;
+    for (int t = threadIdx.x; t < (r1 - r0) * SNN_WPR; t += SN_WARPS * 32) {
+        low[t] = (&lowS[0][0])[t];
+        high[t] = (&highS[0][0])[t];
+    }
+}
+
 // ---- launchers (image.cu picks them when the parameters match) ----------------------------------------
 int snn_launch_gray6(snn_ctx* ctx, const ExtractPlan& pl, int nf) {
     k_gray6<<<dim3(13, 13, nf * pl.nq), dim3(32, 8), 0, ctx->stream>>>(pl.Dc, pl.info, pl.gray, pl.bufA);
@@ -341,8 +452,8 @@ int snn_launch_gauss_fast(snn_ctx* ctx, const ExtractPlan& pl, int npass, int pp
 }
 
 int snn_launch_sobel_nms2(snn_ctx* ctx, const ExtractPlan& pl, int npass, int ppf, float* mag_dbg) {
-    k_sobel_nms2<<<dim3(13, 13, npass), dim3(32, 8), 0, ctx->stream>>>(pl.bufC, pl.info, ppf, pl.low, pl.high,
-                                                                        mag_dbg);
-    SNN_LAUNCH_CHECK("k_sobel_nms2");
+    k_sobel_nms3<<<dim3((SNN_SMAX + SN_ROWS - 1) / SN_ROWS, npass), SN_WARPS * 32, 0, ctx->stream>>>(
+        pl.bufC, pl.info, ppf, pl.low, pl.high, mag_dbg);
+    SNN_LAUNCH_CHECK("k_sobel_nms3");
     return SNN_OK;
 }
