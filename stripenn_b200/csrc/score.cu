@@ -52,27 +52,42 @@ __device__ double select_kth(const double* a, int n, int k, double* slot) {
     return *slot;
 }
 
+// Window accessor: the stripe's window staged in shared memory (the common case) or, for windows
+// that do not fit, read through the band / CSR view.
+struct Win {
+    const double* sm;   // staged window, row-major [h][ncols], or nullptr
+    MatView m;
+    int64_t R0, cmin;
+    int ncols;
+    __device__ __forceinline__ double at(int j, int64_t gc) const {
+        return sm ? sm[j * ncols + (int)(gc - cmin)] : snn_mat_at(m, R0 + j, gc);
+    }
+};
+
 __global__ void __launch_bounds__(SCORE_THREADS) k_score(MatView m, const int64_t* __restrict__ pos,
                                                          const int32_t* __restrict__ stale,
-                                                         const double* __restrict__ expected,
+                                                         const int32_t* __restrict__ order,
+                                                         const double* __restrict__ rexp,
                                                          const double* __restrict__ bg,
                                                          const int32_t* __restrict__ bg_valid, ScoreParams P,
-                                                         int want_p, int want_s, double* __restrict__ out) {
+                                                         int wcap, int want_p, int want_s,
+                                                         double* __restrict__ out) {
     extern __shared__ double sh[];
     double* cm = sh;               // centre row means (O/E)         [hmax]
     double* lm = cm + P.hmax;      // left                            [hmax]
     double* rm = lm + P.hmax;      // right                           [hmax]
     double* pv = rm + P.hmax;      // per-row p-values / scratch      [hmax]
-    int* ridx = (int*)(pv + P.hmax);                 // compacted row index [hmax]
-    unsigned char* rdel = (unsigned char*)(ridx + P.hmax);  // row deleted  [hmax]
-    __shared__ double ex[SNN_NDIST];
+    double* win = pv + P.hmax;     // staged window                   [wcap]
+    int* ridx = (int*)(win + wcap);                          // compacted row index [hmax]
+    unsigned char* rdel = (unsigned char*)(ridx + P.hmax);   // row deleted          [hmax]
+    __shared__ double rex[SNN_NDIST];   // 1 / (expected[d] + 1e-8)
     __shared__ unsigned char dead[SCORE_MAXCOLS];
     __shared__ double slot;
     __shared__ double red[8];
     __shared__ int redi[4];
     __shared__ int bad_flag;
 
-    const int64_t s = blockIdx.x;
+    const int64_t s = order ? order[blockIdx.x] : blockIdx.x;
     const int64_t p1 = pos[s * 4 + 0], p2 = pos[s * 4 + 1], p3 = pos[s * 4 + 2], p4 = pos[s * 4 + 3];
     const int64_t r = P.binsize;
     const int bs = P.bs;
@@ -83,7 +98,7 @@ __global__ void __launch_bounds__(SCORE_THREADS) k_score(MatView m, const int64_
         for (int t = 0; t < 6; ++t) o[t] = qnan();
     }
     if (want_s)
-        for (int t = threadIdx.x; t < SNN_NDIST; t += SCORE_THREADS) ex[t] = expected[t];
+        for (int t = threadIdx.x; t < SNN_NDIST; t += SCORE_THREADS) rex[t] = rexp[t];
     __syncthreads();
     // cooler region checks (fake/real cooler raise; we answer NaN)
     if (p1 < 1 || p3 < 1 || p2 < p1 || p4 < p3 || p2 > P.chromsize || p4 > P.chromsize) return;
@@ -92,13 +107,48 @@ __global__ void __launch_bounds__(SCORE_THREADS) k_score(MatView m, const int64_
     const int h = (int)(R1 - R0);
     if (h <= 0 || h > P.hmax) return;
 
+    // column ranges of both consumers
+    int64_t lmost = p1 - (int64_t)bs * r;
+    if (lmost < 1) lmost = 1;
+    int64_t rmost = p2 + (int64_t)bs * r;
+    if (rmost > P.chromsize) rmost = P.chromsize;
+    const int64_t C0 = lmost / r, C1 = (rmost + r - 1) / r;       // p-value window
+    const int64_t xsi = p1 / r, xei = p2 / r, ysi = p3 / r, yei = p4 / r;
+    int64_t lmb = xsi - bs, rmb = xei + bs;
+    if (lmb < 1) lmb = 1;
+    if (rmb >= P.nbins) rmb = P.nbins - 1;
+    const int64_t cC0 = p1 / r, cC1 = (p2 + r - 1) / r;           // centre: "chr:xs-xe"
+    int64_t cmin = C0, cmax = C1;
+    if (want_s) {
+        if (lmb < cmin) cmin = lmb;
+        if (cC0 < cmin) cmin = cC0;
+        if (rmb > cmax) cmax = rmb;
+        if (cC1 > cmax) cmax = cC1;
+    }
+    if (!want_p) { cmin = lmb < cC0 ? lmb : cC0; cmax = rmb > cC1 ? rmb : cC1; }
+    if (cmin < 0) cmin = 0;
+    if (cmax > P.nbins) cmax = P.nbins;
+    const int64_t ncw = cmax - cmin;
+    Win W;
+    W.m = m; W.R0 = R0; W.cmin = cmin; W.ncols = (int)ncw;
+    W.sm = (ncw > 0 && (int64_t)h * ncw <= wcap) ? win : nullptr;
+    if (W.sm) {
+        // upper triangle part (col >= row): a warp per window row, lanes along the band row
+        for (int j = warp; j < h; j += nwarp) {
+            const int64_t row = R0 + j;
+            int64_t c0 = cmin > row ? cmin : row;
+            for (int64_t c = c0 + lane; c < cmax; c += 32) win[j * (int)ncw + (int)(c - cmin)] = snn_mat_at(m, row, c);
+        }
+        // lower triangle part (row > col): a warp per window column, lanes along the band row of that column
+        for (int64_t c = cmin + warp; c < cmax; c += nwarp) {
+            int64_t i0 = R0 > c + 1 ? R0 : c + 1;
+            for (int64_t i = i0 + lane; i < R1; i += 32) win[(int)(i - R0) * (int)ncw + (int)(c - cmin)] = snn_mat_at(m, i, c);
+        }
+        __syncthreads();
+    }
+
     // ================================ p-value (getStripe.py:552-605) ================================
     if (want_p) {
-        int64_t lmost = p1 - (int64_t)bs * r;
-        if (lmost < 1) lmost = 1;
-        int64_t rmost = p2 + (int64_t)bs * r;
-        if (rmost > P.chromsize) rmost = P.chromsize;
-        const int64_t C0 = lmost / r, C1 = (rmost + r - 1) / r;
         const int64_t ncol = C1 - C0;
         int64_t ca, cb, la, lb, ra, rb;
         snn_pyslice(bs, -(int64_t)bs, ncol, &ca, &cb);   // mat[:, bs:-bs]
@@ -111,50 +161,42 @@ __global__ void __launch_bounds__(SCORE_THREADS) k_score(MatView m, const int64_
         else if (x2 == y2) mode = 1;
         else if (stale && stale[s * 2] >= 0) mode = 2;
         else mode = 3;
-        for (int j = warp; j < h; j += nwarp) {
-            const int64_t row = R0 + j;
+        for (int j = threadIdx.x; j < h; j += SCORE_THREADS) {
             double sc = 0.0, sl = 0.0, sr = 0.0;
-            for (int64_t c = lane; c < ncol; c += 32) {
-                const double v = snn_nan0(snn_mat_at(m, row, C0 + c));
+            for (int64_t c = 0; c < ncol; ++c) {
+                const double v = snn_nan0(W.at(j, C0 + c));
                 if (c >= ca && c < cb) sc += v;
                 if (c >= la && c < lb) sl += v;
                 if (c >= ra && c < rb) sr += v;
             }
-            for (int off = 16; off > 0; off >>= 1) {
-                sc += __shfl_xor_sync(0xffffffffu, sc, off);
-                sl += __shfl_xor_sync(0xffffffffu, sl, off);
-                sr += __shfl_xor_sync(0xffffffffu, sr, off);
-            }
-            if (lane == 0) {
-                const double mc = (cb > ca) ? sc / (double)(cb - ca) : qnan();
-                const double ml = (lb > la) ? sl / (double)(lb - la) : qnan();
-                const double mr = (rb > ra) ? sr / (double)(rb - ra) : qnan();
-                const double dl = mc - ml, dr = mc - mr;
-                double p = qnan();
-                if (mode != 3) {
-                    int table, d;
-                    if (mode == 0) { table = 1; d = j < 399 ? j : 399; }
-                    else if (mode == 1) {
-                        int64_t dd = y2 - y1 - j - 1;
-                        if (dd > 399) dd = 399;
-                        if (dd < 0) dd += SNN_NDIST;   // numpy negative index
-                        d = (int)dd;
-                        table = 0;
-                    } else { table = stale[s * 2] ? 0 : 1; d = stale[s * 2 + 1]; }
-                    if (d >= 0 && d < SNN_NDIST) {
-                        // table order in memory: 0 bgleft_up, 1 bgright_up, 2 bgleft_down, 3 bgright_down
-                        const int tl = table == 0 ? 0 : 2, tr = table == 0 ? 1 : 3;
-                        const int64_t rl = (int64_t)tl * SNN_NDIST + d, rr = (int64_t)tr * SNN_NDIST + d;
-                        const int nl = bg_valid[rl], nr = bg_valid[rr];
-                        const double a = (double)count_ge(bg + rl * P.bg_ncol, nl, dl) / (double)nl;
-                        const double b = (double)count_ge(bg + rr * P.bg_ncol, nr, dr) / (double)nr;
-                        p = a;                // Python max(a, b)
-                        if (b > p) p = b;
-                        if (p == 0.0) p = 1.0 / (double)P.bg_ncol;
-                    }
+            const double mc = (cb > ca) ? sc / (double)(cb - ca) : qnan();
+            const double ml = (lb > la) ? sl / (double)(lb - la) : qnan();
+            const double mr = (rb > ra) ? sr / (double)(rb - ra) : qnan();
+            const double dl = mc - ml, dr = mc - mr;
+            double p = qnan();
+            if (mode != 3) {
+                int table, d;
+                if (mode == 0) { table = 1; d = j < 399 ? j : 399; }
+                else if (mode == 1) {
+                    int64_t dd = y2 - y1 - j - 1;
+                    if (dd > 399) dd = 399;
+                    if (dd < 0) dd += SNN_NDIST;   // numpy negative index
+                    d = (int)dd;
+                    table = 0;
+                } else { table = stale[s * 2] ? 0 : 1; d = stale[s * 2 + 1]; }
+                if (d >= 0 && d < SNN_NDIST) {
+                    // table order in memory: 0 bgleft_up, 1 bgright_up, 2 bgleft_down, 3 bgright_down
+                    const int tl = table == 0 ? 0 : 2, tr = table == 0 ? 1 : 3;
+                    const int64_t rl = (int64_t)tl * SNN_NDIST + d, rr = (int64_t)tr * SNN_NDIST + d;
+                    const int nl = bg_valid[rl], nr = bg_valid[rr];
+                    const double a = (double)count_ge(bg + rl * P.bg_ncol, nl, dl) / (double)nl;
+                    const double b = (double)count_ge(bg + rr * P.bg_ncol, nr, dr) / (double)nr;
+                    p = a;                // Python max(a, b)
+                    if (b > p) p = b;
+                    if (p == 0.0) p = 1.0 / (double)P.bg_ncol;
                 }
-                pv[j] = p;
             }
+            pv[j] = p;
         }
         __syncthreads();
         // np.median: NaN if any NaN, else mean of the middle pair
@@ -175,12 +217,6 @@ __global__ void __launch_bounds__(SCORE_THREADS) k_score(MatView m, const int64_
     if (!want_s) return;
 
     // ============================ stripiness (getStripe.py:661-759) ================================
-    const int64_t xsi = p1 / r, xei = p2 / r, ysi = p3 / r, yei = p4 / r;
-    int64_t lmb = xsi - bs, rmb = xei + bs;
-    if (lmb < 1) lmb = 1;
-    if (rmb >= P.nbins) rmb = P.nbins - 1;
-    // fetched column ranges (bins) and the first expected-value column of each part
-    const int64_t cC0 = p1 / r, cC1 = (p2 + r - 1) / r;  // centre: "chr:xs-xe"
     const int64_t lC0 = lmb, lC1 = xsi;                   // left:   "chr:lm*r - xsi*r"
     const int64_t rC0 = xei, rC1 = rmb;                   // right:  "chr:xei*r - rm*r"
     const int wc = (int)(cC1 - cC0), wl = (int)(lC1 - lC0), wr = (int)(rC1 - rC0);
@@ -195,7 +231,7 @@ __global__ void __launch_bounds__(SCORE_THREADS) k_score(MatView m, const int64_
         int64_t gc = c < wc ? cC0 + c : (c < wc + wl ? lC0 + (c - wc) : rC0 + (c - wc - wl));
         bool all = true;
         for (int j = 0; j < h && all; ++j) {
-            const double v = snn_mat_at(m, R0 + j, gc);
+            const double v = W.at(j, gc);
             if (v == v) all = false;  // observed finite or inf -> O/E not NaN (expected + 1e-8 is finite)
         }
         dead[c] = all ? 1 : 0;
@@ -206,38 +242,50 @@ __global__ void __launch_bounds__(SCORE_THREADS) k_score(MatView m, const int64_
     // xs == ys, else shape[0]-1-x  (getStripe.py:713-731); np.delete wraps negatives
     if (threadIdx.x == 0) {
         const bool diag = (p1 == p3);
-        for (int part = 0; part < 3; ++part) {
-            const int w0 = part == 0 ? 0 : (part == 1 ? wc : wc + wl);
-            const int wn = part == 0 ? wc : (part == 1 ? wl : wr);
-            for (int x = 0; x < wn; ++x) {
-                if (!dead[w0 + x]) continue;
-                int idx = diag ? x : h - 1 - x;
-                if (idx < 0) idx += h;
-                if (idx < 0 || idx >= h) { bad_flag = 1; continue; }  // IndexError in the reference
-                rdel[idx] = 1;
+        bool any = false;
+        for (int c = 0; c < ncols; ++c) any |= dead[c] != 0;
+        if (any) {
+            for (int part = 0; part < 3; ++part) {
+                const int w0 = part == 0 ? 0 : (part == 1 ? wc : wc + wl);
+                const int wn = part == 0 ? wc : (part == 1 ? wl : wr);
+                for (int x = 0; x < wn; ++x) {
+                    if (!dead[w0 + x]) continue;
+                    int idx = diag ? x : h - 1 - x;
+                    if (idx < 0) idx += h;
+                    if (idx < 0 || idx >= h) { bad_flag = 1; continue; }  // IndexError in the reference
+                    rdel[idx] = 1;
+                }
             }
         }
-        int k = 0;
-        for (int j = 0; j < h; ++j)
-            if (!rdel[j]) ridx[k++] = j;
-        redi[0] = k;
+        redi[1] = any ? 1 : 0;
     }
     __syncthreads();
     if (bad_flag) return;
+    if (redi[1]) {
+        if (threadIdx.x == 0) {
+            int k = 0;
+            for (int j = 0; j < h; ++j)
+                if (!rdel[j]) ridx[k++] = j;
+            redi[0] = k;
+        }
+    } else {
+        for (int j = threadIdx.x; j < h; j += SCORE_THREADS) ridx[j] = j;
+        if (threadIdx.x == 0) redi[0] = h;
+    }
+    __syncthreads();
     const int hk = redi[0];
     int lc = 0, ll = 0, lr = 0;  // live columns per part
     for (int c = 0; c < ncols; ++c) {
         if (dead[c]) continue;
         if (c < wc) ++lc; else if (c < wc + wl) ++ll; else ++lr;
     }
-    // ---- pass 2: row means of nan0(O/E) over the live columns; observed sums for getMean
-    double tot_oe = 0.0, tot_obs = 0.0;
-    int n_obs = 0;
-    for (int k = warp; k < hk; k += nwarp) {
+    // ---- pass 2: row means of nan0(O/E) over the live columns (thread per row)
+    double tot_oe = 0.0;
+    for (int k = threadIdx.x; k < hk; k += SCORE_THREADS) {
         const int j = ridx[k];
         const int64_t row = R0 + j;
         double sc = 0.0, sl = 0.0, sr = 0.0;
-        for (int c = lane; c < ncols; c += 32) {
+        for (int c = 0; c < ncols; ++c) {
             if (dead[c]) continue;
             int64_t gc, ecol;
             if (c < wc) { gc = cC0 + c; ecol = xsi + c; }
@@ -246,35 +294,27 @@ __global__ void __launch_bounds__(SCORE_THREADS) k_score(MatView m, const int64_
             int64_t dd = ecol - row;
             if (dd < 0) dd = -dd;
             if (dd > 399) dd = 399;
-            const double obs = snn_mat_at(m, row, gc);
-            const double v = snn_nan0(obs / (ex[dd] + .00000001));
+            const double v = snn_nan0(W.at(j, gc) * rex[dd]);
             if (c < wc) sc += v; else if (c < wc + wl) sl += v; else sr += v;
         }
-        for (int off = 16; off > 0; off >>= 1) {
-            sc += __shfl_xor_sync(0xffffffffu, sc, off);
-            sl += __shfl_xor_sync(0xffffffffu, sl, off);
-            sr += __shfl_xor_sync(0xffffffffu, sr, off);
-        }
-        if (lane == 0) {
-            cm[k] = lc ? sc / (double)lc : qnan();
-            lm[k] = ll ? sl / (double)ll : qnan();
-            rm[k] = lr ? sr / (double)lr : qnan();
-            tot_oe += sc;
-        }
+        cm[k] = lc ? sc / (double)lc : qnan();
+        lm[k] = ll ? sl / (double)ll : qnan();
+        rm[k] = lr ? sr / (double)lr : qnan();
+        tot_oe += sc;
     }
     // getMean: nanmean / nansum of the observed centre window (all rows, all columns)
-    for (int j = warp; j < h; j += nwarp) {
-        double so = 0.0;
-        int no = 0;
-        for (int c = lane; c < wc; c += 32) {
-            const double obs = snn_mat_at(m, R0 + j, cC0 + c);
-            if (obs == obs) { so += obs; ++no; }
+    double tot_obs = 0.0;
+    int n_obs = 0;
+    for (int j = threadIdx.x; j < h; j += SCORE_THREADS) {
+        for (int c = 0; c < wc; ++c) {
+            const double obs = W.at(j, cC0 + c);
+            if (obs == obs) { tot_obs += obs; ++n_obs; }
         }
-        for (int off = 16; off > 0; off >>= 1) {
-            so += __shfl_xor_sync(0xffffffffu, so, off);
-            no += __shfl_xor_sync(0xffffffffu, no, off);
-        }
-        if (lane == 0) { tot_obs += so; n_obs += no; }
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        tot_oe += __shfl_xor_sync(0xffffffffu, tot_oe, off);
+        tot_obs += __shfl_xor_sync(0xffffffffu, tot_obs, off);
+        n_obs += __shfl_xor_sync(0xffffffffu, n_obs, off);
     }
     if (lane == 0) { red[warp] = tot_oe; red[4 + warp] = tot_obs; redi[warp] = n_obs; }
     __syncthreads();
@@ -340,56 +380,83 @@ __global__ void __launch_bounds__(SCORE_THREADS) k_score(MatView m, const int64_
     if (threadIdx.x == 0) o[1] = med * avgdiff;
 }
 
+__global__ void k_recip_expected(const double* __restrict__ ex, double* __restrict__ rex) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < SNN_NDIST) rex[t] = 1.0 / (ex[t] + .00000001);
+}
+
 int snn_score_impl(snn_ctx* ctx, SnnChrom* c, int64_t n, const int64_t* pos, const int32_t* stale,
                    const double* expected, double* pvalue, double* stripiness, double* oe_mean, double* oe_total,
                    double* o_mean, double* o_sum) {
     const int want_p = pvalue != nullptr;
     const int want_s = expected != nullptr && (stripiness || oe_mean || oe_total || o_mean || o_sum);
     if (!want_p && !want_s) return SNN_OK;
-    // shared-memory rows needed: the tallest stripe of the batch
-    int64_t hmax = 1;
+    const int bs = (int)(50000.0 / (double)c->binsize);
+    // Launch classes by window size so that the common small stripes do not pay the shared
+    // memory of the largest one: {rows, staged window doubles}.
+    struct Cls { int hcap, wcap; };
+    const Cls cls[3] = {{128, 4096}, {512, 12288}, {4800, 0}};
+    std::vector<int32_t> order[3];
     for (int64_t i = 0; i < n; ++i) {
-        int64_t p3 = pos[i * 4 + 2], p4 = pos[i * 4 + 3];
-        if (p3 < 1 || p4 < p3 || p4 > c->chromsize) continue;
-        int64_t h = (p4 + c->binsize - 1) / c->binsize - p3 / c->binsize;
-        if (h > hmax) hmax = h;
+        int64_t p1 = pos[i * 4], p2 = pos[i * 4 + 1], p3 = pos[i * 4 + 2], p4 = pos[i * 4 + 3];
+        int64_t h = 1, w = 1;
+        if (p3 >= 1 && p4 >= p3 && p4 <= c->chromsize) h = (p4 + c->binsize - 1) / c->binsize - p3 / c->binsize;
+        if (p1 >= 1 && p2 >= p1) w = (p2 + c->binsize - 1) / c->binsize - p1 / c->binsize + 2 * bs + 2;
+        int k = 2;
+        if (h <= cls[0].hcap && h * w <= cls[0].wcap) k = 0;
+        else if (h <= cls[1].hcap && h * w <= cls[1].wcap) k = 1;
+        order[k].push_back((int32_t)i);
     }
-    hmax = (hmax + 31) & ~(int64_t)31;
-    const size_t per_row = 4 * sizeof(double) + sizeof(int) + 1;
-    if (hmax * per_row > 200 * 1024) hmax = (200 * 1024 / per_row) & ~(size_t)31;  // taller stripes -> NaN
-    const size_t smem = (size_t)hmax * per_row + 64;
-    SNN_CUDA(cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-
     size_t pbytes = ((size_t)n * 4 * sizeof(int64_t) + 255) & ~(size_t)255;
     size_t sbytes = stale ? (((size_t)n * 2 * sizeof(int32_t) + 255) & ~(size_t)255) : 0;
-    size_t ebytes = 4096;
+    size_t ebytes = 8192;
+    size_t orbytes = ((size_t)n * sizeof(int32_t) + 255) & ~(size_t)255;
     size_t obytes = (size_t)n * 6 * sizeof(double);
     void* scratch = nullptr;
-    int rc = snn_scratch(ctx, pbytes + sbytes + ebytes + obytes, &scratch);
+    int rc = snn_scratch(ctx, pbytes + sbytes + ebytes + orbytes + obytes, &scratch);
     if (rc) return rc;
     char* b = (char*)scratch;
     int64_t* dpos = (int64_t*)b;
     int32_t* dstale = stale ? (int32_t*)(b + pbytes) : nullptr;
     double* dex = (double*)(b + pbytes + sbytes);
-    double* dout = (double*)(b + pbytes + sbytes + ebytes);
+    double* drex = dex + 512;
+    int32_t* dorder = (int32_t*)(b + pbytes + sbytes + ebytes);
+    double* dout = (double*)(b + pbytes + sbytes + ebytes + orbytes);
     SNN_CUDA(cudaMemcpyAsync(dpos, pos, (size_t)n * 4 * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
     if (stale)
         SNN_CUDA(cudaMemcpyAsync(dstale, stale, (size_t)n * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
-    if (want_s)
+    std::vector<int32_t> flat;
+    flat.reserve(n);
+    size_t start[3];
+    for (int k = 0; k < 3; ++k) { start[k] = flat.size(); flat.insert(flat.end(), order[k].begin(), order[k].end()); }
+    SNN_CUDA(cudaMemcpyAsync(dorder, flat.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    int launches = 0;
+    SnnScope scope(ctx, ST_SCORE, 0);
+    if (want_s) {
         SNN_CUDA(cudaMemcpyAsync(dex, expected, SNN_NDIST * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    ScoreParams P;
-    P.binsize = c->binsize;
-    P.chromsize = c->chromsize;
-    P.nbins = c->nbins;
-    P.bs = (int)(50000.0 / (double)c->binsize);
-    P.hmax = (int)hmax;
-    P.bg_ncol = ctx->bg_ncol;
-    {
-        SnnScope scope(ctx, ST_SCORE, 1);
-        k_score<<<(unsigned)n, SCORE_THREADS, smem, ctx->stream>>>(snn_view(c), dpos, dstale, dex, ctx->bg_sorted,
-                                                                   ctx->bg_valid, P, want_p, want_s, dout);
-        SNN_LAUNCH_CHECK("k_score");
+        k_recip_expected<<<2, 256, 0, ctx->stream>>>(dex, drex);
+        SNN_LAUNCH_CHECK("k_recip_expected");
+        ++launches;
     }
+    const size_t per_row = 4 * sizeof(double) + sizeof(int) + 1;
+    for (int k = 0; k < 3; ++k) {
+        if (order[k].empty()) continue;
+        ScoreParams P;
+        P.binsize = c->binsize;
+        P.chromsize = c->chromsize;
+        P.nbins = c->nbins;
+        P.bs = bs;
+        P.hmax = cls[k].hcap;
+        P.bg_ncol = ctx->bg_ncol;
+        const size_t smem = (size_t)cls[k].hcap * per_row + (size_t)cls[k].wcap * sizeof(double) + 64;
+        SNN_CUDA(cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_score<<<(unsigned)order[k].size(), SCORE_THREADS, smem, ctx->stream>>>(
+            snn_view(c), dpos, dstale, dorder + start[k], drex, ctx->bg_sorted, ctx->bg_valid, P, cls[k].wcap, want_p,
+            want_s, dout);
+        SNN_LAUNCH_CHECK("k_score");
+        ++launches;
+    }
+    scope.n = launches;
     std::vector<double> host((size_t)n * 6);
     SNN_CUDA(cudaMemcpyAsync(host.data(), dout, obytes, cudaMemcpyDeviceToHost, ctx->stream));
     SNN_CUDA(cudaStreamSynchronize(ctx->stream));
