@@ -148,6 +148,10 @@ def config_chroms(cfg: str) -> Tuple[List[Tuple[str, int]], int, bool]:
         return [("chr1", HG38["chr1"])], 1000, False
     if cfg == "tiny":  # 2,400-bin toy chromosome used by the golden fixtures
         return [("T1", 2400 * 5000 - 1234)], 5000, False
+    if cfg == "tiny1k":  # 1 kb bins: bs = 50, exercises the wide flanks / negative-slice wraps
+        return [("U1", 2600 * 1000 - 321)], 1000, False
+    if cfg == "tiny10k":  # 10 kb bins: bs = 5, odd block split (bu = 2, bd = 3), balanced
+        return [("V1", 2100 * 10000 - 4321), ("V2", 1300 * 10000 - 99)], 10000, True
     if cfg == "tiny2":  # two small chromosomes, balanced
         return [("chrA", 2400 * 5000 - 1234), ("chrB", 1500 * 5000 - 77)], 5000, True
     raise ValueError("unknown config %r" % cfg)

@@ -299,3 +299,32 @@ def test_generic_and_specialised_kernels_agree(dev, tiny2_cm, monkeypatch):
                     assert np.array_equal(x[k], y[k]), (idx, bi, k)
     finally:
         gen.close()
+
+
+@pytest.mark.parametrize("cfg,norm", [("tiny1k", "None"), ("tiny10k", "weight")])
+def test_other_resolutions_match_oracle(dev, cfg, norm):
+    """1 kb (bs = 50: 110-column scoring windows, background rows that wrap around the fetched
+    unit) and 10 kb (bs = 5, uneven bu/bd split) against the oracle, end to end."""
+    cm = synth.make_config(cfg)
+    unf, fil, st = cp.run_stages(cm, norm=norm, maxpixel="0.96,0.99", device=dev, return_stages=True)
+    ounf, ofil, ost = driver.compute(cm, norm=norm, maxpixel="0.96,0.99", return_stages=True)
+    for a, b in zip(st["bg"], ost["bg"]):
+        assert a.shape == b.shape
+        np.testing.assert_allclose(a, b, rtol=1e-12, atol=1e-12, equal_nan=True)
+    assert len(unf) == len(ounf["pos1"]) > 0
+    for k in ("pos1", "pos2", "pos3", "pos4"):
+        assert unf[k].astype(np.int64).tolist() == list(ounf[k]), k
+    assert unf["maxpixel"].tolist() == list(ounf["maxpixel"])
+    for k in ("Mean", "pvalue", "Stripiness"):
+        np.testing.assert_allclose(unf[k].to_numpy(dtype=float), np.array(ounf[k], float), rtol=RTOL, atol=0,
+                                   equal_nan=True)
+    assert fil["pos1"].astype(np.int64).tolist() == list(ofil["pos1"])
+    # score mode on the same map
+    tab = synth.make_stripe_table(cm, 60)
+    df = pd.DataFrame({"chr": tab["chr"], "pos1": tab["pos1"], "pos2": tab["pos2"], "chr2": tab["chr"],
+                       "pos3": tab["pos3"], "pos4": tab["pos4"]})
+    res = score_table(cm, df, norm=norm, device=dev)
+    o = driver.score(cm, tab, norm=norm)
+    for k in o:
+        np.testing.assert_allclose(res[k].to_numpy(dtype=float), np.array(o[k], float), rtol=RTOL, atol=0,
+                                   equal_nan=True)
