@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--config", default="cfg2")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--streams", type=int, default=2, help="host threads (contexts/streams) feeding each GPU")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -218,7 +219,7 @@ def reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------ score mode
-def score_bench(dev, cm, stream, torch, n_stripes=100000):
+def score_bench(devs, cm, stream, torch, n_stripes=100000):
     """BASELINE.json config 5 on the resident genome: re-score 100k synthetic candidate stripes
     (p-value + stripiness + O/E + observed mean, one fused kernel) through Device.score.  The
     chromosomes and the background tables are the ones the last compute step left on the device."""
@@ -231,7 +232,12 @@ def score_bench(dev, cm, stream, torch, n_stripes=100000):
     chrs = np.asarray(tab["chr"]).astype(str)
     groups = {c: np.nonzero(chrs == c)[0] for c in names}
     cid = {c: cm.chromnames.index(c) for c in names}
-    ex = {c: dev.expected(cid[c]) for c in names}
+    owner = {}
+    for d in devs:                      # each chromosome lives in the context that processed it
+        for k in d.loaded:
+            owner[k] = d
+    names = [c for c in names if cid[c] in owner]
+    ex = {c: owner[cid[c]].expected(cid[c]) for c in names}
     h = -(-pos[:, 3] // r) - pos[:, 2] // r
     w = -(-pos[:, 1] // r) - pos[:, 0] // r
     alg_bytes = float(np.sum(8 * h * (w + 2 * bs)) + 48 * len(pos) + 4 * 400 * 1000 * 8)
@@ -241,13 +247,14 @@ def score_bench(dev, cm, stream, torch, n_stripes=100000):
         for c in names:
             idx = groups[c]
             if len(idx):
-                res = dev.score(cid[c], pos[idx], ex[c], True)
+                res = owner[cid[c]].score(cid[c], pos[idx], ex[c], True)
                 out[idx] = res["stripiness"]
         return out
 
     for _ in range(2):
         run()
-    dev.reset_stage_times()
+    for d in devs:
+        d.reset_stage_times()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     reps = 3
@@ -257,7 +264,8 @@ def score_bench(dev, cm, stream, torch, n_stripes=100000):
     e1.record(stream)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
-    st = dev.stage_times()["score"]
+    sts = [d.stage_times()["score"] for d in devs]
+    st = {"ms": sum(x["ms"] for x in sts), "launches": sum(x["launches"] for x in sts)}
     kms = st["ms"] / reps
     peak, src = measured_peaks()
     ach = alg_bytes / 1e9 / (kms / 1e3)
@@ -307,9 +315,17 @@ def native_arm(args):
     mpix_rank = genome_mpixels(cm, [c for c in chromnames if c in cm.chroms])
     nnz_rank = sum(cm.chroms[c].nnz for c in cm.chroms)
 
-    dev = Device(local, timing=True)
+    os.environ["NCCL_DEBUG"] = os.environ.get("SNN_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
+    nstreams = 1 if strong else max(1, args.streams)
     stream = torch.cuda.current_stream()
-    dev.set_stream(stream.cuda_stream)
+    devs, tstreams = [], []
+    for k in range(nstreams):
+        d = Device(local, timing=True)
+        ts = torch.cuda.Stream() if nstreams > 1 else stream
+        d.set_stream(ts.cuda_stream)
+        devs.append(d)
+        tstreams.append(ts)
+    dev = devs[0]
     comm = cp.TorchComm() if strong else None
 
     # resident copies (HBM) and pinned host copies of the pixel tables
@@ -321,7 +337,7 @@ def native_arm(args):
         resident[c] = [h.cuda(non_blocking=True) for h in host]
     torch.cuda.synchronize()
 
-    class ResidentMatrix(gs.DeviceMatrix):
+    class ResidentMatrix(gs.DeviceMatrix):  # noqa: E306
         """DeviceMatrix whose chromosomes are built from pixel tables already in HBM."""
         def ensure(self, chrom, band_width=None):
             cid = self.chrom_id(chrom)
@@ -349,24 +365,34 @@ def native_arm(args):
 
     host_ms = {}
 
-    def step(matrix_cls):
+    def one_rank(d, c):
         t_in = time.perf_counter()
-        for cid in list(dev.loaded):
-            dev.unload_chrom(cid)
-        lib = matrix_cls(cm, bal, dev)
+        for cid in list(d.loaded):
+            d.unload_chrom(cid)
+        lib = matrix_cls_now[0](cm, bal, d)
         obj = gs.getStripe(lib, cm.binsize, 10, 8, 2.0, all_names, chromnames, all_sizes, chromsizes, 1, 3,
                            123456789, 0)
         t0 = time.perf_counter()
-        unf, fil = cp.run_pipeline(obj, cm, qs, chromnames, 0.1, '0', False, comm)
-        host_ms.clear()
-        host_ms.update(obj.last_host_ms)
-        host_ms['unload+setup'] = (t0 - t_in) * 1e3
+        unf, fil = cp.run_pipeline(obj, cm, qs, chromnames, 0.1, '0', False, c)
+        if d is devs[0]:
+            host_ms.clear()
+            host_ms.update(obj.last_host_ms)
+            host_ms['unload+setup'] = (t0 - t_in) * 1e3
         return unf, fil
+
+    matrix_cls_now = [None]
+
+    def step(matrix_cls):
+        matrix_cls_now[0] = matrix_cls
+        if nstreams == 1:
+            return one_rank(dev, comm)
+        return cp.run_threads(lambda tc: one_rank(devs[tc.rank], tc), nstreams)[0]
 
     def timed(matrix_cls, k, w):
         for _ in range(w):
             step(matrix_cls)
-        dev.reset_stage_times()
+        for d in devs:
+            d.reset_stage_times()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -389,16 +415,23 @@ def native_arm(args):
     sampler.start()
     ms_dev, (unf, fil) = timed(ResidentMatrix, steps, warm)
     clocks = sampler.stop()
-    stages = dev.stage_times()
+    stages = {}
+    for d in devs:
+        for k, v in d.stage_times().items():
+            acc = stages.setdefault(k, {"ms": 0.0, "launches": 0})
+            acc["ms"] += v["ms"]
+            acc["launches"] += v["launches"]
     host_phases = {k: round(v, 2) for k, v in host_ms.items()}
-    dev.h2d_bytes = dev.d2h_bytes = 0
+    for d in devs:
+        d.h2d_bytes = d.d2h_bytes = 0
     ms_e2e, _ = timed(PinnedMatrix, steps, 1)
-    h2d_step, d2h_step = dev.h2d_bytes // (steps + 1), dev.d2h_bytes // (steps + 1)
+    h2d_step = sum(d.h2d_bytes for d in devs) // (steps + 1)
+    d2h_step = sum(d.d2h_bytes for d in devs) // (steps + 1)
 
     score_mode = None
     if rank == 0:
         try:
-            score_mode = score_bench(dev, cm, stream, torch)
+            score_mode = score_bench(devs, cm, stream, torch)
         except Exception as e:  # secondary measurement must not break the headline
             score_mode = {"error": repr(e)}
     if world > 1:
@@ -452,6 +485,7 @@ def native_arm(args):
                                        "per genome), --norm None, -m %s, stages 1-5 of compute" %
                                        (args.config, sum(int(math.ceil(s / binsize)) for s in sizes),
                                         mpix_rank if not strong else mpix_total, QS),
+                           "host_threads_per_gpu": nstreams,
                            "parallelism": ("1 genome per GPU (independent samples)" if not strong else
                                            "1 genome sharded by chromosome (LPT) over %d GPUs" % world),
                            "l2": "inputs larger than L2 (pixel tables %.0f MB per genome)" % (nnz_rank * 12 / 1e6),
@@ -461,7 +495,8 @@ def native_arm(args):
                         "d2h_bytes_per_step": int(d2h_step), "ms_per_step": ms_e2e / steps},
                 "gpu_launches": launches, "host_phases_ms_last_step": host_phases, "score_mode": score_mode, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
-    dev.close()
+    for d in devs:
+        d.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -159,6 +159,58 @@ class TorchComm:
         return out
 
 
+class ThreadComm:
+    """Several host threads feeding ONE GPU through separate contexts/streams ("virtual ranks"):
+    while one thread post-processes its chromosome on the host (table assembly, dedup), the
+    kernels of the others keep the GPU busy.  Same exchange points as the multi-GPU pipeline,
+    implemented with a barrier.  Create with ThreadComm.group(k)."""
+
+    def __init__(self, rank, world, shared):
+        self.rank, self.world, self._sh = rank, world, shared
+
+    @classmethod
+    def group(cls, world):
+        import threading
+        shared = {"slots": [None] * world, "barrier": threading.Barrier(world)}
+        return [cls(r, world, shared) for r in range(world)]
+
+    def all_gather(self, obj):
+        sh = self._sh
+        sh["slots"][self.rank] = obj
+        sh["barrier"].wait()
+        out = list(sh["slots"])
+        sh["barrier"].wait()
+        return out
+
+
+def run_threads(fn, world):
+    """Run fn(comm) on `world` host threads (one ThreadComm each); returns the per-rank results
+    and re-raises the first exception."""
+    import threading
+    comms = ThreadComm.group(world)
+    res, err = [None] * world, [None] * world
+
+    def work(i):
+        try:
+            res[i] = fn(comms[i])
+        except BaseException as e:  # noqa: BLE001 - re-raised below
+            err[i] = e
+            comms[i]._sh["barrier"].abort()
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    for e in err:
+        if e is not None and not isinstance(e, threading.BrokenBarrierError):
+            raise e
+    for e in err:
+        if e is not None:
+            raise e
+    return res
+
+
 def lpt_partition(names, sizes, world):
     """Longest-processing-time-first assignment of chromosomes to ranks (work ~ bins).
     Deterministic: ties keep file order.  Returns {chrom: rank}."""
@@ -256,7 +308,7 @@ def run_pipeline(obj, cm, qs, chromnames, pvalue, mask, slow, comm=None, say=lam
 def run_stages(cm: ContactMap, norm='KR', chrom='all', canny=2.0, minL=10, maxW=8,
                maxpixel='0.95,0.96,0.97,0.98,0.99', numcores=1, pvalue=0.1, mask='0', slow=False,
                bfilter=3, seed=123456789, device=None, device_id=0, gray_variant=0, verbose=False,
-               return_stages=False, comm=None):
+               return_stages=False, comm=None, streams=1):
     """Stages 1-5 of ``compute`` on an in-memory contact map: everything between "matrix
     available" and "result tables on the host" (the span the Mpixels/s metric is defined on).
     With a multi-rank `comm` every rank processes the chromosomes it owns and all ranks return
@@ -266,6 +318,18 @@ def run_stages(cm: ContactMap, norm='KR', chrom='all', canny=2.0, minL=10, maxW=
     chroms = chrom.split(',') if isinstance(chrom, str) else list(chrom)
     bal = resolve_norm(cm, norm, "compute", verbose)
     all_names, all_sizes, chromnames, chromsizes = compute_chromosomes(cm, chroms)
+    if streams > 1 and comm is None and device is None:
+        # `streams` host threads, each with its own context on the same GPU (see ThreadComm)
+        def one(tc):
+            d = Device(device_id)
+            try:
+                o = make_object(cm, bal, d, all_names, all_sizes, chromnames, chromsizes, minL, maxW, canny,
+                                numcores, bfilter, seed, gray_variant)
+                return run_pipeline(o, cm, qs, chromnames, pvalue, mask, slow, tc,
+                                    say if tc.rank == 0 else (lambda *a, **k: None), return_stages)
+            finally:
+                d.close()
+        return run_threads(one, streams)[0]
     own = device is None
     dev = device if device is not None else Device(device_id)
     try:

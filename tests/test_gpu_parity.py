@@ -328,3 +328,12 @@ def test_other_resolutions_match_oracle(dev, cfg, norm):
     for k in o:
         np.testing.assert_allclose(res[k].to_numpy(dtype=float), np.array(o[k], float), rtol=RTOL, atol=0,
                                    equal_nan=True)
+
+
+def test_host_threads_give_identical_tables(tiny2_cm):
+    """streams=2: two host threads / contexts on one GPU (ThreadComm) vs the single-context run."""
+    a_unf, a_fil = cp.run_stages(tiny2_cm, norm="KR", maxpixel="0.95,0.98", streams=1)
+    b_unf, b_fil = cp.run_stages(tiny2_cm, norm="KR", maxpixel="0.95,0.98", streams=2)
+    assert len(a_unf) > 0
+    assert a_unf.reset_index(drop=True).equals(b_unf.reset_index(drop=True))
+    assert a_fil.reset_index(drop=True).equals(b_fil.reset_index(drop=True))
