@@ -145,7 +145,8 @@ int snn_set_background_impl(snn_ctx* ctx, int64_t ncol, const double* tables) {
     }
     SNN_CUDA(cudaMemcpyAsync(scratch, tables, bytes, cudaMemcpyHostToDevice, ctx->stream));
     size_t smem = (size_t)npow2 * sizeof(double);
-    SNN_CUDA(cudaFuncSetAttribute(k_bg_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // constant across calls (host threads may race on the attribute otherwise)
+    SNN_CUDA(cudaFuncSetAttribute(k_bg_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     {
         SnnScope scope(ctx, ST_BGSORT, 1);
         k_bg_sort<<<(unsigned)rows, 512, smem, ctx->stream>>>((const double*)scratch, ncol, npow2, ctx->bg_sorted,

@@ -439,6 +439,14 @@ int snn_score_impl(snn_ctx* ctx, SnnChrom* c, int64_t n, const int64_t* pos, con
         ++launches;
     }
     const size_t per_row = 4 * sizeof(double) + sizeof(int) + 1;
+    {   // one attribute value for every launch (contexts on several host threads share the function)
+        size_t worst = 0;
+        for (int k = 0; k < 3; ++k) {
+            size_t v = (size_t)cls[k].hcap * per_row + (size_t)cls[k].wcap * sizeof(double) + 64;
+            if (v > worst) worst = v;
+        }
+        SNN_CUDA(cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)worst));
+    }
     for (int k = 0; k < 3; ++k) {
         if (order[k].empty()) continue;
         ScoreParams P;
@@ -449,7 +457,6 @@ int snn_score_impl(snn_ctx* ctx, SnnChrom* c, int64_t n, const int64_t* pos, con
         P.hmax = cls[k].hcap;
         P.bg_ncol = ctx->bg_ncol;
         const size_t smem = (size_t)cls[k].hcap * per_row + (size_t)cls[k].wcap * sizeof(double) + 64;
-        SNN_CUDA(cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_score<<<(unsigned)order[k].size(), SCORE_THREADS, smem, ctx->stream>>>(
             snn_view(c), dpos, dstale, dorder + start[k], drex, ctx->bg_sorted, ctx->bg_valid, P, cls[k].wcap, want_p,
             want_s, dout);

@@ -251,20 +251,24 @@ class getStripe:
         return full[0], full[1], full[2], full[3]
 
     # ------------------------------------------------------------------ a5-a15
-    def _candidate_frame(self, cand, chrom, perc):
+    def _candidate_frame(self, cand, chrom_names, perc):
+        """Candidate records -> DataFrame with the reference's columns (getStripe.py:1099-1110).
+        `chrom_names` is one name or an array with one name per record."""
         n = len(cand)
         h = cand["h"].astype(np.int64)
         w = cand["w"].astype(np.int64)
         with np.errstate(divide="ignore", invalid="ignore"):
             mean = cand["total"] / h / w
+        chrs = np.full(n, chrom_names, dtype=object) if isinstance(chrom_names, str) else np.asarray(chrom_names, dtype=object)
+        label = np.full(n, str(perc * 100) + '%', dtype=object)
         df = pd.DataFrame({
-            'chr': [chrom] * n, 'pos1': cand["pos1"], 'pos2': cand["pos2"], 'chr2': [chrom] * n,
+            'chr': chrs, 'pos1': cand["pos1"], 'pos2': cand["pos2"], 'chr2': chrs,
             'pos3': cand["pos3"], 'pos4': cand["pos4"],
             'length': cand["pos4"] - cand["pos3"] + 1, 'width': cand["pos2"] - cand["pos1"] + 1,
-            'total': cand["total"], 'Mean': mean, 'maxpixel': [str(perc * 100) + '%'] * n,
+            'total': cand["total"], 'Mean': mean, 'maxpixel': label,
             'num': cand["frame"].astype(np.int64), 'start': cand["start"].astype(np.int64),
             'end': cand["end"].astype(np.int64), 'x': cand["x"].astype(np.int64),
-            'y': cand["y"].astype(np.int64), 'h': h, 'w': w, 'medpixel': np.full(n, np.nan)})
+            'y': cand["y"].astype(np.int64), 'h': h, 'w': w, 'medpixel': np.full(n, np.nan)}, copy=False)
         return df
 
     def extract_all(self, MP, quantiles: Sequence[float], bgleft_up, bgright_up, bgleft_down,
@@ -302,17 +306,18 @@ class getStripe:
             else:
                 pv = np.zeros(0)
             kept.append((chrom, cand, pv))
+        # one table per maxpixel value, chromosomes in order (one DataFrame construction per q)
+        kept = [k for k in kept if len(k[1])]
         out = []
+        if kept:
+            allc = np.concatenate([k[1] for k in kept])
+            allp = np.concatenate([k[2] for k in kept])
+            alln = np.concatenate([np.full(len(k[1]), k[0], dtype=object) for k in kept])
         for qi, perc in enumerate(quantiles):
-            parts, pvs = [], []
-            for chrom, cand, pv in kept:
-                sel = cand["q"] == qi
-                if sel.any():
-                    parts.append(self._candidate_frame(cand[sel], chrom, perc))
-                    pvs.append(pv[sel])
-            if parts:
-                res = pd.concat(parts).reset_index(drop=True)
-                res = res.assign(pvalue=np.concatenate(pvs))
+            sel = (allc["q"] == qi) if kept else None
+            if kept and sel.any():
+                res = self._candidate_frame(allc[sel], alln[sel], perc)
+                res['pvalue'] = allp[sel]
             else:
                 res = pd.DataFrame(columns=RESULT_COLUMNS + ['pvalue'])
             out.append(res)
