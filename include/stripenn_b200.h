@@ -147,6 +147,16 @@ int snn_score(snn_ctx* ctx, int chrom_id, int64_t n, const int64_t* pos, const i
               double* pvalue, double* stripiness, double* oe_mean, double* oe_total,
               double* o_mean, double* o_sum);
 
+/* Same for stripes of several resident chromosomes in ONE call (the reference loops over the
+ * whole table: getStripe.py:576 `for i in range(len(df))`, :764 `Parallel(...)(... for i in
+ * range(nrow))`): chrom_ids = the nchrom chromosomes involved, expected = nchrom x SNN_NDIST
+ * (row k = mpmean of chrom_ids[k]; NULL: p-values only), chrom_index[i] = index into chrom_ids
+ * of stripe i (NULL: all stripes belong to chrom_ids[0]).  All chromosomes share one bin size. */
+int snn_score_multi(snn_ctx* ctx, int nchrom, const int32_t* chrom_ids, const double* expected,
+                    int64_t n, const int32_t* chrom_index, const int64_t* pos, const int32_t* stale,
+                    double* pvalue, double* stripiness, double* oe_mean, double* oe_total,
+                    double* o_mean, double* o_sum);
+
 /* ---- a15: getStripe.RemoveRedundant (:1116-1196) — host code (C++), no device work.
  * group = chromosome index per row, num = window id, pos = n x 4, h/w = the size columns,
  * key = pvalue or Stripiness (unused for by = 0).  by: 0 size, 1 pvalue, 2 score.

@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libstripenn_b200.so")
+# STRIPENN_B200_LIB: another build of the same library (kernel tuning experiments, tools/)
+LIB_PATH = os.environ.get("STRIPENN_B200_LIB") or os.path.join(HERE, "lib", "libstripenn_b200.so")
 
 NDIST = 400
 NBRIGHT = 6
@@ -66,6 +67,7 @@ SIGNATURES = {
     "snn_debug_stages": (C.c_int, [_P, C.c_int, C.c_double, _P, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_int, _i32p, _P, _P, _P, _P, _P, _P, _P]),
     "snn_score": (C.c_int, [_P, C.c_int, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "snn_score_multi": (C.c_int, [_P, C.c_int, _P, _P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "snn_remove_redundant": (C.c_int, [C.c_int64, _P, _P, _P, _P, _P, _P, C.c_int, _P]),
     "snn_stage_times": (C.c_int, [_P, C.c_int, C.POINTER(C.c_char_p), _f64p, _i64p]),
     "snn_reset_stage_times": (C.c_int, [_P]),

@@ -6,7 +6,7 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include "snn_internal.cuh"
+#include "score_warp.cuh"
 
 static thread_local std::string g_last_error;
 
@@ -341,6 +341,27 @@ int snn_score(snn_ctx* ctx, int chrom_id, int64_t n, const int64_t* pos, const i
     if (pvalue && !ctx->bg_sorted)
         return snn_fail(ctx, SNN_ESTATE, "snn_score: p-values requested before snn_set_background");
     return snn_score_impl(ctx, c, n, pos, stale, expected, pvalue, stripiness, oe_mean, oe_total, o_mean, o_sum);
+}
+
+int snn_score_multi(snn_ctx* ctx, int nchrom, const int32_t* chrom_ids, const double* expected, int64_t n,
+                    const int32_t* chrom_index, const int64_t* pos, const int32_t* stale, double* pvalue,
+                    double* stripiness, double* oe_mean, double* oe_total, double* o_mean, double* o_sum) {
+    if (!ctx) return snn_fail(nullptr, SNN_EINVAL, "ctx is NULL");
+    if (nchrom < 1 || !chrom_ids || n < 0 || (n > 0 && !pos))
+        return snn_fail(ctx, SNN_EINVAL, "snn_score_multi: bad arguments");
+    SNN_CUDA(cudaSetDevice(ctx->device));
+    std::vector<ScoreSlot> slots((size_t)nchrom);
+    for (int k = 0; k < nchrom; ++k) {
+        SnnChrom* c = snn_find_chrom(ctx, chrom_ids[k]);
+        if (!c) return snn_fail(ctx, SNN_ESTATE, "chromosome %d is not loaded", chrom_ids[k]);
+        slots[k].c = c;
+        slots[k].expected = expected ? expected + (size_t)k * SNN_NDIST : nullptr;
+    }
+    if (n == 0) return SNN_OK;
+    if (pvalue && !ctx->bg_sorted)
+        return snn_fail(ctx, SNN_ESTATE, "snn_score_multi: p-values requested before snn_set_background");
+    return snn_score_multi_impl(ctx, slots, n, chrom_index, pos, stale, pvalue, stripiness, oe_mean, oe_total,
+                                o_mean, o_sum);
 }
 
 int snn_stage_times(snn_ctx* ctx, int cap, const char** names, double* ms, int64_t* launches) {

@@ -10,6 +10,8 @@
 //                  here, see the comment), [1 2 1] passes from float64 copies in shared memory
 // ncu (profiles/r01a_*): the generic kernels were bound by the conversion (XU) pipe at 64-68 %
 // and by issue slots at 84 %, not by FP64 or HBM.
+#include <stdlib.h>
+
 #include "image.cuh"
 
 __device__ __forceinline__ int f_reflect101(int i, int n) {
@@ -178,6 +180,146 @@ __global__ void __launch_bounds__(256) k_gauss_h8(const float* __restrict__ in_a
     *reinterpret_cast<float4*>(out + j0 + 4) = o1;
 }
 
+// ---- Gaussian, marching versions -------------------------------------------------------------------
+// ncu on k_gauss_v8/h8 (profiles/r01c): 61 / 94 instructions per output for 25 float64 operations,
+// load latency exposed (long-scoreboard 5.9 stalled warps per issue) because every thread loads
+// its 24 inputs and then computes.  Here a thread walks along the filter axis with the 2R+1
+// inputs of the current output in registers (rotating slots, the loop is unrolled by 2R+1 so no
+// value is ever moved), each input is loaded and widened ONCE, and the loads of the next 2R+1
+// outputs are in flight while the current ones are computed.  What is left per output is the
+// 25 float64 operations of scipy's correlate1d plus ~8 others: the FP64 pipe is the bound.
+#define GV_SEG 102   // outputs per thread along axis 0 (6 groups of 17 at the default radius)
+
+template <int R>
+__global__ void __launch_bounds__(128) k_gauss_vm(const float* __restrict__ in_all, const FrameInfo* __restrict__ info,
+                                                  int passes_per_frame, GaussParams G, float* __restrict__ out_all) {
+    constexpr int W = 2 * R + 1;
+    const int pass = blockIdx.z;
+    const int S = info[pass / passes_per_frame].S;
+    const int j = blockIdx.x * 32 + threadIdx.x;
+    const int i0 = (blockIdx.y * 4 + threadIdx.y) * GV_SEG;
+    if (j >= S || i0 >= S) return;
+    const int i1 = min(i0 + GV_SEG, S);
+    const float* in = in_all + (int64_t)pass * SNN_SMAX * SNN_SMAX + j;
+    float* out = out_all + (int64_t)pass * SNN_SMAX * SNN_SMAX + j;
+    double x[W];   // at output row i (slot u = (i - i0) % W): row i - R + k lives in slot (u + 1 + k) % W
+    x[0] = 0.0;
+#pragma unroll
+    for (int k = 0; k < 2 * R; ++k) {
+        const int r = i0 - R + k;
+        x[k + 1] = (r >= 0 && r < S) ? (double)in[r * SNN_SMAX] : 0.0;
+    }
+    float nx[W];
+#pragma unroll
+    for (int u = 0; u < W; ++u) {
+        const int r = i0 + R + u;
+        nx[u] = (r < S) ? in[r * SNN_SMAX] : 0.f;
+    }
+    const float* pin = in + (int64_t)(i0 + W + R) * SNN_SMAX;   // first row of the next group's inputs
+    float* pout = out + (int64_t)i0 * SNN_SMAX;
+    for (int base = i0; base < i1; base += W) {
+        float cur[W];
+#pragma unroll
+        for (int u = 0; u < W; ++u) cur[u] = nx[u];
+        if (base + W < i1) {
+            if (base + 2 * W + R <= S) {          // every row of the next group exists: plain loads
+#pragma unroll
+                for (int u = 0; u < W; ++u) nx[u] = pin[u * SNN_SMAX];
+            } else {
+#pragma unroll
+                for (int u = 0; u < W; ++u) nx[u] = (base + W + R + u < S) ? pin[u * SNN_SMAX] : 0.f;
+            }
+        }
+        const int left = i1 - base;                 // outputs still wanted (tail group: stores predicated)
+#pragma unroll
+        for (int u = 0; u < W; ++u) {
+            x[u] = (double)cur[u];
+            double t = x[(u + 1 + R) % W] * G.w[R];
+#pragma unroll
+            for (int k = R; k >= 1; --k) t = t + (x[(u + 1 + R - k) % W] + x[(u + 1 + R + k) % W]) * G.w[R - k];
+            if (u < left) pout[u * SNN_SMAX] = (float)t;
+        }
+        pin += W * SNN_SMAX;
+        pout += W * SNN_SMAX;
+    }
+}
+
+// axis 1 + bleed-over division: a CTA (4 warps) owns a tile of 32 rows x 8(2R+1) columns.  It
+// stages the tile plus R halo columns in shared memory (coalesced loads, zeros outside the
+// image), then lane = row and warp = 2(2R+1)-column segment: the same walk as above along the
+// row out of shared memory (odd pitch: the 32 lanes hit 32 banks) into a second tile, and a
+// coalesced pass divides by the bleed-over image and stores.  37 KB per CTA: 6 CTAs per SM.
+#define GH_ROWS 32
+#define GH_WARPS 4
+template <int R>
+__global__ void __launch_bounds__(GH_WARPS * 32) k_gauss_hm(const float* __restrict__ in_all,
+                                                            const FrameInfo* __restrict__ info, int passes_per_frame,
+                                                            GaussParams G, const float* __restrict__ bleed_all,
+                                                            float* __restrict__ out_all) {
+    constexpr int W = 2 * R + 1;
+    constexpr int TC = 2 * W * GH_WARPS;          // tile columns
+    constexpr int PIN = (TC + 2 * R) | 1;         // input tile pitch (tile column t at index t + R)
+    constexpr int POUT = TC | 1;
+    __shared__ float tin[GH_ROWS * PIN];
+    __shared__ float tout[GH_ROWS * POUT];
+    const int pass = blockIdx.z;
+    const int f = pass / passes_per_frame;
+    const int S = info[f].S;
+    const int r0 = blockIdx.y * GH_ROWS, ct0 = blockIdx.x * TC;
+    if (r0 >= S || ct0 >= S) return;
+    const int nr = min(GH_ROWS, S - r0);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* in = in_all + (int64_t)pass * SNN_SMAX * SNN_SMAX + (int64_t)r0 * SNN_SMAX;
+    // phase 1: rows -> tin with cp.async (all copies of a thread in flight at once; a source
+    // size of 0 zero-fills the cells outside the image)
+    {
+        constexpr int NCOL = TC + 2 * R;
+        const unsigned tin_s = (unsigned)__cvta_generic_to_shared(tin);
+#pragma unroll 4
+        for (int e = threadIdx.x; e < GH_ROWS * NCOL; e += GH_WARPS * 32) {
+            const int rr = e / NCOL, p = e - rr * NCOL;
+            const int c = ct0 - R + p;
+            const bool ok = rr < nr && c >= 0 && c < S;
+            const float* src = ok ? in + rr * SNN_SMAX + c : in;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(tin_s + (unsigned)(rr * PIN + p) * 4u),
+                         "l"(src), "r"(ok ? 4 : 0));
+        }
+        asm volatile("cp.async.commit_group;");
+        asm volatile("cp.async.wait_group 0;");
+    }
+    __syncthreads();
+    // phase 2: lane = row, warp = segment of 2W columns
+    {
+        const float* pin = tin + lane * PIN + warp * 2 * W;   // pin[k] = tile column (segment start - R + k)
+        float* pout = tout + lane * POUT + warp * 2 * W;
+        double x[W];
+        x[0] = 0.0;
+#pragma unroll
+        for (int k = 0; k < 2 * R; ++k) x[k + 1] = (double)pin[k];
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+#pragma unroll
+            for (int u = 0; u < W; ++u) {
+                x[u] = (double)pin[g * W + u + 2 * R];
+                double t = x[(u + 1 + R) % W] * G.w[R];
+#pragma unroll
+                for (int k = R; k >= 1; --k) t = t + (x[(u + 1 + R - k) % W] + x[(u + 1 + R + k) % W]) * G.w[R - k];
+                pout[g * W + u] = (float)t;
+            }
+        }
+    }
+    __syncthreads();
+    // phase 3: divide by the bleed-over image, coalesced stores
+    const float* bleed = bleed_all + (int64_t)f * SNN_SMAX * SNN_SMAX + (int64_t)r0 * SNN_SMAX + ct0;
+    float* out = out_all + (int64_t)pass * SNN_SMAX * SNN_SMAX + (int64_t)r0 * SNN_SMAX + ct0;
+    const int nc = min(TC, S - ct0);
+#pragma unroll 4
+    for (int e = threadIdx.x; e < GH_ROWS * TC; e += GH_WARPS * 32) {
+        const int rr = e / TC, t = e - rr * TC;
+        if (rr < nr && t < nc) out[rr * SNN_SMAX + t] = tout[rr * POUT + t] / bleed[rr * SNN_SMAX + t];
+    }
+}
+
 // ---- Sobel + magnitude + NMS ------------------------------------------------------------------------
 __device__ __forceinline__ int f_symm(int i, int n) {
     if (i < 0) i = -i - 1;
@@ -318,7 +460,7 @@ __global__ void __launch_bounds__(256) k_sobel_nms2(const float* __restrict__ sm
 // its source position — exactly how ndi.sobel pads the derivative image in its second pass.
 #define SN_ROWS 64
 #define SN_WARPS 15
-__global__ void __launch_bounds__(SN_WARPS * 32) k_sobel_nms3(const float* __restrict__ sm_all,
+__global__ void __launch_bounds__(SN_WARPS * 32, 3) k_sobel_nms3(const float* __restrict__ sm_all,
                                                               const FrameInfo* __restrict__ info,
                                                               int passes_per_frame, uint32_t* __restrict__ low_all,
                                                               uint32_t* __restrict__ high_all,
@@ -336,56 +478,65 @@ __global__ void __launch_bounds__(SN_WARPS * 32) k_sobel_nms3(const float* __res
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cbase = warp * 28;
-    if (cbase < S) {
+    if (cbase < S) {    // S >= 11 here (smaller windows are skipped upstream)
         const int c = cbase + lane - 2;
-        const int cc = f_symm(c, S);
-        const bool colok = cc >= 0 && cc < S;
-        const float* smo = sm_all + (int64_t)pass * SNN_SMAX * SNN_SMAX + (colok ? cc : 0);
+        const int cc = min(max(f_symm(c, S), 0), S - 1);   // lanes beyond the image read a valid (unused) column
+        const float* colp = sm_all + (int64_t)pass * SNN_SMAX * SNN_SMAX + cc;
         const unsigned FULL = 0xffffffffu;
+        const bool lanemine = lane >= 2 && lane < 30 && c >= 1 && c <= S - 2;   // NMS columns of this lane
+        const bool lanedbg = lane >= 2 && lane < 30 && c < S;
+        const int rlo = max(r0, 1), rhi = min(r1, S - 1);                       // NMS rows [rlo, rhi)
+        const int word = cbase >> 5, off = cbase & 31;
         float s0 = 0.f, s1 = 0.f;
         double dj0 = 0.0, dj1 = 0.0;
         float mA = 0.f, mB = 0.f, isB = 0.f, jsB = 0.f;
+        float mAl = 0.f, mAr = 0.f, mBl = 0.f, mBr = 0.f;   // horizontal neighbours, carried down the rows
+        // the row after next is already in flight while a row is processed
+        float nxt = colp[f_symm(r0 - 2, S) * SNN_SMAX];
         for (int rho = r0 - 2; rho <= r1 + 1; ++rho) {
-            const int rr = f_symm(rho, S);
-            const float s2 = (colok && rr >= 0 && rr < S) ? smo[rr * SNN_SMAX] : 0.f;
+            const float s2 = nxt;
+            {
+                int rn = rho + 1;                       // scipy 'reflect' row of the next iteration
+                rn = rn < 0 ? -rn - 1 : rn;
+                rn = rn >= S ? 2 * S - 1 - rn : rn;
+                rn = max(rn, 0);
+                nxt = colp[rn * SNN_SMAX];
+            }
             // axis-1 derivative of row rho
             const float sl = __shfl_up_sync(FULL, s2, 1), sr = __shfl_down_sync(FULL, s2, 1);
             const double djn = (double)(-__fsub_rn(sl, sr));
-            // axis-0 derivative of row rho-1, then the [1 2 1] passes
-            const double di1 = (double)(-__fsub_rn(s0, s2));
-            const double dil = __shfl_up_sync(FULL, di1, 1), dir = __shfl_down_sync(FULL, di1, 1);
+            // axis-0 derivative of row rho-1 (float32, exact — see above), then the [1 2 1] passes;
+            // the neighbours travel as float32 and are widened after the shuffle
+            const float di1f = -__fsub_rn(s0, s2);
+            const double di1 = (double)di1f;
+            const double dil = (double)__shfl_up_sync(FULL, di1f, 1), dir = (double)__shfl_down_sync(FULL, di1f, 1);
             const float is1 = (float)(di1 * 2.0 + (dil + dir) * 1.0);
             const float js1 = (float)(dj1 * 2.0 + (dj0 + djn) * 1.0);
             float mm = is1 * is1;
             mm = mm + js1 * js1;
             const float m1 = sqrtf(mm);
             // NMS of row rho-2 from mag rows rho-3 (mA), rho-2 (mB), rho-1 (m1)
-            const float mAl = __shfl_up_sync(FULL, mA, 1), mAr = __shfl_down_sync(FULL, mA, 1);
-            const float mBl = __shfl_up_sync(FULL, mB, 1), mBr = __shfl_down_sync(FULL, mB, 1);
             const float m1l = __shfl_up_sync(FULL, m1, 1), m1r = __shfl_down_sync(FULL, m1, 1);
             const int r = rho - 2;
             bool keep = false, strong = false;
-            const bool mine = lane >= 2 && lane < 30 && c < S;
-            if (mag_dbg && mine && rho - 1 >= r0 && rho - 1 < r1)
+            if (mag_dbg && lanedbg && rho - 1 >= r0 && rho - 1 < r1)
                 mag_dbg[(int64_t)pass * SNN_SMAX * SNN_SMAX + (rho - 1) * SNN_SMAX + c] = m1;
-            if (mine && r >= r0 && r < r1 && r >= 1 && r <= S - 2 && c >= 1 && c <= S - 2 && mB >= 0.1f) {
+            const bool rowok = r >= rlo && r < rhi;     // warp-uniform
+            if (rowok && lanemine && mB >= 0.1f) {
                 const float is = isB, js = jsB, m = mB;
                 const bool up = is >= 0.f, down = is <= 0.f, right = js >= 0.f, left = js <= 0.f;
-                const bool cond1 = (up && right) || (down && left);
-                const bool cond2 = (down && right) || (up && left);
+                const bool c1 = (up && right) || (down && left);
+                const bool c2 = !c1 && ((down && right) || (up && left));
                 const float ai = fabsf(is), aj = fabsf(js);
-                float w = 0.f, n11 = 0.f, n12 = 0.f, n21 = 0.f, n22 = 0.f;
-                bool ok = true;
-                if (cond1) {
-                    if (ai > aj) { w = aj / ai; n11 = m1;  n12 = m1r; n21 = mA;  n22 = mAl; }
-                    else         { w = ai / aj; n11 = mBr; n12 = m1r; n21 = mBl; n22 = mAl; }
-                } else if (cond2) {
-                    if (ai < aj) { w = ai / aj; n11 = mBr; n12 = mAr; n21 = mBl; n22 = m1l; }
-                    else         { w = aj / ai; n11 = mA;  n12 = mAr; n21 = m1;  n22 = m1l; }
-                } else {
-                    ok = false;
-                }
-                if (ok) {
+                if (c1 || c2) {
+                    // the four branches of _nonmaximum_suppression_bilinear differ only in WHICH
+                    // neighbours they read: the weight is always smaller/larger gradient component
+                    // (cond1: |i|>|j| -> |j|/|i| else |i|/|j| ; cond2: |i|<|j| -> |i|/|j| else |j|/|i|)
+                    const bool idom = c1 ? (ai > aj) : !(ai < aj);
+                    const float w = (idom ? aj : ai) / (idom ? ai : aj);
+                    const float n12 = c1 ? m1r : mAr, n22 = c1 ? mAl : m1l;
+                    const float n11 = idom ? (c1 ? m1 : mA) : mBr;
+                    const float n21 = idom ? (c1 ? mA : m1) : mBl;
                     const double omw = 1.0 - (double)w;
                     const double plus = (double)(n12 * w) + (double)n11 * omw;
                     const double minus = (double)(n22 * w) + (double)n21 * omw;
@@ -394,20 +545,24 @@ __global__ void __launch_bounds__(SN_WARPS * 32) k_sobel_nms3(const float* __res
                     strong = keep && (m >= 0.2f);
                 }
             }
-            const unsigned lw = (__ballot_sync(FULL, keep) >> 2) & 0x0fffffffu;
-            const unsigned hw = (__ballot_sync(FULL, strong) >> 2) & 0x0fffffffu;
-            if (lane == 0 && lw) {
-                const int word = cbase >> 5, off = cbase & 31;
-                atomicOr(&lowS[r - r0][word], lw << off);
-                if (off > 4 && word + 1 < SNN_WPR) atomicOr(&lowS[r - r0][word + 1], lw >> (32 - off));
-                if (hw) {
-                    atomicOr(&highS[r - r0][word], hw << off);
-                    if (off > 4 && word + 1 < SNN_WPR) atomicOr(&highS[r - r0][word + 1], hw >> (32 - off));
+            if (rowok) {
+                const unsigned lw = (__ballot_sync(FULL, keep) >> 2) & 0x0fffffffu;
+                if (lw) {
+                    const unsigned hw = (__ballot_sync(FULL, strong) >> 2) & 0x0fffffffu;
+                    if (lane == 0) {
+                        atomicOr(&lowS[r - r0][word], lw << off);
+                        if (off > 4 && word + 1 < SNN_WPR) atomicOr(&lowS[r - r0][word + 1], lw >> (32 - off));
+                        if (hw) {
+                            atomicOr(&highS[r - r0][word], hw << off);
+                            if (off > 4 && word + 1 < SNN_WPR) atomicOr(&highS[r - r0][word + 1], hw >> (32 - off));
+                        }
+                    }
                 }
             }
             s0 = s1; s1 = s2;
             dj0 = dj1; dj1 = djn;
             mA = mB; mB = m1;
+            mAl = mBl; mAr = mBr; mBl = m1l; mBr = m1r;
             isB = is1; jsB = js1;
         }
     }
@@ -429,7 +584,27 @@ int snn_launch_gray6(snn_ctx* ctx, const ExtractPlan& pl, int nf) {
 
 bool snn_gauss_fast_supported(int radius) { return radius == 8 || radius == 10 || radius == 6; }
 
+template <int R>
+static int launch_gauss_march(snn_ctx* ctx, const ExtractPlan& pl, int npass, int ppf) {
+    constexpr int TC = 2 * (2 * R + 1) * GH_WARPS;
+    const int nseg = (SNN_SMAX + GV_SEG - 1) / GV_SEG;
+    k_gauss_vm<R><<<dim3(13, (nseg + 3) / 4, npass), dim3(32, 4), 0, ctx->stream>>>(pl.bufA, pl.info, ppf, pl.gauss,
+                                                                                   pl.bufB);
+    k_gauss_hm<R><<<dim3((SNN_SMAX + TC - 1) / TC, (SNN_SMAX + GH_ROWS - 1) / GH_ROWS, npass), GH_WARPS * 32, 0,
+                    ctx->stream>>>(pl.bufB, pl.info, ppf, pl.gauss, pl.bleed, pl.bufC);
+    SNN_LAUNCH_CHECK("k_gauss_march");
+    return SNN_OK;
+}
+
 int snn_launch_gauss_fast(snn_ctx* ctx, const ExtractPlan& pl, int npass, int ppf) {
+    static const bool old8 = getenv("SNN_GAUSS8") != nullptr;   // A/B switch for the 8-outputs-per-thread kernels
+    if (!old8) {
+        switch (pl.gauss.radius) {
+            case 8: return launch_gauss_march<8>(ctx, pl, npass, ppf);
+            case 10: return launch_gauss_march<10>(ctx, pl, npass, ppf);
+            default: return launch_gauss_march<6>(ctx, pl, npass, ppf);
+        }
+    }
     const dim3 gv(13, (SNN_SMAX + 8 * NOUT - 1) / (8 * NOUT), npass), bv(32, 8);
     const int per_pass = SNN_SMAX * ((SNN_SMAX + NOUT - 1) / NOUT);
     const dim3 gh((per_pass + 255) / 256, 1, npass), bh(256);

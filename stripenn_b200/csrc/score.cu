@@ -9,7 +9,11 @@
 //
 // Roofline: HBM.  Algorithmic bytes per stripe: 8 * h * (w + 2*bs) window bytes + 48 B out;
 // the 12.8 MB background tables are read once per launch (L2-resident afterwards).
-#include "snn_internal.cuh"
+#include <string.h>
+
+#include <algorithm>
+
+#include "score_warp.cuh"
 
 #define SCORE_THREADS 128
 #define SCORE_MAXCOLS 512
@@ -380,88 +384,153 @@ __global__ void __launch_bounds__(SCORE_THREADS) k_score(MatView m, const int64_
     if (threadIdx.x == 0) o[1] = med * avgdiff;
 }
 
-__global__ void k_recip_expected(const double* __restrict__ ex, double* __restrict__ rex) {
+// slot y: ex[y*1024 + t] -> ex[y*1024 + 512 + t] = 1 / (expected + 1e-8)   (getStripe.py:650)
+__global__ void k_recip_expected(double* __restrict__ ex) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < SNN_NDIST) rex[t] = 1.0 / (ex[t] + .00000001);
+    double* e = ex + (size_t)blockIdx.y * 1024;
+    if (t < SNN_NDIST) e[512 + t] = 1.0 / (e[t] + .00000001);
 }
 
-int snn_score_impl(snn_ctx* ctx, SnnChrom* c, int64_t n, const int64_t* pos, const int32_t* stale,
-                   const double* expected, double* pvalue, double* stripiness, double* oe_mean, double* oe_total,
-                   double* o_mean, double* o_sum) {
+// ---- host side ------------------------------------------------------------------------------------------
+// One call scores stripes of any number of resident chromosomes (`slots`): the warp kernel takes
+// every stripe whose window is in-band and small (conservative tests on the bp coordinates, no
+// divisions), the CTA kernel above takes the rest per chromosome.
+static inline size_t up256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+int snn_score_multi_impl(snn_ctx* ctx, const std::vector<ScoreSlot>& slots, int64_t n, const int32_t* slot_of,
+                         const int64_t* pos, const int32_t* stale, double* pvalue, double* stripiness,
+                         double* oe_mean, double* oe_total, double* o_mean, double* o_sum) {
     const int want_p = pvalue != nullptr;
-    const int want_s = expected != nullptr && (stripiness || oe_mean || oe_total || o_mean || o_sum);
-    if (!want_p && !want_s) return SNN_OK;
-    const int bs = (int)(50000.0 / (double)c->binsize);
-    // Launch classes by window size so that the common small stripes do not pay the shared
-    // memory of the largest one: {rows, staged window doubles}.
+    bool any_exp = false;
+    for (const ScoreSlot& sl : slots) any_exp |= sl.expected != nullptr;
+    const int want_s = any_exp && (stripiness || oe_mean || oe_total || o_mean || o_sum);
+    if ((!want_p && !want_s) || n <= 0) return SNN_OK;
+    const int nslot = (int)slots.size();
+    const int64_t r = slots[0].c->binsize;
+    for (const ScoreSlot& sl : slots)
+        if (sl.c->binsize != r || (want_s && !sl.expected))
+            return snn_fail(ctx, SNN_EINVAL, "snn_score: chromosomes of one call share bin size and expected tables");
+    const int bs = (int)(50000.0 / (double)r);
+
+    // ---- classification.  Warp classes by height {64, 128, SW_HMAX}; CTA classes as before.
+    static const int kWarpH[3] = {64, 128, SW_HMAX};
     struct Cls { int hcap, wcap; };
-    const Cls cls[3] = {{128, 4096}, {512, 12288}, {4800, 0}};
-    std::vector<int32_t> order[3];
+    static const Cls cls[3] = {{128, 4096}, {512, 12288}, {4800, 0}};
+    std::vector<int32_t> worder[3];
+    std::vector<std::vector<int32_t>> gorder((size_t)nslot * 3);
+    const int64_t wmaxbp = (int64_t)std::min(62, SW_MAXCOLS - 2 - 2 * bs) * r;
     for (int64_t i = 0; i < n; ++i) {
-        int64_t p1 = pos[i * 4], p2 = pos[i * 4 + 1], p3 = pos[i * 4 + 2], p4 = pos[i * 4 + 3];
+        const int sl = slot_of ? slot_of[i] : 0;
+        if (sl < 0 || sl >= nslot) return snn_fail(ctx, SNN_EINVAL, "snn_score: chromosome slot out of range");
+        const SnnChrom* c = slots[sl].c;
+        const int64_t p1 = pos[i * 4], p2 = pos[i * 4 + 1], p3 = pos[i * 4 + 2], p4 = pos[i * 4 + 3];
+        const bool valid = p1 >= 1 && p3 >= 1 && p2 >= p1 && p4 >= p3 && p2 <= c->chromsize && p4 <= c->chromsize;
+        int wk = -1;
+        if (valid && !ctx->force_generic && bs <= 64 && wmaxbp >= 0 && (p2 - p1) <= wmaxbp) {
+            const int64_t reach = (int64_t)(c->bw - 1 - bs) * r;   // |row - col| < bw for the whole window
+            if ((p2 - p3) < reach && (p4 - p1) < reach) {
+                for (int k = 0; k < 3 && wk < 0; ++k)
+                    if ((p4 - p3) <= (int64_t)(kWarpH[k] - 2) * r) wk = k;
+            }
+        }
+        if (wk >= 0) { worder[wk].push_back((int32_t)i); continue; }
         int64_t h = 1, w = 1;
-        if (p3 >= 1 && p4 >= p3 && p4 <= c->chromsize) h = (p4 + c->binsize - 1) / c->binsize - p3 / c->binsize;
-        if (p1 >= 1 && p2 >= p1) w = (p2 + c->binsize - 1) / c->binsize - p1 / c->binsize + 2 * bs + 2;
+        if (p3 >= 1 && p4 >= p3 && p4 <= c->chromsize) h = (p4 + r - 1) / r - p3 / r;
+        if (p1 >= 1 && p2 >= p1) w = (p2 + r - 1) / r - p1 / r + 2 * bs + 2;
         int k = 2;
         if (h <= cls[0].hcap && h * w <= cls[0].wcap) k = 0;
         else if (h <= cls[1].hcap && h * w <= cls[1].wcap) k = 1;
-        order[k].push_back((int32_t)i);
+        gorder[(size_t)sl * 3 + k].push_back((int32_t)i);
     }
-    size_t pbytes = ((size_t)n * 4 * sizeof(int64_t) + 255) & ~(size_t)255;
-    size_t sbytes = stale ? (((size_t)n * 2 * sizeof(int32_t) + 255) & ~(size_t)255) : 0;
-    size_t ebytes = 8192;
-    size_t orbytes = ((size_t)n * sizeof(int32_t) + 255) & ~(size_t)255;
-    size_t obytes = (size_t)n * 6 * sizeof(double);
+
+    // ---- device scratch
+    const size_t pbytes = up256((size_t)n * 4 * sizeof(int64_t));
+    const size_t sbytes = stale ? up256((size_t)n * 2 * sizeof(int32_t)) : 0;
+    const size_t ebytes = up256((size_t)nslot * 1024 * sizeof(double));   // expected | 1/(expected+1e-8), 512 each
+    const size_t cbytes = up256((size_t)nslot * sizeof(ChromDev));
+    const size_t orbytes = up256((size_t)n * sizeof(int32_t));
+    const size_t slbytes = slot_of ? up256((size_t)n * sizeof(int32_t)) : 0;
+    const size_t obytes = (size_t)n * 6 * sizeof(double);
     void* scratch = nullptr;
-    int rc = snn_scratch(ctx, pbytes + sbytes + ebytes + orbytes + obytes, &scratch);
+    int rc = snn_scratch(ctx, pbytes + sbytes + ebytes + cbytes + orbytes + slbytes + obytes, &scratch);
     if (rc) return rc;
     char* b = (char*)scratch;
-    int64_t* dpos = (int64_t*)b;
-    int32_t* dstale = stale ? (int32_t*)(b + pbytes) : nullptr;
-    double* dex = (double*)(b + pbytes + sbytes);
-    double* drex = dex + 512;
-    int32_t* dorder = (int32_t*)(b + pbytes + sbytes + ebytes);
-    double* dout = (double*)(b + pbytes + sbytes + ebytes + orbytes);
+    int64_t* dpos = (int64_t*)b;                      b += pbytes;
+    int32_t* dstale = stale ? (int32_t*)b : nullptr;  b += sbytes;
+    double* dex = (double*)b;                         b += ebytes;
+    ChromDev* dcd = (ChromDev*)b;                     b += cbytes;
+    int32_t* dorder = (int32_t*)b;                    b += orbytes;
+    int32_t* dslot = slot_of ? (int32_t*)b : nullptr; b += slbytes;
+    double* dout = (double*)b;
     SNN_CUDA(cudaMemcpyAsync(dpos, pos, (size_t)n * 4 * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
     if (stale)
         SNN_CUDA(cudaMemcpyAsync(dstale, stale, (size_t)n * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    if (slot_of)
+        SNN_CUDA(cudaMemcpyAsync(dslot, slot_of, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     std::vector<int32_t> flat;
-    flat.reserve(n);
-    size_t start[3];
-    for (int k = 0; k < 3; ++k) { start[k] = flat.size(); flat.insert(flat.end(), order[k].begin(), order[k].end()); }
+    flat.reserve((size_t)n);
+    size_t wstart[3];
+    for (int k = 0; k < 3; ++k) { wstart[k] = flat.size(); flat.insert(flat.end(), worder[k].begin(), worder[k].end()); }
+    std::vector<size_t> gstart(gorder.size());
+    for (size_t g = 0; g < gorder.size(); ++g) { gstart[g] = flat.size(); flat.insert(flat.end(), gorder[g].begin(), gorder[g].end()); }
     SNN_CUDA(cudaMemcpyAsync(dorder, flat.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<ChromDev> hcd((size_t)nslot);
+    std::vector<double> hex((size_t)nslot * 1024, 0.0);
+    for (int sl = 0; sl < nslot; ++sl) {
+        hcd[sl].m = snn_view(slots[sl].c);
+        hcd[sl].chromsize = slots[sl].c->chromsize;
+        hcd[sl].nbins = slots[sl].c->nbins;
+        hcd[sl].rex = want_s ? dex + (size_t)sl * 1024 + 512 : nullptr;
+        if (want_s) memcpy(hex.data() + (size_t)sl * 1024, slots[sl].expected, SNN_NDIST * sizeof(double));
+    }
+    SNN_CUDA(cudaMemcpyAsync(dcd, hcd.data(), (size_t)nslot * sizeof(ChromDev), cudaMemcpyHostToDevice, ctx->stream));
     int launches = 0;
     SnnScope scope(ctx, ST_SCORE, 0);
     if (want_s) {
-        SNN_CUDA(cudaMemcpyAsync(dex, expected, SNN_NDIST * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-        k_recip_expected<<<2, 256, 0, ctx->stream>>>(dex, drex);
+        SNN_CUDA(cudaMemcpyAsync(dex, hex.data(), hex.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        k_recip_expected<<<dim3(2, nslot), 256, 0, ctx->stream>>>(dex);
         SNN_LAUNCH_CHECK("k_recip_expected");
         ++launches;
     }
-    const size_t per_row = 4 * sizeof(double) + sizeof(int) + 1;
-    {   // one attribute value for every launch (contexts on several host threads share the function)
-        size_t worst = 0;
-        for (int k = 0; k < 3; ++k) {
-            size_t v = (size_t)cls[k].hcap * per_row + (size_t)cls[k].wcap * sizeof(double) + 64;
-            if (v > worst) worst = v;
-        }
-        SNN_CUDA(cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)worst));
-    }
+    // ---- warp kernel: one launch per height class, all chromosomes together
     for (int k = 0; k < 3; ++k) {
-        if (order[k].empty()) continue;
-        ScoreParams P;
-        P.binsize = c->binsize;
-        P.chromsize = c->chromsize;
-        P.nbins = c->nbins;
-        P.bs = bs;
-        P.hmax = cls[k].hcap;
-        P.bg_ncol = ctx->bg_ncol;
-        const size_t smem = (size_t)cls[k].hcap * per_row + (size_t)cls[k].wcap * sizeof(double) + 64;
-        k_score<<<(unsigned)order[k].size(), SCORE_THREADS, smem, ctx->stream>>>(
-            snn_view(c), dpos, dstale, dorder + start[k], drex, ctx->bg_sorted, ctx->bg_valid, P, cls[k].wcap, want_p,
-            want_s, dout);
-        SNN_LAUNCH_CHECK("k_score");
+        if (worder[k].empty()) continue;
+        rc = snn_launch_score_warp(ctx, dcd, dslot, dpos, dstale, dorder + wstart[k], (int)worder[k].size(), r, bs,
+                                   kWarpH[k], want_p, want_s, dout);
+        if (rc) return rc;
         ++launches;
+    }
+    // ---- CTA kernel for the rest
+    const size_t per_row = 4 * sizeof(double) + sizeof(int) + 1;
+    bool attr_set = false;
+    for (int sl = 0; sl < nslot; ++sl) {
+        for (int k = 0; k < 3; ++k) {
+            const std::vector<int32_t>& ord = gorder[(size_t)sl * 3 + k];
+            if (ord.empty()) continue;
+            if (!attr_set) {   // one attribute value for every launch (contexts on several host threads share the function)
+                size_t worst = 0;
+                for (int q = 0; q < 3; ++q) {
+                    size_t v = (size_t)cls[q].hcap * per_row + (size_t)cls[q].wcap * sizeof(double) + 64;
+                    if (v > worst) worst = v;
+                }
+                SNN_CUDA(cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)worst));
+                attr_set = true;
+            }
+            const SnnChrom* c = slots[sl].c;
+            ScoreParams P;
+            P.binsize = c->binsize;
+            P.chromsize = c->chromsize;
+            P.nbins = c->nbins;
+            P.bs = bs;
+            P.hmax = cls[k].hcap;
+            P.bg_ncol = ctx->bg_ncol;
+            const size_t smem = (size_t)cls[k].hcap * per_row + (size_t)cls[k].wcap * sizeof(double) + 64;
+            k_score<<<(unsigned)ord.size(), SCORE_THREADS, smem, ctx->stream>>>(
+                snn_view(c), dpos, dstale, dorder + gstart[(size_t)sl * 3 + k], hcd[sl].rex, ctx->bg_sorted,
+                ctx->bg_valid, P, cls[k].wcap, want_p, want_s, dout);
+            SNN_LAUNCH_CHECK("k_score");
+            ++launches;
+        }
     }
     scope.n = launches;
     std::vector<double> host((size_t)n * 6);
@@ -476,4 +545,14 @@ int snn_score_impl(snn_ctx* ctx, SnnChrom* c, int64_t n, const int64_t* pos, con
         if (o_sum) o_sum[i] = host[i * 6 + 5];
     }
     return SNN_OK;
+}
+
+int snn_score_impl(snn_ctx* ctx, SnnChrom* c, int64_t n, const int64_t* pos, const int32_t* stale,
+                   const double* expected, double* pvalue, double* stripiness, double* oe_mean, double* oe_total,
+                   double* o_mean, double* o_sum) {
+    std::vector<ScoreSlot> slots(1);
+    slots[0].c = c;
+    slots[0].expected = expected;
+    return snn_score_multi_impl(ctx, slots, n, nullptr, pos, stale, pvalue, stripiness, oe_mean, oe_total, o_mean,
+                                o_sum);
 }

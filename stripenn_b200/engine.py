@@ -215,6 +215,31 @@ class Device:
         self.d2h_bytes += n * 48
         return res
 
+    def score_multi(self, chrom_ids, chrom_index, pos, expected=None, want_pvalue=True, stale=None):
+        """snn_score for stripes of several resident chromosomes in one call: chrom_ids = the
+        chromosomes involved, chrom_index[i] = index into chrom_ids of stripe i, expected =
+        (len(chrom_ids), 400) mpmean rows or None."""
+        p = np.ascontiguousarray(pos, dtype=np.int64).reshape(-1, 4)
+        n = int(p.shape[0])
+        res = {k: np.full(n, np.nan) for k in ("pvalue", "stripiness", "oe_mean", "oe_total", "o_mean", "o_sum")}
+        if n == 0:
+            return res
+        ids = np.ascontiguousarray(chrom_ids, dtype=np.int32)
+        ci = np.ascontiguousarray(chrom_index, dtype=np.int32)
+        assert ci.shape[0] == n
+        ex = None if expected is None else np.ascontiguousarray(expected, dtype=np.float64).reshape(len(ids), NDIST)
+        st = None if stale is None else np.ascontiguousarray(stale, dtype=np.int32).reshape(-1, 2)
+        check(self.lib.snn_score_multi(self.h, int(len(ids)), ptr(ids), ptr(ex), n, ptr(ci), ptr(p), ptr(st),
+                                       ptr(res["pvalue"]) if want_pvalue else None,
+                                       ptr(res["stripiness"]) if ex is not None else None,
+                                       ptr(res["oe_mean"]) if ex is not None else None,
+                                       ptr(res["oe_total"]) if ex is not None else None,
+                                       ptr(res["o_mean"]) if ex is not None else None,
+                                       ptr(res["o_sum"]) if ex is not None else None), self.h)
+        self.h2d_bytes += p.nbytes + ci.nbytes + (0 if ex is None else ex.nbytes)
+        self.d2h_bytes += n * 48
+        return res
+
     # ------------------------------------------------------------------ timers
     def enable_timing(self, on=True):
         check(self.lib.snn_enable_stage_timing(self.h, 1 if on else 0), self.h)

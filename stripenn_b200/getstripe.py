@@ -283,7 +283,7 @@ class getStripe:
         nq = len(quantiles)
         weights = gaussian_weights(self.canny)
         self._install_background((bgleft_up, bgright_up, bgleft_down, bgright_down))
-        kept: List[tuple] = []   # (chrom, candidate records, p-values)
+        kept: List[tuple] = []   # (chrom, chromosome id, candidate records, positions)
         for chrom in (self.chromnames if chroms is None else chroms):
             cid = self.unbalLib.ensure(chrom)
             lo, hi = (0, None) if frame_range is None else frame_range
@@ -301,18 +301,19 @@ class getStripe:
                 # cross-window RemoveRedundant('size') (getStripe.py:852): one group per q
                 keep = remove_redundant_mask(cand["q"], frame, pos, hh, ww, None, "size")
                 cand, pos = cand[keep], pos[keep]
-            if len(cand):
-                pv = self.dev.score(cid, pos, None, True, self._stale_rows(pos))["pvalue"]
-            else:
-                pv = np.zeros(0)
-            kept.append((chrom, cand, pv))
+            kept.append((chrom, cid, cand, pos if len(cand) else np.zeros((0, 4), np.int64)))
+        # p-values of every chromosome's candidates in ONE device call (all chromosomes are resident)
+        kept = [k for k in kept if len(k[2])]
+        if kept:
+            ids = np.array([k[1] for k in kept], dtype=np.int32)
+            index = np.concatenate([np.full(len(k[2]), i, dtype=np.int32) for i, k in enumerate(kept)])
+            allpos = np.concatenate([k[3] for k in kept])
+            allp = self.dev.score_multi(ids, index, allpos, None, True, self._stale_rows(allpos))["pvalue"]
         # one table per maxpixel value, chromosomes in order (one DataFrame construction per q)
-        kept = [k for k in kept if len(k[1])]
         out = []
         if kept:
-            allc = np.concatenate([k[1] for k in kept])
-            allp = np.concatenate([k[2] for k in kept])
-            alln = np.concatenate([np.full(len(k[1]), k[0], dtype=object) for k in kept])
+            allc = np.concatenate([k[2] for k in kept])
+            alln = np.concatenate([np.full(len(k[2]), k[0], dtype=object) for k in kept])
         for qi, perc in enumerate(quantiles):
             sel = (allc["q"] == qi) if kept else None
             if kept and sel.any():
@@ -363,6 +364,14 @@ class getStripe:
         groups = {str(uniq[k]): order[bounds[k]:bounds[k + 1]] for k in range(len(uniq))}
         return chrs, pos, groups
 
+    def _slots(self, chrs, groups):
+        """(chromosome ids, per-row index into them) for Device.score_multi; uploads what is missing."""
+        ids = np.array([self.unbalLib.ensure(c) for c in groups], dtype=np.int32)
+        index = np.empty(len(chrs), dtype=np.int32)
+        for k, idx in enumerate(groups.values()):
+            index[idx] = k
+        return ids, index
+
     def _stale_rows(self, pos):
         """Background row inherited by stripes that are neither on nor under the diagonal
         (getStripe.py:583-597: the loop variables persist across stripes).  None when every
@@ -394,12 +403,8 @@ class getStripe:
         self._install_background((bgleft_up, bgright_up, bgleft_down, bgright_down))
         chrs, pos, groups = self._by_chrom(df)
         stale = self._stale_rows(pos)
-        out = np.full(len(pos), np.nan)
-        for c, idx in groups.items():
-            cid = self.unbalLib.ensure(c)
-            st = None if stale is None else stale[idx]
-            out[idx] = self.dev.score(cid, pos[idx], None, True, st)["pvalue"]
-        return out.tolist()
+        ids, index = self._slots(chrs, groups)
+        return self.dev.score_multi(ids, index, pos, None, True, stale)["pvalue"].tolist()
 
     def scoringstripes(self, df, expecVal, mask='0'):
         """getStripe.py:608-788 -> (Stripiness, O/E mean, O/E total) lists."""
@@ -410,12 +415,10 @@ class getStripe:
         if n == 0:
             return g.tolist(), m.tolist(), t.tolist()
         chrs, pos, groups = self._by_chrom(df)
-        for c, idx in groups.items():
-            cid = self.unbalLib.ensure(c)
-            idx = np.asarray(idx)
-            res = self.dev.score(cid, pos[idx], np.asarray(expecVal[c], dtype=np.float64), False)
-            g[idx], m[idx], t[idx] = res["stripiness"], res["oe_mean"], res["oe_total"]
-        return g.tolist(), m.tolist(), t.tolist()
+        ids, index = self._slots(chrs, groups)
+        ex = np.stack([np.asarray(expecVal[c], dtype=np.float64) for c in groups])
+        res = self.dev.score_multi(ids, index, pos, ex, False)
+        return res["stripiness"].tolist(), res["oe_mean"].tolist(), res["oe_total"].tolist()
 
     def getMean(self, df):
         """getStripe.py:501-534 -> (nanmean, nansum) lists of the stripe bodies."""
@@ -424,10 +427,6 @@ class getStripe:
         if n == 0:
             return ms.tolist(), ss.tolist()
         chrs, pos, groups = self._by_chrom(df)
-        dummy = np.zeros(NDIST)
-        for c, idx in groups.items():
-            cid = self.unbalLib.ensure(c)
-            idx = np.asarray(idx)
-            res = self.dev.score(cid, pos[idx], dummy, False)
-            ms[idx], ss[idx] = res["o_mean"], res["o_sum"]
-        return ms.tolist(), ss.tolist()
+        ids, index = self._slots(chrs, groups)
+        res = self.dev.score_multi(ids, index, pos, np.zeros((len(ids), NDIST)), False)
+        return res["o_mean"].tolist(), res["o_sum"].tolist()

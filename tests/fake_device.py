@@ -109,3 +109,16 @@ class FakeDevice:
             om, osum = sc.observed_mean(self.mat, table)
             res["o_mean"], res["o_sum"] = np.array(om, dtype=float), np.array(osum, dtype=float)
         return res
+
+    def score_multi(self, chrom_ids, chrom_index, pos, expected=None, want_pvalue=True, stale=None):
+        pos = np.asarray(pos).reshape(-1, 4)
+        index = np.asarray(chrom_index)
+        res = {k: np.full(len(pos), np.nan) for k in ("pvalue", "stripiness", "oe_mean", "oe_total", "o_mean", "o_sum")}
+        for k, cid in enumerate(chrom_ids):
+            idx = np.nonzero(index == k)[0]
+            if not len(idx):
+                continue
+            part = self.score(int(cid), pos[idx], None if expected is None else np.asarray(expected)[k], want_pvalue)
+            for name, v in part.items():
+                res[name][idx] = v
+        return res

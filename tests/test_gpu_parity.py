@@ -301,6 +301,62 @@ def test_generic_and_specialised_kernels_agree(dev, tiny2_cm, monkeypatch):
         gen.close()
 
 
+@pytest.mark.parametrize("cfg,norm", [("tiny2", "KR"), ("tiny1k", "None"), ("tiny10k", "weight")])
+def test_warp_and_cta_scoring_kernels_agree(dev, cfg, norm, monkeypatch):
+    """snn_score routes in-band windows to the warp-per-stripe kernel (score_warp.cu) and the
+    rest to the CTA-per-stripe kernel (score.cu); SNN_FORCE_GENERIC=1 sends everything to the
+    latter.  Same stripes (random ones, tall ones, ones clamped at both chromosome ends, NaN-
+    weight bins under KR) through both, one multi-chromosome call each: counts-based outputs
+    identical, sums within 1e-12."""
+    from stripenn_b200.engine import Device
+    cm = synth.make_config(cfg)
+    bal = cp.resolve_norm(cm, norm, "compute", False)
+    monkeypatch.setenv("SNN_FORCE_GENERIC", "1")
+    gen = Device(0)
+    monkeypatch.delenv("SNN_FORCE_GENERIC")
+    try:
+        r = cm.binsize
+        names = [c for c in cm.chromnames if c in cm.chroms]
+        tab = synth.make_stripe_table(cm, 400, chroms=names)
+        pos = np.stack([tab["pos1"], tab["pos2"], tab["pos3"], tab["pos4"]], axis=1).astype(np.int64)
+        chrs = np.asarray(tab["chr"]).astype(str)
+        rng = np.random.default_rng(5)
+        extra, extra_c = [], []
+        for c in names:                       # clamps at both ends, tall and wide stripes, off-diagonal ones
+            nb, size = cm.nbins(c), cm.chroms[c].size_bp
+            for a, w, hh in ((0, 3, 30), (1, 5, 70), (2, 8, 150), (nb - 40, 4, 39), (nb - 200, 6, 199),
+                             (nb // 2, 2, 310), (nb // 2, 40, 60), (nb // 3, 70, 20)):
+                a = int(max(a, 0))
+                p1, p2 = a * r + 1, min((a + w) * r, size)
+                extra.append((p1, p2, p1, min((a + hh) * r, size)))          # down
+                extra.append((p1, p2, max((a + w - hh) * r + 1, 1), p2))      # up
+                extra.append((p1, p2, max(p1 - 7 * r, 1), min(p2 + 9 * r, size)))  # neither (stale rows)
+                extra_c += [c] * 3
+        pos = np.concatenate([pos, np.array(extra, dtype=np.int64)])
+        chrs = np.concatenate([chrs, np.array(extra_c)])
+        perm = rng.permutation(len(pos))
+        pos, chrs = pos[perm], chrs[perm]
+        outs = []
+        for d in (dev, gen):
+            lib = gs.DeviceMatrix(cm, bal, d)
+            obj = gs.getStripe(lib, r, 10, 8, 2.0, cm.chromnames, names, cm.chromsizes,
+                               [cm.chroms[c].size_bp for c in names], 1, 3, 123456789, 0)
+            bg = obj.nulldist()
+            ex = obj.mpmean()
+            df = pd.DataFrame({"chr": chrs, "pos1": pos[:, 0], "pos2": pos[:, 1], "pos3": pos[:, 2], "pos4": pos[:, 3]})
+            pv = np.array(obj.pvalue(*bg, df), dtype=float)
+            st, om, ot = (np.array(v, dtype=float) for v in obj.scoringstripes(df, ex))
+            gm, gsum = (np.array(v, dtype=float) for v in obj.getMean(df))
+            outs.append((pv, st, om, ot, gm, gsum))
+        a, b = outs
+        assert np.isfinite(a[0]).sum() > 300 and np.isfinite(a[1]).sum() > 300
+        np.testing.assert_array_equal(a[0], b[0])                             # p-values: ratios of counts
+        for x, y in zip(a[1:], b[1:]):
+            np.testing.assert_allclose(x, y, rtol=1e-12, atol=0, equal_nan=True)
+    finally:
+        gen.close()
+
+
 @pytest.mark.parametrize("cfg,norm", [("tiny1k", "None"), ("tiny10k", "weight")])
 def test_other_resolutions_match_oracle(dev, cfg, norm):
     """1 kb (bs = 50: 110-column scoring windows, background rows that wrap around the fetched
