@@ -231,54 +231,91 @@ def make_object(cm, bal, dev, all_names, all_sizes, chromnames, chromsizes, minL
                         numcores, bfilter, seed, gray_variant)
 
 
+class DeviceQueue:
+    """One worker thread that issues every device call of a pipeline, in submission order.  The
+    calls block inside the C library (GIL released) while the GPU works, so the submitting
+    thread is free to do the host-side steps (sampling plan, RemoveRedundant, table assembly)
+    of earlier results at the same time.  A context is only ever touched by this thread while
+    the queue is open — the C ABI's one-thread-at-a-time rule holds."""
+
+    def __init__(self):
+        from concurrent.futures import ThreadPoolExecutor
+        self._ex = ThreadPoolExecutor(max_workers=1, thread_name_prefix="snn-device")
+
+    def submit(self, fn, *args, **kw):
+        return self._ex.submit(fn, *args, **kw)
+
+    def close(self):
+        self._ex.shutdown(wait=True)
+
+
 def run_pipeline(obj, cm, qs, chromnames, pvalue, mask, slow, comm=None, say=lambda *a, **k: None,
                  return_stages=False):
     """Stages 1-5 of compute (stripenn.py:120-152) for the chromosomes this rank owns, with the
-    two host-side exchanges the background needs.  `obj` is a getStripe-shaped object."""
+    two host-side exchanges the background needs.  `obj` is a getStripe-shaped object.
+
+    Device work is queued in the reference's stage order (maxpixel values, expected values, row
+    flags, candidate search per chromosome, background samples, p-values, stripiness) on one
+    DeviceQueue; the host steps in between (sample plan, pruning, tables) run on this thread
+    while the queue keeps the GPU busy.  Results are identical to calling the stages one after
+    the other (getStripe.extract_all etc.)."""
     comm = comm or LocalComm()
     clock = StageClock()
     all_names = list(obj.all_chromnames)
     owner = lpt_partition(all_names, obj.all_chromsizes, comm.world)
     mine = lambda c: owner.get(c, 0) == comm.rank
     my_sel = [c for c in chromnames if mine(c)]
-    say('1. Maximum pixel value calculation ...')
-    MP = obj.getQuantile_slow(cm, my_sel, qs) if slow else obj.getQuantile_original(cm, my_sel, qs)
-    clock.lap('quantiles')
-    say('2. Expected value calculation ...')
-    saved = obj.chromnames
-    obj.chromnames = my_sel
+    dq = DeviceQueue()
     try:
-        EV = obj.mpmean()
+        say('1. Maximum pixel value calculation ...')
+        quant = obj.getQuantile_slow if slow else obj.getQuantile_original
+        f_mp = {c: dq.submit(quant, cm, [c], qs) for c in my_sel}
+        say('2. Expected value calculation ...')
+
+        f_ev = {c: dq.submit(obj.expected_values, c) for c in my_sel}
+        say('3. Background distribution estimation ...')
+        names2 = obj.background_chromosomes()
+        f_avail = dq.submit(obj.available_counts, [c for c in names2 if mine(c)])
+        say('4. Finding candidate stripes from each chromosome ...')
+        # the searches are queued right behind the flags: they only need the maxpixel values
+        f_cand = [(c, dq.submit(lambda c=c: obj.search_candidates(c, f_mp[c].result()[c]))) for c in my_sel]
+        MP = {c: f_mp[c].result()[c] for c in my_sel}
+        clock.lap('quantiles')
+        EV = {c: f_ev[c].result() for c in my_sel}
+        clock.lap('expected')
+        avail = {}
+        for part in comm.all_gather(f_avail.result()):
+            avail.update(part)
+        names2b, budget = obj.sample_budget(names2, avail)
+        clock.lap('row_flags')
+        # sampling plan on the host while the searches run, its device part queued behind them
+        f_cols = {c: dq.submit(obj.background_columns, c, obj.plan_chromosome(c, int(budget[names2b.index(c)])))
+                  for c in names2b if mine(c)}
+        clock.lap('background plan')
+        kept = []
+        for c, f in f_cand:
+            cand, pos = obj.prune_candidates(f.result())
+            if len(cand):
+                kept.append((c, cand, pos))
+        clock.lap('search+prune')
+        allcols = {}
+        for part in comm.all_gather({c: f.result() for c, f in f_cols.items()}):
+            allcols.update(part)
+        full = np.concatenate([allcols[c] for c in names2b], axis=2) if names2b else np.zeros((4, 400, 0))
+        bg = (full[0], full[1], full[2], full[3])
+        clock.lap('background')
+        allp = dq.submit(obj.candidate_pvalues, kept, bg).result()
+        per_q = obj.candidate_tables(kept, allp, qs)
+        clock.lap('pvalue+tables')
+        empty = pd.DataFrame(columns=gs.RESULT_COLUMNS + ['pvalue'])
+        nonempty = [t for t in per_q if len(t)]
+        local = pd.concat(nonempty) if nonempty else empty
+        local = obj.RemoveRedundant(local, 'pvalue')     # pairs never cross chromosomes
+        clock.lap('dedup')
+        say('5. Stripiness calculation ...')
+        s = dq.submit(obj.scoringstripes, local, EV, mask).result()[0]
     finally:
-        obj.chromnames = saved
-    clock.lap('expected')
-    say('3. Background distribution estimation ...')
-    names2 = obj.background_chromosomes()
-    avail = {}
-    for part in comm.all_gather(obj.available_counts([c for c in names2 if mine(c)])):
-        avail.update(part)
-    names2b, budget = obj.sample_budget(names2, avail)
-    clock.lap('row_flags')
-    cols = {}
-    for c in names2b:
-        if mine(c):
-            cols[c] = obj.background_columns(c, obj.plan_chromosome(c, int(budget[names2b.index(c)])))
-    allcols = {}
-    for part in comm.all_gather(cols):
-        allcols.update(part)
-    full = np.concatenate([allcols[c] for c in names2b], axis=2) if names2b else np.zeros((4, 400, 0))
-    bg = (full[0], full[1], full[2], full[3])
-    clock.lap('background')
-    say('4. Finding candidate stripes from each chromosome ...')
-    per_q = obj.extract_all(MP, qs, *bg, chroms=my_sel)
-    clock.lap('extract+pvalue')
-    empty = pd.DataFrame(columns=gs.RESULT_COLUMNS + ['pvalue'])
-    nonempty = [t for t in per_q if len(t)]
-    local = pd.concat(nonempty) if nonempty else empty
-    local = obj.RemoveRedundant(local, 'pvalue')     # pairs never cross chromosomes
-    clock.lap('dedup')
-    say('5. Stripiness calculation ...')
-    s = obj.scoringstripes(local, EV, mask)[0]
+        dq.close()
     local = local.drop(columns=['total', 'num', 'start', 'end', 'x', 'y', 'h', 'w', 'medpixel'])
     local.insert(local.shape[1], 'Stripiness', s, True)
     clock.lap('stripiness')

@@ -16,6 +16,7 @@ struct GrayParams {
     float r32;      // the constant red channel after blur + clip + float32
     double kv;      // (np.ones((bf,bf)) / (bf*bf))[0,0]
     double bright[SNN_NBRIGHT];
+    double kb[SNN_NBRIGHT];   // (1.0 - 0.0) / (bright - 0.0)  (ImageProcessing.py:15)
     double mp[64];  // maxpixel values
 };
 

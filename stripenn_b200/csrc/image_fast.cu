@@ -49,17 +49,16 @@ __global__ void __launch_bounds__(256) k_gray6(const double* __restrict__ Dc_all
     }
     const float CR = 0.299f, CG = 0.587f, CB = 0.114f;
     const int x = threadIdx.x, y0 = threadIdx.y * 4;
+    const float rterm = P.r32 * CR;                   // the red channel's share (constant image)
     for (int bi = 0; bi < SNN_NBRIGHT; ++bi) {
         const double b = P.bright[bi];
-        const double k = (1.0 - 0.0) / (b - 0.0);
+        const double k = P.kb[bi];                    // (1.0 - 0.0) / (b - 0.0), divided on the host
         __syncthreads();  // G ready / previous pass done with Pk
         for (int t = tid; t < GT * GT; t += 256) {
-            const double g = G[t];
-            double a;
-            if (g != g || g <= 0.0) a = 0.0;      // ImageProcessing.py:17-23 (NaN cells stay 0)
-            else if (g > b) a = 1.0;
-            else a = k * g;
-            Pk[t] = P.kv * a;                     // the tap product of cv.filter2D
+            const double g = G[t];                    // never NaN: the tile is clipped with fmin/fmax above
+            // ImageProcessing.py:17-23: v <= 0 -> 0 ; v > b -> 1 ; else k * v
+            const double a = (g > b) ? 1.0 : k * g;   // g = 0 gives k * 0 = 0
+            Pk[t] = P.kv * a;                         // the tap product of cv.filter2D
         }
         __syncthreads();
         if (tx0 + x < S) {
@@ -68,28 +67,31 @@ __global__ void __launch_bounds__(256) k_gray6(const double* __restrict__ Dc_all
             for (int i = 0; i < 6; ++i)
 #pragma unroll
                 for (int j = 0; j < 3; ++j) p[i][j] = Pk[(y0 + i) * GT + x + j];
-            float* gray = gray_all + ((int64_t)fq * SNN_NBRIGHT + bi) * SNN_SMAX * SNN_SMAX;
+            float* gray = gray_all + ((int64_t)fq * SNN_NBRIGHT + bi) * SNN_SMAX * SNN_SMAX +
+                          (int64_t)(ty0 + y0) * SNN_SMAX + tx0 + x;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                if (ty0 + y0 + i >= S) break;
-                double acc = 0.0;
+                // cv.filter2D: accumulator from 0, taps row-major; 0.0 + p is p for p >= 0
+                double acc = p[i][0];
+                acc = acc + p[i][1];
+                acc = acc + p[i][2];
 #pragma unroll
-                for (int ky = 0; ky < 3; ++ky)
+                for (int ky = 1; ky < 3; ++ky)
 #pragma unroll
                     for (int kx = 0; kx < 3; ++kx) acc = acc + p[i + ky][kx];
-                acc = fmin(fmax(acc, 0.0), 1.0);
+                if (acc > 1.0) acc = 1.0;             // np.clip(blur, 0, 1): the sum is never negative or NaN
                 const float g = (float)acc;
                 float out;
                 if (P.variant == SNN_GRAY_IPP) {
-                    const float t = (P.r32 * CR) + (g * CG);
+                    const float t = rterm + (g * CG);
                     out = __fmaf_rn(g, CB, t);
                 } else if (P.variant == SNN_GRAY_FMA2) {
-                    const float t = __fmaf_rn(g, CG, P.r32 * CR);
+                    const float t = __fmaf_rn(g, CG, rterm);
                     out = __fmaf_rn(g, CB, t);
                 } else {
-                    out = ((P.r32 * CR) + (g * CG)) + (g * CB);
+                    out = (rterm + (g * CG)) + (g * CB);
                 }
-                gray[(ty0 + y0 + i) * SNN_SMAX + tx0 + x] = out;
+                if (ty0 + y0 + i < S) gray[i * SNN_SMAX] = out;
             }
         }
     }
@@ -271,18 +273,26 @@ __global__ void __launch_bounds__(GH_WARPS * 32) k_gauss_hm(const float* __restr
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float* in = in_all + (int64_t)pass * SNN_SMAX * SNN_SMAX + (int64_t)r0 * SNN_SMAX;
     // phase 1: rows -> tin with cp.async (all copies of a thread in flight at once; a source
-    // size of 0 zero-fills the cells outside the image)
+    // size of 0 zero-fills the cells outside the image).  Warp = row, lanes along the columns.
     {
         constexpr int NCOL = TC + 2 * R;
+        constexpr int NIT = (NCOL + 31) / 32;
         const unsigned tin_s = (unsigned)__cvta_generic_to_shared(tin);
-#pragma unroll 4
-        for (int e = threadIdx.x; e < GH_ROWS * NCOL; e += GH_WARPS * 32) {
-            const int rr = e / NCOL, p = e - rr * NCOL;
-            const int c = ct0 - R + p;
-            const bool ok = rr < nr && c >= 0 && c < S;
-            const float* src = ok ? in + rr * SNN_SMAX + c : in;
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(tin_s + (unsigned)(rr * PIN + p) * 4u),
-                         "l"(src), "r"(ok ? 4 : 0));
+#pragma unroll 2
+        for (int rr = warp; rr < GH_ROWS; rr += GH_WARPS) {
+            const bool rowok = rr < nr;
+            const float* grow = in + rr * SNN_SMAX + (ct0 - R);
+            const unsigned sdst = tin_s + (unsigned)(rr * PIN) * 4u;
+#pragma unroll
+            for (int it = 0; it < NIT; ++it) {
+                const int p = lane + 32 * it;
+                if (p < NCOL) {
+                    const int c = ct0 - R + p;
+                    const bool ok = rowok && c >= 0 && c < S;
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sdst + (unsigned)p * 4u),
+                                 "l"(ok ? grow + p : in), "r"(ok ? 4 : 0));
+                }
+            }
         }
         asm volatile("cp.async.commit_group;");
         asm volatile("cp.async.wait_group 0;");
@@ -313,10 +323,29 @@ __global__ void __launch_bounds__(GH_WARPS * 32) k_gauss_hm(const float* __restr
     const float* bleed = bleed_all + (int64_t)f * SNN_SMAX * SNN_SMAX + (int64_t)r0 * SNN_SMAX + ct0;
     float* out = out_all + (int64_t)pass * SNN_SMAX * SNN_SMAX + (int64_t)r0 * SNN_SMAX + ct0;
     const int nc = min(TC, S - ct0);
-#pragma unroll 4
-    for (int e = threadIdx.x; e < GH_ROWS * TC; e += GH_WARPS * 32) {
-        const int rr = e / TC, t = e - rr * TC;
-        if (rr < nr && t < nc) out[rr * SNN_SMAX + t] = tout[rr * POUT + t] / bleed[rr * SNN_SMAX + t];
+    constexpr int NIT3 = (TC + 31) / 32;
+    // four rows at a time: all their bleed-over loads are in flight before the first division
+#pragma unroll 1
+    for (int rb = warp; rb < nr; rb += 4 * GH_WARPS) {
+        float bv[4][NIT3];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int rr = rb + k * GH_WARPS;
+#pragma unroll
+            for (int it = 0; it < NIT3; ++it) {
+                const int t = lane + 32 * it;
+                bv[k][it] = (rr < nr && t < nc) ? bleed[rr * SNN_SMAX + t] : 1.f;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int rr = rb + k * GH_WARPS;
+#pragma unroll
+            for (int it = 0; it < NIT3; ++it) {
+                const int t = lane + 32 * it;
+                if (rr < nr && t < nc) out[rr * SNN_SMAX + t] = tout[rr * POUT + t] / bv[k][it];
+            }
+        }
     }
 }
 
@@ -460,7 +489,8 @@ __global__ void __launch_bounds__(256) k_sobel_nms2(const float* __restrict__ sm
 // its source position — exactly how ndi.sobel pads the derivative image in its second pass.
 #define SN_ROWS 64
 #define SN_WARPS 15
-__global__ void __launch_bounds__(SN_WARPS * 32, 3) k_sobel_nms3(const float* __restrict__ sm_all,
+template <bool DBG>
+__global__ void __launch_bounds__(SN_WARPS * 32, 2) k_sobel_nms3(const float* __restrict__ sm_all,
                                                               const FrameInfo* __restrict__ info,
                                                               int passes_per_frame, uint32_t* __restrict__ low_all,
                                                               uint32_t* __restrict__ high_all,
@@ -491,16 +521,19 @@ __global__ void __launch_bounds__(SN_WARPS * 32, 3) k_sobel_nms3(const float* __
         double dj0 = 0.0, dj1 = 0.0;
         float mA = 0.f, mB = 0.f, isB = 0.f, jsB = 0.f;
         float mAl = 0.f, mAr = 0.f, mBl = 0.f, mBr = 0.f;   // horizontal neighbours, carried down the rows
-        // the row after next is already in flight while a row is processed
+        // two rows are in flight while a row is processed
         float nxt = colp[f_symm(r0 - 2, S) * SNN_SMAX];
+        float nxt2 = colp[max(f_symm(r0 - 1, S), 0) * SNN_SMAX];
+#pragma unroll 3
         for (int rho = r0 - 2; rho <= r1 + 1; ++rho) {
             const float s2 = nxt;
+            nxt = nxt2;
             {
-                int rn = rho + 1;                       // scipy 'reflect' row of the next iteration
+                int rn = rho + 2;                       // scipy 'reflect' row of the iteration after next
                 rn = rn < 0 ? -rn - 1 : rn;
                 rn = rn >= S ? 2 * S - 1 - rn : rn;
-                rn = max(rn, 0);
-                nxt = colp[rn * SNN_SMAX];
+                rn = min(max(rn, 0), S - 1);
+                nxt2 = colp[rn * SNN_SMAX];
             }
             // axis-1 derivative of row rho
             const float sl = __shfl_up_sync(FULL, s2, 1), sr = __shfl_down_sync(FULL, s2, 1);
@@ -519,7 +552,7 @@ __global__ void __launch_bounds__(SN_WARPS * 32, 3) k_sobel_nms3(const float* __
             const float m1l = __shfl_up_sync(FULL, m1, 1), m1r = __shfl_down_sync(FULL, m1, 1);
             const int r = rho - 2;
             bool keep = false, strong = false;
-            if (mag_dbg && lanedbg && rho - 1 >= r0 && rho - 1 < r1)
+            if (DBG && lanedbg && rho - 1 >= r0 && rho - 1 < r1)
                 mag_dbg[(int64_t)pass * SNN_SMAX * SNN_SMAX + (rho - 1) * SNN_SMAX + c] = m1;
             const bool rowok = r >= rlo && r < rhi;     // warp-uniform
             if (rowok && lanemine && mB >= 0.1f) {
@@ -627,8 +660,11 @@ int snn_launch_gauss_fast(snn_ctx* ctx, const ExtractPlan& pl, int npass, int pp
 }
 
 int snn_launch_sobel_nms2(snn_ctx* ctx, const ExtractPlan& pl, int npass, int ppf, float* mag_dbg) {
-    k_sobel_nms3<<<dim3((SNN_SMAX + SN_ROWS - 1) / SN_ROWS, npass), SN_WARPS * 32, 0, ctx->stream>>>(
-        pl.bufC, pl.info, ppf, pl.low, pl.high, mag_dbg);
+    const dim3 grid((SNN_SMAX + SN_ROWS - 1) / SN_ROWS, npass);
+    if (mag_dbg)
+        k_sobel_nms3<true><<<grid, SN_WARPS * 32, 0, ctx->stream>>>(pl.bufC, pl.info, ppf, pl.low, pl.high, mag_dbg);
+    else
+        k_sobel_nms3<false><<<grid, SN_WARPS * 32, 0, ctx->stream>>>(pl.bufC, pl.info, ppf, pl.low, pl.high, mag_dbg);
     SNN_LAUNCH_CHECK("k_sobel_nms3");
     return SNN_OK;
 }

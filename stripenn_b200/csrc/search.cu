@@ -67,6 +67,84 @@ __device__ __forceinline__ int next_clear(const uint32_t* row, int p, int S) {
     return S;
 }
 
+// r = a + b over 13 words with carry (one 416-bit addition)
+__device__ __forceinline__ void add416(const uint32_t (&a)[SNN_WPR], const uint32_t (&b)[SNN_WPR],
+                                       uint32_t (&r)[SNN_WPR]) {
+    uint32_t c;
+    asm("add.cc.u32 %0, %8, %15;\n\t"
+        "addc.cc.u32 %1, %9, %16;\n\t"
+        "addc.cc.u32 %2, %10, %17;\n\t"
+        "addc.cc.u32 %3, %11, %18;\n\t"
+        "addc.cc.u32 %4, %12, %19;\n\t"
+        "addc.cc.u32 %5, %13, %20;\n\t"
+        "addc.cc.u32 %6, %14, %21;\n\t"
+        "addc.u32 %7, 0, 0;"
+        : "=&r"(r[0]), "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(c)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(b[0]), "r"(b[1]),
+          "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]));
+    asm("add.cc.u32 %0, %6, 0xffffffff;\n\t"      // carry flag := c
+        "addc.cc.u32 %0, %7, %13;\n\t"
+        "addc.cc.u32 %1, %8, %14;\n\t"
+        "addc.cc.u32 %2, %9, %15;\n\t"
+        "addc.cc.u32 %3, %10, %16;\n\t"
+        "addc.cc.u32 %4, %11, %17;\n\t"
+        "addc.u32 %5, %12, %18;"
+        : "=&r"(r[7]), "=&r"(r[8]), "=&r"(r[9]), "=&r"(r[10]), "=&r"(r[11]), "=&r"(r[12])
+        : "r"(c), "r"(a[7]), "r"(a[8]), "r"(a[9]), "r"(a[10]), "r"(a[11]), "r"(a[12]), "r"(b[7]), "r"(b[8]),
+          "r"(b[9]), "r"(b[10]), "r"(b[11]), "r"(b[12]));
+}
+
+// Flood the seed bits (a subset of m) through the runs of ones of m, both directions, over a
+// 13-word row.  Adding a seed to a run of ones ripples a carry to the run's end: the bits that
+// differ from m are exactly the part of the run from the seed upwards.  The downward half is
+// the same addition on the bit-reversed row.
+__device__ __forceinline__ void flood_row(const uint32_t (&m)[SNN_WPR], uint32_t (&g)[SNN_WPR]) {
+    uint32_t t[SNN_WPR], mr[SNN_WPR], gr[SNN_WPR];
+    add416(m, g, t);
+#pragma unroll
+    for (int w = 0; w < SNN_WPR; ++w) g[w] = (((t[w] ^ m[w]) & m[w]) | g[w]);
+#pragma unroll
+    for (int w = 0; w < SNN_WPR; ++w) {
+        mr[w] = __brev(m[SNN_WPR - 1 - w]);
+        gr[w] = __brev(g[SNN_WPR - 1 - w]);
+    }
+    add416(mr, gr, t);
+#pragma unroll
+    for (int w = 0; w < SNN_WPR; ++w) gr[w] = (((t[w] ^ mr[w]) & mr[w]) | gr[w]);
+#pragma unroll
+    for (int w = 0; w < SNN_WPR; ++w) g[w] = __brev(gr[SNN_WPR - 1 - w]);
+}
+
+// The run automaton of ImageProcessing.block (ImageProcessing.py:127-138) fed with gaps instead
+// of single rows: `g` zeros in a row.  Zeros fill a 5-slot buffer that ones do not reset; the
+// 6th zero closes the run (keeping the longest) and empties the buffer, and so on every 6 zeros.
+struct BlockScan {
+    int count, buf, last, best, end;
+    __device__ __forceinline__ void zeros(int g) {
+        if (g <= 0) return;
+        if (buf + g <= 5) { buf += g; return; }
+        if (count > best) { best = count; end = last; }
+        count = 0;
+        const int rem = g - (5 - buf) - 1;
+        buf = rem % 6;
+    }
+    // bits of `wd` = rows r0 .. r0+n-1 of the column (bit 0 = row r0)
+    __device__ __forceinline__ void word(uint32_t wd, int r0, int n) {
+        int pos = 0;
+        while (wd) {
+            const int b = __ffs(wd) - 1;
+            zeros(b - pos);
+            const uint32_t rest = wd >> b;                       // starts with a one
+            const int n1 = (rest == 0xffffffffu) ? 32 : __ffs(~rest) - 1;   // length of this run of ones
+            count += n1;
+            last = r0 + b + n1 - 1;
+            pos = b + n1;
+            wd = (pos >= 32) ? 0u : (wd & ~((1u << pos) - 1u));
+        }
+        zeros(n - pos);
+    }
+};
+
 struct SearchParams {
     int nq, minH, maxW;
     int raw_cap;
@@ -82,7 +160,7 @@ __global__ void __launch_bounds__(NTHR) k_search(const uint32_t* __restrict__ lo
     uint32_t* C = E + SNN_SMAX * SNN_WPR;
     uint32_t* V = C + SNN_SMAX * SNN_WPR;
     uint32_t* T = V + SNN_SMAX * SNN_WPR;
-    __shared__ uint32_t colV[SNN_WPR], colT[SNN_WPR];
+    __shared__ uint32_t colV[SNN_WPR], colT[SNN_WPR], colOK[SNN_WPR];   // per-column any-bit / >= 3 ones masks
     __shared__ short cEnd[SNN_SMAX];
     __shared__ unsigned char cUd[SNN_SMAX];
     __shared__ short cnt[SNN_SMAX];
@@ -92,6 +170,7 @@ __global__ void __launch_bounds__(NTHR) k_search(const uint32_t* __restrict__ lo
     __shared__ RawCand pend[SNN_SMAX];
     __shared__ int npend;
     __shared__ int base_sh;
+    __shared__ unsigned char dirty[2][SNN_SMAX + 2];   // row r at index r + 1
 
     const int pass = blockIdx.x;
     const int S = info[pass / (P.nq * SNN_NBRIGHT)].S;
@@ -107,67 +186,48 @@ __global__ void __launch_bounds__(NTHR) k_search(const uint32_t* __restrict__ lo
     if (tid == 0) npend = 0;
     __syncthreads();
 
-    // ---- hysteresis: grow C inside E to the fixed point (8-connectivity).  Per iteration a
-    // thread owns one row: 3x3 dilation from the rows above/below, then a full horizontal
-    // flood inside the row (Kogge-Stone fill with carries across the 13 words).
+    // ---- hysteresis: grow C inside E to the fixed point (8-connectivity).  A thread owns one
+    // row: 3x3 dilation from the rows above/below, then a full horizontal flood inside the row
+    // (two 416-bit additions, see flood_row).  A row is recomputed only if itself or a vertical
+    // neighbour changed in the previous sweep.
     {
         const int r = tid;
+        if (tid < SNN_SMAX + 2) { dirty[0][tid] = (tid >= 1 && tid <= S) ? 1 : 0; dirty[1][tid] = 0; }
+        __syncthreads();
+        int cur = 0;
         for (;;) {
             bool changed = false;
             uint32_t nw[SNN_WPR];
-            if (r < S) {
-                const uint32_t* cu = (r > 0) ? C + (r - 1) * SNN_WPR : nullptr;
+            if (r < S && (dirty[cur][r] | dirty[cur][r + 1] | dirty[cur][r + 2])) {
+                const uint32_t* cu = C + (r - 1) * SNN_WPR;
                 const uint32_t* cc = C + r * SNN_WPR;
-                const uint32_t* cd = (r < S - 1) ? C + (r + 1) * SNN_WPR : nullptr;
-                const uint32_t* er = E + r * SNN_WPR;
-                uint32_t v[SNN_WPR];
+                const uint32_t* cd = C + (r + 1) * SNN_WPR;
+                const bool hasu = r > 0, hasd = r < S - 1;
+                uint32_t v[SNN_WPR], er[SNN_WPR], own[SNN_WPR];
 #pragma unroll
-                for (int w = 0; w < SNN_WPR; ++w) v[w] = cc[w] | (cu ? cu[w] : 0u) | (cd ? cd[w] : 0u);
+                for (int w = 0; w < SNN_WPR; ++w) {
+                    own[w] = cc[w];
+                    er[w] = E[r * SNN_WPR + w];
+                    v[w] = own[w] | (hasu ? cu[w] : 0u) | (hasd ? cd[w] : 0u);
+                }
 #pragma unroll
                 for (int w = 0; w < SNN_WPR; ++w) {
                     uint32_t sp = v[w] | (v[w] << 1) | (v[w] >> 1);
                     if (w > 0) sp |= v[w - 1] >> 31;
                     if (w < SNN_WPR - 1) sp |= v[w + 1] << 31;
-                    nw[w] = (sp & er[w]) | cc[w];
+                    nw[w] = (sp & er[w]) | own[w];
                 }
-                // flood towards higher bits
-                uint32_t carry = 0;
+                flood_row(er, nw);
 #pragma unroll
-                for (int w = 0; w < SNN_WPR; ++w) {
-                    uint32_t m = er[w];
-                    uint32_t g = nw[w] | (carry & m);
-                    uint32_t p = m;
-                    g |= p & (g << 1); p &= p << 1;
-                    g |= p & (g << 2); p &= p << 2;
-                    g |= p & (g << 4); p &= p << 4;
-                    g |= p & (g << 8); p &= p << 8;
-                    g |= p & (g << 16);
-                    nw[w] = g;
-                    carry = g >> 31;
-                }
-                // flood towards lower bits
-                carry = 0;
-#pragma unroll
-                for (int w = SNN_WPR - 1; w >= 0; --w) {
-                    uint32_t m = er[w];
-                    uint32_t g = nw[w] | ((carry << 31) & m);
-                    uint32_t p = m;
-                    g |= p & (g >> 1); p &= p >> 1;
-                    g |= p & (g >> 2); p &= p >> 2;
-                    g |= p & (g >> 4); p &= p >> 4;
-                    g |= p & (g >> 8); p &= p >> 8;
-                    g |= p & (g >> 16);
-                    nw[w] = g;
-                    carry = g & 1u;
-                }
-#pragma unroll
-                for (int w = 0; w < SNN_WPR; ++w) changed |= (nw[w] != cc[w]);
+                for (int w = 0; w < SNN_WPR; ++w) changed |= (nw[w] != own[w]);
             }
             __syncthreads();  // all reads of C done
-            if (r < S && changed) {
+            if (changed) {
 #pragma unroll
                 for (int w = 0; w < SNN_WPR; ++w) C[r * SNN_WPR + w] = nw[w];
             }
+            if (r < S) dirty[cur ^ 1][r + 1] = changed ? 1 : 0;
+            cur ^= 1;
             if (!__syncthreads_or(changed)) break;
         }
     }
@@ -178,31 +238,45 @@ __global__ void __launch_bounds__(NTHR) k_search(const uint32_t* __restrict__ lo
         for (int t = tid; t < S * SNN_WPR; t += NTHR) dbg_edges[(int64_t)pass * SNN_SMAX * SNN_WPR + t] = E[t];
 
     // ---- verticalLine: hit(x, y) = Fx > 0 && 3 Fy^2 < Fx^2 ; vert[x][y-1] = hit[x][y].
-    // vert[r][c] can only be set where column c has an edge pixel in rows r-1..r+1.
+    // vert[r][c] can only be set where column c has an edge pixel in rows r-1..r+1; for those
+    // columns the 3x3 neighbourhood (columns c..c+2) is cut out of 64-bit windows of the rows.
     if (tid < S) {
         const int r = tid;
-        uint32_t any = 0;
+        const bool hasu = r > 0, hasd = r < S - 1;
+        const uint32_t* eu = E + (r - 1) * SNN_WPR;
+        const uint32_t* ec = E + r * SNN_WPR;
+        const uint32_t* ed = E + (r + 1) * SNN_WPR;
+        uint32_t a_lo = hasu ? eu[0] : 0u, b_lo = ec[0], c_lo = hasd ? ed[0] : 0u;
+#pragma unroll
         for (int w = 0; w < SNN_WPR; ++w) {
-            uint32_t d = E[r * SNN_WPR + w];
-            if (r > 0) d |= E[(r - 1) * SNN_WPR + w];
-            if (r < S - 1) d |= E[(r + 1) * SNN_WPR + w];
+            uint32_t a_hi = 0u, b_hi = 0u, c_hi = 0u;
+            if (w + 1 < SNN_WPR) {
+                a_hi = hasu ? eu[w + 1] : 0u;
+                b_hi = ec[w + 1];
+                c_hi = hasd ? ed[w + 1] : 0u;
+            }
+            uint32_t d = a_lo | b_lo | c_lo;
             uint32_t out = 0;
-            while (d) {
-                int bit = __ffs(d) - 1;
-                d &= d - 1;
-                int c = w * 32 + bit;
-                if (c > S - 2) continue;
-                // y = c + 1 ; columns y-1 = c, y, y+1 = c + 2
-                int a0 = getbit(E, S, r - 1, c), a1 = getbit(E, S, r - 1, c + 1), a2 = getbit(E, S, r - 1, c + 2);
-                int b0 = getbit(E, S, r, c), b2 = getbit(E, S, r, c + 2);
-                int c0 = getbit(E, S, r + 1, c), c1 = getbit(E, S, r + 1, c + 1), c2 = getbit(E, S, r + 1, c + 2);
-                int fx = (a0 + 2 * b0 + c0) - (a2 + 2 * b2 + c2);
-                int fy = (c0 + 2 * c1 + c2) - (a0 + 2 * a1 + a2);
-                if (fx > 0 && 3 * fy * fy < fx * fx) out |= 1u << bit;
+            if (d) {
+                const uint64_t A = ((uint64_t)a_hi << 32) | a_lo, B = ((uint64_t)b_hi << 32) | b_lo,
+                               Cc = ((uint64_t)c_hi << 32) | c_lo;
+                while (d) {
+                    const int bit = __ffs(d) - 1;
+                    d &= d - 1;
+                    if (w * 32 + bit > S - 2) break;          // bits ascend: nothing further qualifies
+                    const int ta = (int)(A >> bit) & 7, tb = (int)(B >> bit) & 7, tc = (int)(Cc >> bit) & 7;
+                    // [1 2 1] sums: columns c / c+2 over the three rows, rows r-1 / r+1 over the three columns
+                    const int col0 = (ta & 1) + 2 * (tb & 1) + (tc & 1);
+                    const int col2 = (ta >> 2) + 2 * (tb >> 2) + (tc >> 2);
+                    const int rowu = (ta & 1) + 2 * ((ta >> 1) & 1) + (ta >> 2);
+                    const int rowd = (tc & 1) + 2 * ((tc >> 1) & 1) + (tc >> 2);
+                    const int fx = col0 - col2, fy = rowd - rowu;
+                    if (fx > 0 && 3 * fy * fy < fx * fx) out |= 1u << bit;
+                }
             }
             V[r * SNN_WPR + w] = out;
-            any |= out;
             if (out) atomicOr(&colV[w], out);
+            a_lo = a_hi; b_lo = b_hi; c_lo = c_hi;
         }
     }
     __syncthreads();
@@ -210,47 +284,63 @@ __global__ void __launch_bounds__(NTHR) k_search(const uint32_t* __restrict__ lo
         for (int t = tid; t < S * SNN_WPR; t += NTHR) dbg_vert[(int64_t)pass * SNN_SMAX * SNN_WPR + t] = V[t];
 
     // ---- block(vert, c) for every column + candidate test (ImageProcessing.py:100-195,
-    // getStripe.py:924-940)
-    if (tid < S) {
+    // getStripe.py:924-940).  A warp owns 32 columns: per block of 32 rows every lane loads one
+    // row's word of (vert[:, c-1] | vert[:, c] | vert[:, c+1]), 32 ballots transpose it so that
+    // lane b holds column b's 32 rows, and the run automaton consumes it gap by gap.
+    {
+        const int w = tid >> 5, lane = tid & 31;        // word index of this warp's columns
         const int c = tid;
-        int best = 0, end = 0;
-        // does any of the columns c-1, c, c+1 hold a one at all?
-        bool some = false;
-        for (int cc = max(c - 1, 0); cc <= min(c + 1, S - 1); ++cc) some |= (colV[cc >> 5] >> (cc & 31)) & 1;
-        if (some) {
-            int count = 0, buf = 0, last = 0;
-            for (int i = 0; i < S; ++i) {
-                int one = getbit(V, S, i, c - 1) | getbit(V, S, i, c) | getbit(V, S, i, c + 1);
-                if (one) {
-                    ++count;
-                    last = i;
-                } else if (buf < 5) {
-                    ++buf;
-                } else {
-                    if (count > best) { best = count; end = last; }
-                    count = 0;
-                    buf = 0;
+        if (w * 32 < S) {
+            const uint32_t near = colV[w] | (w > 0 ? colV[w - 1] >> 31 : 0u) |
+                                  (w + 1 < SNN_WPR ? colV[w + 1] << 31 : 0u);
+            BlockScan bsn;
+            bsn.count = bsn.buf = bsn.last = bsn.best = bsn.end = 0;
+            if (near | (near << 1) | (near >> 1)) {      // some column of this warp sees a one
+                for (int r0 = 0; r0 < S; r0 += 32) {
+                    const int rr = r0 + lane;
+                    uint32_t v3 = 0u;
+                    if (rr < S) {
+                        const uint32_t* vr = V + rr * SNN_WPR;
+                        const uint32_t v = vr[w];
+                        v3 = v | (v << 1) | (v >> 1);
+                        if (w > 0) v3 |= vr[w - 1] >> 31;
+                        if (w + 1 < SNN_WPR) v3 |= vr[w + 1] << 31;
+                    }
+                    uint32_t mine = 0u;
+                    if (__any_sync(0xffffffffu, v3 != 0u)) {
+#pragma unroll
+                        for (int b = 0; b < 32; ++b) {
+                            const uint32_t bal = __ballot_sync(0xffffffffu, (v3 >> b) & 1u);
+                            if (lane == b) mine = bal;
+                        }
+                    }
+                    bsn.word(mine, r0, min(32, S - r0));
                 }
+            } else {
+                bsn.zeros(S);
             }
-            if (count > best) { best = count; end = last; }
+            if (bsn.count > bsn.best) { bsn.best = bsn.count; bsn.end = bsn.last; }
+            if (c < S) {
+                int best = bsn.best, end = bsn.end;
+                if (end < c) end = end - best + 1;
+                int ud = 0;
+                if (best > P.minH) {
+                    int lo = min(c, end), hi = max(c, end);
+                    bool has = false;
+                    for (int i = max(lo, 0); i <= hi && i < S; ++i)
+                        if (getbit(V, S, i, c)) { has = true; break; }
+                    if (has) ud = (end > c) ? 2 : 1;
+                }
+                cEnd[c] = (short)end;
+                cUd[c] = (unsigned char)ud;
+            }
         }
-        if (end < c) end = end - best + 1;
-        int ud = 0;
-        if (best > P.minH) {
-            int lo = min(c, end), hi = max(c, end);
-            bool has = false;
-            for (int i = max(lo, 0); i <= hi && i < S; ++i)
-                if (getbit(V, S, i, c)) { has = true; break; }
-            if (has) ud = (end > c) ? 2 : 1;
-        }
-        cEnd[c] = (short)end;
-        cUd[c] = (unsigned char)ud;
     }
     __syncthreads();
 
     for (int ud = 1; ud <= 2; ++ud) {
         for (int t = tid; t < S * SNN_WPR; t += NTHR) T[t] = 0;
-        if (tid < SNN_WPR) colT[tid] = 0;
+        if (tid < SNN_WPR) { colT[tid] = 0; colOK[tid] = 0; }
         if (tid == 0) nX = 0;
         __syncthreads();
         // paint the candidate segments (half-open row ranges)
@@ -290,15 +380,28 @@ __global__ void __launch_bounds__(NTHR) k_search(const uint32_t* __restrict__ lo
             }
         }
         __syncthreads();
-        // ones per column
-        if (tid < S) {
-            const int c = tid;
-            int n = 0;
-            if ((colT[c >> 5] >> (c & 31)) & 1) {
-                const int w = c >> 5, b = c & 31;
-                for (int r = 0; r < S; ++r) n += (T[r * SNN_WPR + w] >> b) & 1;
+        // ones per column: the same ballot transpose, popcount instead of the automaton
+        {
+            const int w = tid >> 5, lane = tid & 31;
+            if (w * 32 < S) {
+                int n = 0;
+                if (colT[w]) {
+                    for (int r0 = 0; r0 < S; r0 += 32) {
+                        const int rr = r0 + lane;
+                        const uint32_t tw = rr < S ? T[rr * SNN_WPR + w] : 0u;
+                        if (__any_sync(0xffffffffu, tw != 0u)) {
+#pragma unroll
+                            for (int b = 0; b < 32; ++b) {
+                                const uint32_t bal = __ballot_sync(0xffffffffu, (tw >> b) & 1u);
+                                if (lane == b) n += __popc(bal);
+                            }
+                        }
+                    }
+                }
+                if (tid < S) cnt[tid] = (short)n;
+                const uint32_t okm = __ballot_sync(0xffffffffu, tid < S && n >= 3);
+                if (lane == 0) colOK[w] = okm;
             }
-            cnt[c] = (short)n;
         }
         __syncthreads();
         // grouping state machine (getStripe.py:996-1030), sequential
@@ -333,28 +436,33 @@ __global__ void __launch_bounds__(NTHR) k_search(const uint32_t* __restrict__ lo
                 X[nx++] = (int)rv;
             };
             (void)tot;
-            for (int c = 0; c < S; ++c) {
-                if (cnt[c] < 3) continue;
-                ++n;
-                if (prev >= 0) {
-                    // one step of the loop `for k in range(n-1)` with cur = prev, nxt = c
-                    const bool adjacent = (c - prev) == 1;
-                    if (adjacent && open_) {
-                        gcol[gn] = c; glen[gn] = cnt[c]; ++gn;
-                    } else if (adjacent) {
-                        gcol[0] = prev; glen[0] = prevlen; gcol[1] = c; glen[1] = cnt[c]; gn = 2;
-                        unit_len = false; open_ = true; have_ln = true;
-                    } else if (!open_) {
-                        gcol[0] = prev; glen[0] = 1; gn = 1; unit_len = true; have_ln = true;
-                        flush();
-                    } else {
-                        flush();
-                        gcol[0] = prev; glen[0] = prevlen; gn = 1; unit_len = false; open_ = false;
-                        have_ln = true;
+            for (int wq = 0; wq < SNN_WPR; ++wq) {      // columns with >= 3 ones, ascending
+                uint32_t okm = colOK[wq];
+                while (okm) {
+                    const int c = wq * 32 + __ffs(okm) - 1;
+                    okm &= okm - 1;
+                    ++n;
+                    if (prev >= 0) {
+                        // one step of the loop `for k in range(n-1)` with cur = prev, nxt = c
+                        const bool adjacent = (c - prev) == 1;
+                        if (adjacent && open_) {
+                            gcol[gn] = c; glen[gn] = cnt[c]; ++gn;
+                        } else if (adjacent) {
+                            gcol[0] = prev; glen[0] = prevlen; gcol[1] = c; glen[1] = cnt[c]; gn = 2;
+                            unit_len = false; open_ = true; have_ln = true;
+                        } else if (!open_) {
+                            gcol[0] = prev; glen[0] = 1; gn = 1; unit_len = true; have_ln = true;
+                            flush();
+                        } else {
+                            flush();
+                            gcol[0] = prev; glen[0] = prevlen; gn = 1; unit_len = false; open_ = false;
+                            have_ln = true;
+                        }
                     }
+                    prev = c;
+                    prevlen = cnt[c];
+            
                 }
-                prev = c;
-                prevlen = cnt[c];
             }
             if (!have_ln) X[nx++] = 0;
             else flush();
@@ -491,6 +599,8 @@ static int make_plan(snn_ctx* ctx, ExtractPlan* pl, int nq, const double* mp, co
         for (int i = 0; i < SNN_NBRIGHT; ++i) {
             volatile double t = (double)i * delta;
             g.bright[i] = first + t;
+            volatile double num = 1.0 - 0.0, den = g.bright[i] - 0.0;
+            g.kb[i] = num / den;
         }
     }
     for (int i = 0; i < nq; ++i) g.mp[i] = mp[i];

@@ -107,11 +107,11 @@ class getStripe:
     # ------------------------------------------------------------------ a3
     def mpmean(self):
         """getStripe.py:178-235 -> {chrom: list[400]} for the selected chromosomes."""
-        out = {}
-        for c in self.chromnames:
-            cid = self.unbalLib.ensure(c)
-            out[c] = self.dev.expected(cid).tolist()
-        return out
+        return {c: self.expected_values(c) for c in self.chromnames}
+
+    def expected_values(self, chrom):
+        """``calc`` of mpmean (getStripe.py:180-209) for one chromosome -> list[400]."""
+        return self.dev.expected(self.unbalLib.ensure(chrom)).tolist()
 
     # ------------------------------------------------------------------ a4
     @staticmethod
@@ -271,49 +271,51 @@ class getStripe:
             'y': cand["y"].astype(np.int64), 'h': h, 'w': w, 'medpixel': np.full(n, np.nan)}, copy=False)
         return df
 
-    def extract_all(self, MP, quantiles: Sequence[float], bgleft_up, bgright_up, bgleft_down,
-                    bgright_down, frame_range=None, chroms=None):
-        """``extract`` for every maxpixel value at once: the device builds each search window
-        once and runs all Q x 6 brightness passes on it.  Returns one DataFrame per quantile,
-        identical to what the reference's per-quantile loop (stripenn.py:134-138) collects.
+    # extract_all is composed of three steps so that a pipelined driver (compute.run_pipeline) can
+    # keep the device busy with the next chromosome while the host prunes the previous one:
+    def search_candidates(self, chrom, mp_values, frame_range=None):
+        """Device part of ``extract`` for one chromosome and all maxpixel values: raw candidate
+        records of every window (StripeSearch, getStripe.py:864-1114), before any RemoveRedundant."""
+        cid = self.unbalLib.ensure(chrom)
+        lo, hi = (0, None) if frame_range is None else frame_range
+        return self.dev.extract(cid, np.asarray(mp_values, dtype=np.float64), self.canny, self.minH, self.maxW,
+                                self.bfilter, self.gray_variant, lo, hi, gaussian_weights(self.canny))
 
-        Per chromosome: one snn_extract call, the per-window and the cross-window
-        RemoveRedundant('size') of every maxpixel value in one host call each (pairs never cross
-        a maxpixel value or a chromosome), one snn_score call for all p-values."""
-        nq = len(quantiles)
-        weights = gaussian_weights(self.canny)
-        self._install_background((bgleft_up, bgright_up, bgleft_down, bgright_down))
-        kept: List[tuple] = []   # (chrom, chromosome id, candidate records, positions)
-        for chrom in (self.chromnames if chroms is None else chroms):
-            cid = self.unbalLib.ensure(chrom)
-            lo, hi = (0, None) if frame_range is None else frame_range
-            cand = self.dev.extract(cid, np.asarray(MP[chrom], dtype=np.float64), self.canny, self.minH,
-                                    self.maxW, self.bfilter, self.gray_variant, lo, hi, weights)
-            if len(cand):
-                pos = np.stack([cand["pos1"], cand["pos2"], cand["pos3"], cand["pos4"]], axis=1)
-                hh, ww = cand["h"].astype(np.float64), cand["w"].astype(np.float64)
-                frame = cand["frame"].astype(np.int64)
-                nfr = int(frame.max()) + 1
-                # per-window RemoveRedundant('size') (getStripe.py:1112): one group per (q, window)
-                grp = (cand["q"].astype(np.int64) * nfr + frame).astype(np.int32)
-                keep = remove_redundant_mask(grp, np.zeros(len(cand), np.int64), pos, hh, ww, None, "size")
-                cand, pos, hh, ww, frame = cand[keep], pos[keep], hh[keep], ww[keep], frame[keep]
-                # cross-window RemoveRedundant('size') (getStripe.py:852): one group per q
-                keep = remove_redundant_mask(cand["q"], frame, pos, hh, ww, None, "size")
-                cand, pos = cand[keep], pos[keep]
-            kept.append((chrom, cid, cand, pos if len(cand) else np.zeros((0, 4), np.int64)))
-        # p-values of every chromosome's candidates in ONE device call (all chromosomes are resident)
-        kept = [k for k in kept if len(k[2])]
-        if kept:
-            ids = np.array([k[1] for k in kept], dtype=np.int32)
-            index = np.concatenate([np.full(len(k[2]), i, dtype=np.int32) for i, k in enumerate(kept)])
-            allpos = np.concatenate([k[3] for k in kept])
-            allp = self.dev.score_multi(ids, index, allpos, None, True, self._stale_rows(allpos))["pvalue"]
-        # one table per maxpixel value, chromosomes in order (one DataFrame construction per q)
+    @staticmethod
+    def prune_candidates(cand):
+        """Host part: the per-window (getStripe.py:1112) and the cross-window (:852)
+        RemoveRedundant('size') of every maxpixel value in one call each (pairs never cross a
+        maxpixel value or a chromosome).  Returns (records, n x 4 positions)."""
+        if not len(cand):
+            return cand, np.zeros((0, 4), np.int64)
+        pos = np.stack([cand["pos1"], cand["pos2"], cand["pos3"], cand["pos4"]], axis=1)
+        hh, ww = cand["h"].astype(np.float64), cand["w"].astype(np.float64)
+        frame = cand["frame"].astype(np.int64)
+        nfr = int(frame.max()) + 1
+        grp = (cand["q"].astype(np.int64) * nfr + frame).astype(np.int32)       # one group per (q, window)
+        keep = remove_redundant_mask(grp, np.zeros(len(cand), np.int64), pos, hh, ww, None, "size")
+        cand, pos, hh, ww, frame = cand[keep], pos[keep], hh[keep], ww[keep], frame[keep]
+        keep = remove_redundant_mask(cand["q"], frame, pos, hh, ww, None, "size")   # one group per q
+        return cand[keep], pos[keep]
+
+    def candidate_pvalues(self, kept, bg):
+        """p-values of every chromosome's candidates in ONE device call (all chromosomes are
+        resident).  kept = [(chrom, records, positions)] with non-empty records."""
+        if not kept:
+            return np.zeros(0)
+        self._install_background(bg)
+        ids = np.array([self.unbalLib.ensure(k[0]) for k in kept], dtype=np.int32)
+        index = np.concatenate([np.full(len(k[1]), i, dtype=np.int32) for i, k in enumerate(kept)])
+        allpos = np.concatenate([k[2] for k in kept])
+        return self.dev.score_multi(ids, index, allpos, None, True, self._stale_rows(allpos))["pvalue"]
+
+    def candidate_tables(self, kept, allp, quantiles):
+        """One table per maxpixel value, chromosomes in order (what the reference's per-quantile
+        loop, stripenn.py:134-138, collects)."""
         out = []
         if kept:
-            allc = np.concatenate([k[2] for k in kept])
-            alln = np.concatenate([np.full(len(k[2]), k[0], dtype=object) for k in kept])
+            allc = np.concatenate([k[1] for k in kept])
+            alln = np.concatenate([np.full(len(k[1]), k[0], dtype=object) for k in kept])
         for qi, perc in enumerate(quantiles):
             sel = (allc["q"] == qi) if kept else None
             if kept and sel.any():
@@ -323,6 +325,19 @@ class getStripe:
                 res = pd.DataFrame(columns=RESULT_COLUMNS + ['pvalue'])
             out.append(res)
         return out
+
+    def extract_all(self, MP, quantiles: Sequence[float], bgleft_up, bgright_up, bgleft_down,
+                    bgright_down, frame_range=None, chroms=None):
+        """``extract`` for every maxpixel value at once: the device builds each search window
+        once and runs all Q x 6 brightness passes on it.  Returns one DataFrame per quantile,
+        identical to what the reference's per-quantile loop (stripenn.py:134-138) collects."""
+        kept = []
+        for chrom in (self.chromnames if chroms is None else chroms):
+            cand, pos = self.prune_candidates(self.search_candidates(chrom, MP[chrom], frame_range))
+            if len(cand):
+                kept.append((chrom, cand, pos))
+        allp = self.candidate_pvalues(kept, (bgleft_up, bgright_up, bgleft_down, bgright_down))
+        return self.candidate_tables(kept, allp, quantiles)
 
     def extract(self, MP, index, perc, bgleft_up, bgright_up, bgleft_down, bgright_down):
         """getStripe.py:790-862 for one maxpixel value."""
