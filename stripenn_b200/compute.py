@@ -250,78 +250,130 @@ class DeviceQueue:
 
 
 def run_pipeline(obj, cm, qs, chromnames, pvalue, mask, slow, comm=None, say=lambda *a, **k: None,
-                 return_stages=False):
+                 return_stages=False, group=5, ahead=2):
     """Stages 1-5 of compute (stripenn.py:120-152) for the chromosomes this rank owns, with the
     two host-side exchanges the background needs.  `obj` is a getStripe-shaped object.
 
-    Device work is queued in the reference's stage order (maxpixel values, expected values, row
-    flags, candidate search per chromosome, background samples, p-values, stripiness) on one
-    DeviceQueue; the host steps in between (sample plan, pruning, tables) run on this thread
-    while the queue keeps the GPU busy.  Results are identical to calling the stages one after
-    the other (getStripe.extract_all etc.)."""
+    Every device call goes through one DeviceQueue in an order that keeps the GPU busy while this
+    thread does the host steps: maxpixel values, expected values and row flags of all
+    chromosomes; the first candidate searches; the background samples (their sampling plan is
+    drawn on the host meanwhile); then, chromosome by chromosome, search -> RemoveRedundant(size)
+    on the host -> p-values (in groups of `group` chromosomes) -> RemoveRedundant(pvalue) on the
+    host -> stripiness.  RemoveRedundant never pairs rows of different chromosomes
+    (getStripe.py:1127), so pruning per chromosome and re-ordering at the end gives exactly the
+    tables of the stage-by-stage flow (getStripe.extract_all + RemoveRedundant + scoringstripes)."""
     comm = comm or LocalComm()
     clock = StageClock()
     all_names = list(obj.all_chromnames)
     owner = lpt_partition(all_names, obj.all_chromsizes, comm.world)
     mine = lambda c: owner.get(c, 0) == comm.rank
     my_sel = [c for c in chromnames if mine(c)]
+    labels = [str(q * 100) + '%' for q in qs]
     dq = DeviceQueue()
     try:
         say('1. Maximum pixel value calculation ...')
         quant = obj.getQuantile_slow if slow else obj.getQuantile_original
         f_mp = {c: dq.submit(quant, cm, [c], qs) for c in my_sel}
         say('2. Expected value calculation ...')
-
         f_ev = {c: dq.submit(obj.expected_values, c) for c in my_sel}
         say('3. Background distribution estimation ...')
         names2 = obj.background_chromosomes()
         f_avail = dq.submit(obj.available_counts, [c for c in names2 if mine(c)])
         say('4. Finding candidate stripes from each chromosome ...')
-        # the searches are queued right behind the flags: they only need the maxpixel values
-        f_cand = [(c, dq.submit(lambda c=c: obj.search_candidates(c, f_mp[c].result()[c]))) for c in my_sel]
-        MP = {c: f_mp[c].result()[c] for c in my_sel}
-        clock.lap('quantiles')
-        EV = {c: f_ev[c].result() for c in my_sel}
-        clock.lap('expected')
+        todo = list(my_sel)
+        f_cand = []
+
+        def submit_search():
+            if todo:
+                c = todo.pop(0)
+                f_cand.append((c, dq.submit(lambda c=c: obj.search_candidates(c, f_mp[c].result()[c]))))
+        for _ in range(ahead):
+            submit_search()
         avail = {}
         for part in comm.all_gather(f_avail.result()):
             avail.update(part)
+        clock.lap('quantiles+expected+flags')
         names2b, budget = obj.sample_budget(names2, avail)
-        clock.lap('row_flags')
-        # sampling plan on the host while the searches run, its device part queued behind them
+        # sampling plan on the host while the first searches run; its device part goes in next
         f_cols = {c: dq.submit(obj.background_columns, c, obj.plan_chromosome(c, int(budget[names2b.index(c)])))
                   for c in names2b if mine(c)}
-        clock.lap('background plan')
-        kept = []
-        for c, f in f_cand:
-            cand, pos = obj.prune_candidates(f.result())
-            if len(cand):
-                kept.append((c, cand, pos))
-        clock.lap('search+prune')
+        submit_search()
         allcols = {}
         for part in comm.all_gather({c: f.result() for c, f in f_cols.items()}):
             allcols.update(part)
         full = np.concatenate([allcols[c] for c in names2b], axis=2) if names2b else np.zeros((4, 400, 0))
         bg = (full[0], full[1], full[2], full[3])
+        f_bg = dq.submit(obj._install_background, bg)
         clock.lap('background')
-        allp = dq.submit(obj.candidate_pvalues, kept, bg).result()
-        per_q = obj.candidate_tables(kept, allp, qs)
-        clock.lap('pvalue+tables')
-        empty = pd.DataFrame(columns=gs.RESULT_COLUMNS + ['pvalue'])
-        nonempty = [t for t in per_q if len(t)]
-        local = pd.concat(nonempty) if nonempty else empty
-        local = obj.RemoveRedundant(local, 'pvalue')     # pairs never cross chromosomes
-        clock.lap('dedup')
+        MP = {c: f_mp[c].result()[c] for c in my_sel}
+        EV = {c: f_ev[c].result() for c in my_sel}
+        # ---- search -> prune -> p-values (grouped) -> prune by p-value -> stripiness
+        kept, pend, f_pv = [], [], []      # kept: (chrom, records, positions)
+
+        def flush_group():
+            if pend:
+                grp = list(pend)
+                del pend[:]
+                f_pv.append((grp, dq.submit(obj.candidate_pvalues, grp, bg)))
+        i = 0
+        while i < len(f_cand):
+            c, f = f_cand[i]
+            i += 1
+            raw = f.result()
+            submit_search()
+            cand, pos = obj.prune_candidates(raw)
+            if len(cand):
+                kept.append((c, cand, pos))
+                pend.append((c, cand, pos))
+            if len(pend) >= group:
+                flush_group()
+        flush_group()
+        f_bg.result()
+        clock.lap('search+prune')
+        final, f_st, all_pv = [], [], []
+        for grp, f in f_pv:
+            pv = f.result()
+            off = 0
+            rows = []
+            for c, cand, pos in grp:
+                p = pv[off:off + len(cand)]
+                off += len(cand)
+                all_pv.append(p)
+                keep = gs.remove_redundant_mask(np.zeros(len(cand), np.int32), cand["frame"].astype(np.int64), pos,
+                                                cand["h"].astype(np.float64), cand["w"].astype(np.float64),
+                                                np.ascontiguousarray(p, dtype=np.float64), "pvalue")
+                rows.append((c, cand[keep], pos[keep], p[keep]))
+            f_st.append((rows, dq.submit(obj.stripiness_of, [(c, pos) for c, _, pos, _ in rows], EV, mask)))
+        clock.lap('pvalue+dedup')
         say('5. Stripiness calculation ...')
-        s = dq.submit(obj.scoringstripes, local, EV, mask).result()[0]
+        for rows, f in f_st:
+            st = f.result()
+            off = 0
+            for c, cand, pos, p in rows:
+                final.append((c, cand, p, st[off:off + len(cand)]))
+                off += len(cand)
+        clock.lap('stripiness')
     finally:
         dq.close()
-    local = local.drop(columns=['total', 'num', 'start', 'end', 'x', 'y', 'h', 'w', 'medpixel'])
-    local.insert(local.shape[1], 'Stripiness', s, True)
-    clock.lap('stripiness')
-    if comm.world > 1:
+    final = [r for r in final if len(r[1])]
+    if final:
+        allc = np.concatenate([r[1] for r in final])
+        alln = np.concatenate([np.full(len(r[1]), r[0], dtype=object) for r in final])
+        allp = np.concatenate([r[2] for r in final])
+        alls = np.concatenate([r[3] for r in final])
         # reference row order: maxpixel-major, then chromosomes in -k order, then emission order
-        labels = [str(q * 100) + '%' for q in qs]
+        order = np.argsort(allc["q"], kind="stable")
+        allc, alln, allp, alls = allc[order], alln[order], allp[order], alls[order]
+        local = obj._candidate_frame(allc, alln, 0.0)
+        local['maxpixel'] = np.array(labels, dtype=object)[allc["q"]]
+        local['pvalue'] = allp
+        local = local.drop(columns=['total', 'num', 'start', 'end', 'x', 'y', 'h', 'w', 'medpixel'])
+        local.insert(local.shape[1], 'Stripiness', alls, True)
+    else:
+        local = pd.DataFrame(columns=[k for k in gs.RESULT_COLUMNS if k not in
+                                      ('total', 'num', 'start', 'end', 'x', 'y', 'h', 'w', 'medpixel')] +
+                             ['pvalue', 'Stripiness'])
+    if comm.world > 1:
         parts = comm.all_gather(local)
         merged = pd.concat([p for p in parts if len(p)]) if any(len(p) for p in parts) else local
         if len(merged):
@@ -338,6 +390,7 @@ def run_pipeline(obj, cm, qs, chromnames, pvalue, mask, slow, comm=None, say=lam
     clock.lap('tables')
     obj.last_host_ms = clock.ms
     if return_stages:
+        per_q = obj.candidate_tables(kept, np.concatenate(all_pv) if all_pv else np.zeros(0), qs)
         return result_table, res_filter, dict(MP=MP, EV=EV, bg=bg, per_q=per_q)
     return result_table, res_filter
 

@@ -24,60 +24,95 @@ __host__ __device__ inline void frame_geometry(int idx, int64_t nbins, int* star
     *end = (int)e;
 }
 
-__global__ void __launch_bounds__(512) k_frame_prepare(const double* __restrict__ band, int64_t nbins, int bw,
-                                                       int frame0, FrameInfo* __restrict__ info,
-                                                       int32_t* __restrict__ nz_all, double* __restrict__ Dc_all) {
+// The window fetch runs as three small kernels so that a batch of ~51 windows fills the GPU
+// (one CTA per window left 2/3 of the SMs idle for 150 us per batch, profiles/r01b):
+//   k_frame_flags    (window, 50-row slab): which columns hold a non-zero, non-NaN pixel
+//   k_frame_compact  (window): ordered list of those columns, S, window geometry
+//   k_frame_gather   (window, 8-row slab): Dc[a][b] = nan0(M[nz[a]][nz[b]])
+#define FF_SLAB 50
+__global__ void __launch_bounds__(256) k_frame_flags(const double* __restrict__ band, int64_t nbins, int bw,
+                                                     int frame0, int* __restrict__ flag_all) {
     __shared__ int flag[SNN_SMAX];
-    __shared__ int nz[SNN_SMAX];
-    __shared__ int S_sh;
     const int f = blockIdx.x;
-    const int idx = frame0 + f;
     int start, end;
-    frame_geometry(idx, nbins, &start, &end);
+    frame_geometry(frame0 + f, nbins, &start, &end);
     const int n = end - start + 1;
+    const int i0 = blockIdx.y * FF_SLAB;
+    if (i0 >= n) return;
+    const int i1 = min(i0 + FF_SLAB, n);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
     for (int t = threadIdx.x; t < SNN_SMAX; t += blockDim.x) flag[t] = 0;
     __syncthreads();
     // colsum != 0  <=>  the column holds a non-zero, non-NaN pixel (values are non-negative)
-    for (int i = warp; i < n; i += nwarp) {
+    for (int i = i0 + warp; i < i1; i += nwarp) {
         const double* row = band + (int64_t)(start + i) * bw;
         bool any = false;
         for (int d = lane; d < n - i; d += 32) {
-            double v = row[d];
+            const double v = row[d];
             if (v == v && v != 0.0) {
                 any = true;
                 flag[i + d] = 1;
             }
         }
-        if (any) flag[i] = 1;
+        if (__any_sync(0xffffffffu, any) && lane == 0) flag[i] = 1;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        int s = 0;
-        for (int t = 0; t < n; ++t)
-            if (flag[t]) nz[s++] = t;
-        S_sh = s;
+    int* out = flag_all + (int64_t)f * SNN_SMAX;
+    for (int t = threadIdx.x; t < n; t += blockDim.x)
+        if (flag[t]) out[t] = 1;
+}
+
+__global__ void __launch_bounds__(32) k_frame_compact(const int* __restrict__ flag_all, int64_t nbins, int frame0,
+                                                      FrameInfo* __restrict__ info, int32_t* __restrict__ nz_all) {
+    const int f = blockIdx.x, lane = threadIdx.x;
+    int start, end;
+    frame_geometry(frame0 + f, nbins, &start, &end);
+    const int n = end - start + 1;
+    const int* flag = flag_all + (int64_t)f * SNN_SMAX;
+    int32_t* nz = nz_all + (int64_t)f * SNN_SMAX;
+    int S = 0;
+    for (int t0 = 0; t0 < n; t0 += 32) {
+        const int t = t0 + lane;
+        const bool on = t < n && flag[t] != 0;
+        const unsigned b = __ballot_sync(0xffffffffu, on);
+        if (on) nz[S + __popc(b & ((1u << lane) - 1u))] = t;
+        S += __popc(b);
     }
-    __syncthreads();
-    int S = S_sh;
+    const int Sraw = S;
     if (S <= 10) S = 0;  // getStripe.py:818 `if framesize > 10`
-    if (threadIdx.x == 0) {
+    __syncwarp();
+    for (int t = S + lane; t < SNN_SMAX; t += 32) nz[t] = -1;
+    (void)Sraw;
+    if (lane == 0) {
         info[f].S = S;
         info[f].start = start;
         info[f].end = end;
-        info[f].idx = idx;
+        info[f].idx = frame0 + f;
     }
-    for (int t = threadIdx.x; t < SNN_SMAX; t += blockDim.x) nz_all[(int64_t)f * SNN_SMAX + t] = t < S ? nz[t] : -1;
-    if (S == 0) return;
-    double* Dc = Dc_all + (int64_t)f * SNN_SMAX * SNN_SMAX;
-    for (int a = warp; a < S; a += nwarp) {
-        const int ga = nz[a];
-        const double* row = band + (int64_t)(start + ga) * bw;
-        for (int b = a + lane; b < S; b += 32) {
-            double v = snn_nan0(row[nz[b] - ga]);
-            Dc[a * SNN_SMAX + b] = v;
-            Dc[b * SNN_SMAX + a] = v;
-        }
+}
+
+#define FG_ROWS 8
+__global__ void __launch_bounds__(FG_ROWS * 32) k_frame_gather(const double* __restrict__ band, int bw,
+                                                               const FrameInfo* __restrict__ info,
+                                                               const int32_t* __restrict__ nz_all,
+                                                               double* __restrict__ Dc_all) {
+    __shared__ int nz[SNN_SMAX];
+    const int f = blockIdx.x;
+    const int S = info[f].S;
+    const int a = blockIdx.y * FG_ROWS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (blockIdx.y * FG_ROWS >= S) return;
+    for (int t = threadIdx.x; t < S; t += blockDim.x) nz[t] = nz_all[(int64_t)f * SNN_SMAX + t];
+    __syncthreads();
+    if (a >= S) return;
+    const int start = info[f].start;
+    const int ga = nz[a];
+    const double* rowa = band + (int64_t)(start + ga) * (bw - 1) + start;   // M[ga][g] for g >= ga
+    double* out = Dc_all + (int64_t)f * SNN_SMAX * SNN_SMAX + (int64_t)a * SNN_SMAX;
+    for (int b = lane; b < S; b += 32) {
+        const int gb = nz[b];
+        // symmetric matrix element from the band: band[min * (bw - 1) + max] (see score_warp.cu)
+        const double v = gb >= ga ? rowa[gb] : band[(int64_t)(start + gb) * (bw - 1) + start + ga];
+        out[b] = snn_nan0(v);
     }
 }
 
@@ -368,9 +403,16 @@ int snn_image_chain(snn_ctx* ctx, SnnChrom* c, const ExtractPlan& pl, int frame0
     const int npass = nf * pl.nq * SNN_NBRIGHT;
     const int ppf = pl.nq * SNN_NBRIGHT;
     {
-        SnnScope scope(ctx, ST_FRAME, 2);
-        k_frame_prepare<<<nf, 512, 0, ctx->stream>>>(c->band, c->nbins, c->bw, frame0, pl.info, pl.nz, pl.Dc);
-        SNN_LAUNCH_CHECK("k_frame_prepare");
+        SnnScope scope(ctx, ST_FRAME, 4);
+        SNN_CUDA(cudaMemsetAsync(pl.flags, 0, (size_t)nf * SNN_SMAX * sizeof(int), ctx->stream));
+        k_frame_flags<<<dim3(nf, (SNN_SMAX + FF_SLAB - 1) / FF_SLAB), 256, 0, ctx->stream>>>(c->band, c->nbins, c->bw,
+                                                                                           frame0, pl.flags);
+        SNN_LAUNCH_CHECK("k_frame_flags");
+        k_frame_compact<<<nf, 32, 0, ctx->stream>>>(pl.flags, c->nbins, frame0, pl.info, pl.nz);
+        SNN_LAUNCH_CHECK("k_frame_compact");
+        k_frame_gather<<<dim3(nf, (SNN_SMAX + FG_ROWS - 1) / FG_ROWS), FG_ROWS * 32, 0, ctx->stream>>>(
+            c->band, c->bw, pl.info, pl.nz, pl.Dc);
+        SNN_LAUNCH_CHECK("k_frame_gather");
         k_bleed<<<dim3(13, 13, nf), dim3(32, 8), 0, ctx->stream>>>(pl.info, pl.gauss, pl.bleed);
         SNN_LAUNCH_CHECK("k_bleed");
     }

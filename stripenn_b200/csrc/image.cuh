@@ -40,6 +40,7 @@ struct ExtractPlan {
     int fb;
     FrameInfo* info;
     int32_t* nz;      // fb x 400
+    int* flags;       // fb x 400 non-empty column flags
     double* Dc;       // fb x 400 x 400
     float* bleed;     // fb x 400 x 400
     float* bufA;      // npass x 400 x 400 (gray)
@@ -49,7 +50,8 @@ struct ExtractPlan {
     uint32_t* high;   // npass x 400 x 13
     int* counter;     // [0] = number of raw candidates, [1] = overflow flag
     RawCand* raw;
-    int raw_cap;
+    int raw_cap;      // capacity of raw / cand (candidates of one snn_extract call)
+    int batch_cap;    // upper bound of the candidates one batch can add
     snn_candidate* cand;  // finished candidates (device)
 };
 

@@ -520,11 +520,16 @@ __global__ void __launch_bounds__(NTHR) k_search(const uint32_t* __restrict__ lo
 }
 
 // ---- finish: bp coordinates and the window sum of each candidate (getStripe.py:1087-1095) --------
-__global__ void k_finish(const RawCand* __restrict__ raw, int n, const FrameInfo* __restrict__ info,
-                         const int32_t* __restrict__ nz_all, const double* __restrict__ Dc_all, int nq,
-                         int64_t binsize, int64_t chromsize, snn_candidate* __restrict__ out) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= n) return;
+// The raw candidates of the current batch are entries [counter[2], counter[0]) of `raw` (k_search
+// appends, k_advance moves counter[2] up after this kernel): no host round trip between batches.
+__global__ void k_finish(const RawCand* __restrict__ raw, const int* __restrict__ counter, int cap,
+                         const FrameInfo* __restrict__ info, const int32_t* __restrict__ nz_all,
+                         const double* __restrict__ Dc_all, int nq, int64_t binsize, int64_t chromsize,
+                         snn_candidate* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int hi = min(counter[0], cap);
+    const int warp = counter[2] + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (warp >= hi) return;
     const RawCand rc = raw[warp];
     const int f = rc.pass / (nq * SNN_NBRIGHT);
     const FrameInfo fi = info[f];
@@ -568,12 +573,14 @@ __global__ void k_finish(const RawCand* __restrict__ raw, int n, const FrameInfo
     }
 }
 
+__global__ void k_advance(int* counter) { counter[2] = counter[0]; }
+
 // ---- host side ------------------------------------------------------------------------------------------
 static size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 
 static int make_plan(snn_ctx* ctx, ExtractPlan* pl, int nq, const double* mp, const double* gw, int radius,
-                     int minH, int maxW, int bfilter, int variant, int fb, bool dbg, uint32_t** dbgE,
-                     uint32_t** dbgV, float** dbgM) {
+                     int minH, int maxW, int bfilter, int variant, int fb, int total_frames, bool dbg,
+                     uint32_t** dbgE, uint32_t** dbgV, float** dbgM) {
     pl->nq = nq;
     pl->minH = minH;
     pl->maxW = maxW;
@@ -609,11 +616,13 @@ static int make_plan(snn_ctx* ctx, ExtractPlan* pl, int nq, const double* mp, co
 
     const size_t npass = (size_t)fb * nq * SNN_NBRIGHT;
     const size_t img = (size_t)SNN_SMAX * SNN_SMAX;
-    pl->raw_cap = (int)std::min<size_t>(npass * 24 + 4096, (size_t)16 << 20);
+    pl->batch_cap = (int)std::min<size_t>(npass * 24 + 4096, (size_t)16 << 20);   // candidates of one batch
+    pl->raw_cap = (int)std::min<size_t>((size_t)total_frames * nq * SNN_NBRIGHT * 24 + 4096, (size_t)16 << 20);
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
     size_t o_info = take(fb * sizeof(FrameInfo));
     size_t o_nz = take((size_t)fb * SNN_SMAX * sizeof(int32_t));
+    size_t o_flags = take((size_t)fb * SNN_SMAX * sizeof(int));
     size_t o_Dc = take((size_t)fb * img * sizeof(double));
     size_t o_bleed = take((size_t)fb * img * sizeof(float));
     size_t o_A = take(npass * img * sizeof(float));
@@ -636,6 +645,7 @@ static int make_plan(snn_ctx* ctx, ExtractPlan* pl, int nq, const double* mp, co
     char* b = (char*)base;
     pl->info = (FrameInfo*)(b + o_info);
     pl->nz = (int32_t*)(b + o_nz);
+    pl->flags = (int*)(b + o_flags);
     pl->Dc = (double*)(b + o_Dc);
     pl->bleed = (float*)(b + o_bleed);
     pl->bufA = (float*)(b + o_A);
@@ -656,10 +666,12 @@ static int make_plan(snn_ctx* ctx, ExtractPlan* pl, int nq, const double* mp, co
 
 static const size_t kSearchSmem = 4 * (size_t)SNN_SMAX * SNN_WPR * sizeof(uint32_t);
 
+// Enqueue one batch of windows: image chain, search (appends raw candidates), finish (turns the
+// batch's raw candidates into records while its compacted windows are still in the scratch
+// buffers), advance.  Nothing here waits for the device.
 static int run_batch(snn_ctx* ctx, SnnChrom* c, const ExtractPlan& pl, int frame0, int nf, uint32_t* dbgE,
-                     uint32_t* dbgV, float* dbgM, int* n_found) {
+                     uint32_t* dbgV, float* dbgM) {
     const int npass = nf * pl.nq * SNN_NBRIGHT;
-    SNN_CUDA(cudaMemsetAsync(pl.counter, 0, 64, ctx->stream));
     int rc = snn_image_chain(ctx, c, pl, frame0, nf, dbgM);
     if (rc) return rc;
     {
@@ -673,19 +685,26 @@ static int run_batch(snn_ctx* ctx, SnnChrom* c, const ExtractPlan& pl, int frame
                                                             dbgV);
         SNN_LAUNCH_CHECK("k_search");
     }
+    {
+        SnnScope scope(ctx, ST_FINISH, 2);
+        const int blocks = (pl.batch_cap * 32 + 255) / 256;
+        k_finish<<<blocks, 256, 0, ctx->stream>>>(pl.raw, pl.counter, pl.raw_cap, pl.info, pl.nz, pl.Dc, pl.nq,
+                                                  c->binsize, c->chromsize, pl.cand);
+        SNN_LAUNCH_CHECK("k_finish");
+        k_advance<<<1, 1, 0, ctx->stream>>>(pl.counter);
+        SNN_LAUNCH_CHECK("k_advance");
+    }
+    return SNN_OK;
+}
+
+// After the last batch: how many candidates were found (one synchronisation per chromosome).
+static int fetch_count(snn_ctx* ctx, const ExtractPlan& pl, int* n_found) {
     int cnt[2] = {0, 0};
     SNN_CUDA(cudaMemcpyAsync(cnt, pl.counter, sizeof cnt, cudaMemcpyDeviceToHost, ctx->stream));
     SNN_CUDA(cudaStreamSynchronize(ctx->stream));
     if (cnt[1] || cnt[0] > pl.raw_cap)
-        return snn_fail(ctx, SNN_ENOMEM, "snn_extract: more than %d raw candidates in one batch", pl.raw_cap);
+        return snn_fail(ctx, SNN_ENOMEM, "snn_extract: more than %d raw candidates in one call", pl.raw_cap);
     *n_found = cnt[0];
-    if (cnt[0] > 0) {
-        SnnScope scope(ctx, ST_FINISH, 1);
-        int blocks = (cnt[0] * 32 + 255) / 256;
-        k_finish<<<blocks, 256, 0, ctx->stream>>>(pl.raw, cnt[0], pl.info, pl.nz, pl.Dc, pl.nq, c->binsize,
-                                                  c->chromsize, pl.cand);
-        SNN_LAUNCH_CHECK("k_finish");
-    }
     return SNN_OK;
 }
 
@@ -707,22 +726,23 @@ int snn_extract_impl(snn_ctx* ctx, SnnChrom* c, int nq, const double* mp, const 
     if (fb < 1) fb = 1;
     if (fb > total) fb = total;
     ExtractPlan pl;
-    rc = make_plan(ctx, &pl, nq, mp, gw, radius, minH, maxW, bfilter, gray_variant, fb, false, nullptr, nullptr,
-                   nullptr);
+    rc = make_plan(ctx, &pl, nq, mp, gw, radius, minH, maxW, bfilter, gray_variant, fb, total, false, nullptr,
+                   nullptr, nullptr);
     if (rc) return rc;
-    std::vector<snn_candidate> all;
+    SNN_CUDA(cudaMemsetAsync(pl.counter, 0, 64, ctx->stream));
     for (int f0 = frame_lo; f0 < frame_hi; f0 += fb) {
         int nf = std::min(fb, frame_hi - f0);
-        int found = 0;
-        rc = run_batch(ctx, c, pl, f0, nf, nullptr, nullptr, nullptr, &found);
+        rc = run_batch(ctx, c, pl, f0, nf, nullptr, nullptr, nullptr);
         if (rc) return rc;
-        if (found > 0) {
-            size_t old = all.size();
-            all.resize(old + found);
-            SNN_CUDA(cudaMemcpyAsync(all.data() + old, pl.cand, (size_t)found * sizeof(snn_candidate),
-                                     cudaMemcpyDeviceToHost, ctx->stream));
-            SNN_CUDA(cudaStreamSynchronize(ctx->stream));
-        }
+    }
+    int found = 0;
+    rc = fetch_count(ctx, pl, &found);
+    if (rc) return rc;
+    std::vector<snn_candidate> all((size_t)found);
+    if (found > 0) {
+        SNN_CUDA(cudaMemcpyAsync(all.data(), pl.cand, (size_t)found * sizeof(snn_candidate), cudaMemcpyDeviceToHost,
+                                 ctx->stream));
+        SNN_CUDA(cudaStreamSynchronize(ctx->stream));
     }
     // the reference's emission order: maxpixel, window, brightness pass, up/down, pair index
     std::sort(all.begin(), all.end(), [](const snn_candidate& a, const snn_candidate& b) {
@@ -753,10 +773,10 @@ int snn_debug_stages_impl(snn_ctx* ctx, SnnChrom* c, double mp, const double* gw
     ExtractPlan pl;
     uint32_t *dE = nullptr, *dV = nullptr;
     float* dM = nullptr;
-    rc = make_plan(ctx, &pl, 1, &mp, gw, radius, 10, 8, bfilter, gray_variant, 1, true, &dE, &dV, &dM);
+    rc = make_plan(ctx, &pl, 1, &mp, gw, radius, 10, 8, bfilter, gray_variant, 1, 1, true, &dE, &dV, &dM);
     if (rc) return rc;
-    int found = 0;
-    rc = run_batch(ctx, c, pl, frame, 1, dE, dV, dM, &found);
+    SNN_CUDA(cudaMemsetAsync(pl.counter, 0, 64, ctx->stream));
+    rc = run_batch(ctx, c, pl, frame, 1, dE, dV, dM);
     if (rc) return rc;
     FrameInfo fi;
     SNN_CUDA(cudaMemcpyAsync(&fi, pl.info, sizeof fi, cudaMemcpyDeviceToHost, ctx->stream));

@@ -17,7 +17,7 @@ import numpy as np
 import pandas as pd
 
 from .contactmap import ContactMap
-from .engine import Device, gaussian_weights, remove_redundant_mask
+from .engine import Device, gaussian_weights, remove_redundant_mask  # noqa: F401 (re-exported)
 
 NDIST = 400
 RESULT_COLUMNS = ['chr', 'pos1', 'pos2', 'chr2', 'pos3', 'pos4', 'length', 'width', 'total', 'Mean',
@@ -434,6 +434,18 @@ class getStripe:
         ex = np.stack([np.asarray(expecVal[c], dtype=np.float64) for c in groups])
         res = self.dev.score_multi(ids, index, pos, ex, False)
         return res["stripiness"].tolist(), res["oe_mean"].tolist(), res["oe_total"].tolist()
+
+    def stripiness_of(self, parts, expecVal, mask='0'):
+        """scoringstripes for [(chrom, n x 4 positions)] in one device call -> Stripiness array."""
+        if mask != '0':
+            raise NotImplementedError("--mask (getStripe.py:612-639) is not built yet (SURVEY.md §8f row 3)")
+        parts = [(c, pos) for c, pos in parts if len(pos)]
+        if not parts:
+            return np.zeros(0)
+        ids = np.array([self.unbalLib.ensure(c) for c, _ in parts], dtype=np.int32)
+        index = np.concatenate([np.full(len(pos), k, dtype=np.int32) for k, (_, pos) in enumerate(parts)])
+        ex = np.stack([np.asarray(expecVal[c], dtype=np.float64) for c, _ in parts])
+        return self.dev.score_multi(ids, index, np.concatenate([pos for _, pos in parts]), ex, False)["stripiness"]
 
     def getMean(self, df):
         """getStripe.py:501-534 -> (nanmean, nansum) lists of the stripe bodies."""
