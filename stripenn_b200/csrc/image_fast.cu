@@ -608,6 +608,132 @@ __global__ void __launch_bounds__(SN_WARPS * 32, 2) k_sobel_nms3(const float* __
     }
 }
 
+// ---- Sobel + magnitude + NMS, two columns per lane ---------------------------------------------------
+// Same walk as k_sobel_nms3, but a lane owns two ADJACENT columns (a warp covers 64 columns, 60
+// useful + 2 halo each side): half of every horizontal neighbour is already in the lane's own
+// registers, so a row costs 6 shuffles for 60 pixels instead of 6 for 28, the per-row index
+// arithmetic is shared by twice as many pixels, and the two columns give the scheduler two
+// independent dependency chains.  Bits go to the shared-memory masks with atomicOr from the
+// (few) lanes that keep a pixel.
+#define SN4_COLS 60
+#define SN4_WARPS 7
+
+// skimage _nonmaximum_suppression_bilinear for one pixel (see k_sobel_nms3 for the branch merge)
+__device__ __forceinline__ void nms_pixel(float is, float js, float m, float mAl, float mA, float mAr, float mBl,
+                                          float mBr, float m1l, float m1, float m1r, bool* keep, bool* strong) {
+    const bool up = is >= 0.f, down = is <= 0.f, right = js >= 0.f, left = js <= 0.f;
+    const bool c1 = (up && right) || (down && left);
+    const bool c2 = !c1 && ((down && right) || (up && left));
+    *keep = false;
+    *strong = false;
+    if (c1 || c2) {
+        const float ai = fabsf(is), aj = fabsf(js);
+        const bool idom = c1 ? (ai > aj) : !(ai < aj);
+        const float w = (idom ? aj : ai) / (idom ? ai : aj);
+        const float n12 = c1 ? m1r : mAr, n22 = c1 ? mAl : m1l;
+        const float n11 = idom ? (c1 ? m1 : mA) : mBr;
+        const float n21 = idom ? (c1 ? mA : m1) : mBl;
+        const double omw = 1.0 - (double)w;
+        const double plus = (double)(n12 * w) + (double)n11 * omw;
+        const double minus = (double)(n22 * w) + (double)n21 * omw;
+        const double md = (double)m;
+        *keep = (plus <= md) && (minus <= md);
+        *strong = *keep && (m >= 0.2f);
+    }
+}
+
+template <bool DBG>
+__global__ void __launch_bounds__(SN4_WARPS * 32, 4) k_sobel_nms4(const float* __restrict__ sm_all,
+                                                                  const FrameInfo* __restrict__ info,
+                                                                  int passes_per_frame, uint32_t* __restrict__ low_all,
+                                                                  uint32_t* __restrict__ high_all,
+                                                                  float* __restrict__ mag_dbg) {
+    const int pass = blockIdx.y;
+    const int S = info[pass / passes_per_frame].S;
+    const int r0 = blockIdx.x * SN_ROWS;
+    if (r0 >= S) return;
+    const int r1 = min(r0 + SN_ROWS, S);
+    // the masks are zeroed by the launcher; every warp adds its bits with global atomics (only
+    // the ~2 % of pixels that survive the suppression) and no warp ever waits for another
+    uint32_t* low = low_all + (int64_t)pass * SNN_SMAX * SNN_WPR;
+    uint32_t* high = high_all + (int64_t)pass * SNN_SMAX * SNN_WPR;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cbase = warp * SN4_COLS;
+    if (cbase < S) {    // S >= 11 here (smaller windows are skipped upstream)
+        const unsigned FULL = 0xffffffffu;
+        const int ca = cbase + 2 * lane - 2, cb = ca + 1;
+        const float* base = sm_all + (int64_t)pass * SNN_SMAX * SNN_SMAX;
+        const float* pa = base + min(max(f_symm(ca, S), 0), S - 1);
+        const float* pb = base + min(max(f_symm(cb, S), 0), S - 1);
+        const bool useful = lane >= 1 && lane <= 30;
+        const bool mine_a = useful && ca >= 1 && ca <= S - 2, mine_b = useful && cb >= 1 && cb <= S - 2;
+        const int rlo = max(r0, 1), rhi = min(r1, S - 1);       // NMS rows [rlo, rhi)
+        // bit positions of the two columns in the 13-word rows (ca is even: both in one word)
+        const int wword = max(ca, 0) >> 5, wshift = max(ca, 0) & 31;
+        float s0a = 0.f, s1a = 0.f, s0b = 0.f, s1b = 0.f;
+        double dj0a = 0.0, dj1a = 0.0, dj0b = 0.0, dj1b = 0.0;
+        float mAa = 0.f, mBa = 0.f, isBa = 0.f, jsBa = 0.f, mAb = 0.f, mBb = 0.f, isBb = 0.f, jsBb = 0.f;
+        float mAl = 0.f, mBl = 0.f, mAr = 0.f, mBr = 0.f;   // column ca-1 / cb+1 of the two previous rows
+        int rn = f_symm(r0 - 2, S);
+        float nxa = pa[rn * SNN_SMAX], nxb = pb[rn * SNN_SMAX];
+        rn = max(f_symm(r0 - 1, S), 0);
+        float nx2a = pa[rn * SNN_SMAX], nx2b = pb[rn * SNN_SMAX];
+#pragma unroll 3
+        for (int rho = r0 - 2; rho <= r1 + 1; ++rho) {
+            const float s2a = nxa, s2b = nxb;
+            nxa = nx2a;
+            nxb = nx2b;
+            {
+                int q = rho + 2;                        // scipy 'reflect' row of the iteration after next
+                q = q < 0 ? -q - 1 : q;
+                q = q >= S ? 2 * S - 1 - q : q;
+                q = min(max(q, 0), S - 1);
+                nx2a = pa[q * SNN_SMAX];
+                nx2b = pb[q * SNN_SMAX];
+            }
+            // axis-1 derivative of row rho: -(s[c-1] - s[c+1])
+            const float sla = __shfl_up_sync(FULL, s2b, 1), srb = __shfl_down_sync(FULL, s2a, 1);
+            const double djna = (double)(-__fsub_rn(sla, s2b));
+            const double djnb = (double)(-__fsub_rn(s2a, srb));
+            // axis-0 derivative of row rho-1, then the [1 2 1] passes (float64 accumulation)
+            const float dia = -__fsub_rn(s0a, s2a), dib = -__fsub_rn(s0b, s2b);
+            const float dila = __shfl_up_sync(FULL, dib, 1), dirb = __shfl_down_sync(FULL, dia, 1);
+            const double dda = (double)dia, ddb = (double)dib;
+            const float is1a = (float)(dda * 2.0 + ((double)dila + ddb) * 1.0);
+            const float is1b = (float)(ddb * 2.0 + (dda + (double)dirb) * 1.0);
+            const float js1a = (float)(dj1a * 2.0 + (dj0a + djna) * 1.0);
+            const float js1b = (float)(dj1b * 2.0 + (dj0b + djnb) * 1.0);
+            float mma = is1a * is1a, mmb = is1b * is1b;
+            mma = mma + js1a * js1a;
+            mmb = mmb + js1b * js1b;
+            const float m1a = sqrtf(mma), m1b = sqrtf(mmb);
+            const float m1l = __shfl_up_sync(FULL, m1b, 1), m1r = __shfl_down_sync(FULL, m1a, 1);
+            const int r = rho - 2;
+            if (DBG && useful && rho - 1 >= r0 && rho - 1 < r1) {
+                float* md = mag_dbg + (int64_t)pass * SNN_SMAX * SNN_SMAX + (rho - 1) * SNN_SMAX;
+                if (ca >= 0 && ca < S) md[ca] = m1a;
+                if (cb >= 0 && cb < S) md[cb] = m1b;
+            }
+            if (r >= rlo && r < rhi) {      // warp-uniform
+                bool ka = false, ha = false, kb = false, hb = false;
+                if (mine_a && mBa >= 0.1f)
+                    nms_pixel(isBa, jsBa, mBa, mAl, mAa, mAb, mBl, mBb, m1l, m1a, m1b, &ka, &ha);
+                if (mine_b && mBb >= 0.1f)
+                    nms_pixel(isBb, jsBb, mBb, mAa, mAb, mAr, mBa, mBr, m1a, m1b, m1r, &kb, &hb);
+                if (ka | kb) {
+                    atomicOr(&low[r * SNN_WPR + wword], ((ka ? 1u : 0u) | (kb ? 2u : 0u)) << wshift);
+                    if (ha | hb) atomicOr(&high[r * SNN_WPR + wword], ((ha ? 1u : 0u) | (hb ? 2u : 0u)) << wshift);
+                }
+            }
+            s0a = s1a; s1a = s2a; s0b = s1b; s1b = s2b;
+            dj0a = dj1a; dj1a = djna; dj0b = dj1b; dj1b = djnb;
+            mAl = mBl; mBl = m1l; mAr = mBr; mBr = m1r;
+            mAa = mBa; mBa = m1a; mAb = mBb; mBb = m1b;
+            isBa = is1a; jsBa = js1a; isBb = is1b; jsBb = js1b;
+        }
+    }
+}
+
 // ---- launchers (image.cu picks them when the parameters match) ----------------------------------------
 int snn_launch_gray6(snn_ctx* ctx, const ExtractPlan& pl, int nf) {
     k_gray6<<<dim3(13, 13, nf * pl.nq), dim3(32, 8), 0, ctx->stream>>>(pl.Dc, pl.info, pl.gray, pl.bufA);
@@ -661,6 +787,18 @@ int snn_launch_gauss_fast(snn_ctx* ctx, const ExtractPlan& pl, int npass, int pp
 
 int snn_launch_sobel_nms2(snn_ctx* ctx, const ExtractPlan& pl, int npass, int ppf, float* mag_dbg) {
     const dim3 grid((SNN_SMAX + SN_ROWS - 1) / SN_ROWS, npass);
+    static const bool old3 = getenv("SNN_NMS3") != nullptr;   // A/B switch: one column per lane
+    if (!old3) {
+        const size_t mask_bytes = (size_t)npass * SNN_SMAX * SNN_WPR * sizeof(uint32_t);
+        SNN_CUDA(cudaMemsetAsync(pl.low, 0, mask_bytes, ctx->stream));
+        SNN_CUDA(cudaMemsetAsync(pl.high, 0, mask_bytes, ctx->stream));
+        if (mag_dbg)
+            k_sobel_nms4<true><<<grid, SN4_WARPS * 32, 0, ctx->stream>>>(pl.bufC, pl.info, ppf, pl.low, pl.high, mag_dbg);
+        else
+            k_sobel_nms4<false><<<grid, SN4_WARPS * 32, 0, ctx->stream>>>(pl.bufC, pl.info, ppf, pl.low, pl.high, mag_dbg);
+        SNN_LAUNCH_CHECK("k_sobel_nms4");
+        return SNN_OK;
+    }
     if (mag_dbg)
         k_sobel_nms3<true><<<grid, SN_WARPS * 32, 0, ctx->stream>>>(pl.bufC, pl.info, ppf, pl.low, pl.high, mag_dbg);
     else
