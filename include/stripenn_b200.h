@@ -97,6 +97,10 @@ int snn_fetch(snn_ctx* ctx, int chrom_id, int64_t i0, int64_t i1, int64_t j0, in
  * np.quantile(mat[mat > 0], q) over the full symmetric matrix (off-diagonal pixels count
  * twice), numpy 'linear' interpolation reproduced bit-exactly. */
 int snn_quantiles(snn_ctx* ctx, int chrom_id, int nq, const double* q, double* out);
+/* The same for several resident chromosomes in one call (getStripe.py:166 loops over ChrList):
+ * out = nchrom x nq, row k = chrom_ids[k]. */
+int snn_quantiles_multi(snn_ctx* ctx, int nchrom, const int32_t* chrom_ids, int nq, const double* q,
+                        double* out);
 
 /* ---- a3: getStripe.mpmean (getStripe.py:178-235): expected value per diagonal. */
 int snn_expected(snn_ctx* ctx, int chrom_id, double* out /* [SNN_NDIST] */);

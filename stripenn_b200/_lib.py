@@ -58,6 +58,7 @@ SIGNATURES = {
     "snn_unload_chrom": (C.c_int, [_P, C.c_int]),
     "snn_fetch": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _P]),
     "snn_quantiles": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
+    "snn_quantiles_multi": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, _P]),
     "snn_expected": (C.c_int, [_P, C.c_int, _P]),
     "snn_row_flags": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P]),
     "snn_background": (C.c_int, [_P, C.c_int, C.c_int64, _P, _P]),

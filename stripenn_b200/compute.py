@@ -273,7 +273,7 @@ def run_pipeline(obj, cm, qs, chromnames, pvalue, mask, slow, comm=None, say=lam
     try:
         say('1. Maximum pixel value calculation ...')
         quant = obj.getQuantile_slow if slow else obj.getQuantile_original
-        f_mp = {c: dq.submit(quant, cm, [c], qs) for c in my_sel}
+        f_mp_all = dq.submit(quant, cm, my_sel, qs)
         say('2. Expected value calculation ...')
         f_ev = {c: dq.submit(obj.expected_values, c) for c in my_sel}
         say('3. Background distribution estimation ...')
@@ -286,7 +286,7 @@ def run_pipeline(obj, cm, qs, chromnames, pvalue, mask, slow, comm=None, say=lam
         def submit_search():
             if todo:
                 c = todo.pop(0)
-                f_cand.append((c, dq.submit(lambda c=c: obj.search_candidates(c, f_mp[c].result()[c]))))
+                f_cand.append((c, dq.submit(lambda c=c: obj.search_candidates(c, f_mp_all.result()[c]))))
         for _ in range(ahead):
             submit_search()
         avail = {}
@@ -305,7 +305,7 @@ def run_pipeline(obj, cm, qs, chromnames, pvalue, mask, slow, comm=None, say=lam
         bg = (full[0], full[1], full[2], full[3])
         f_bg = dq.submit(obj._install_background, bg)
         clock.lap('background')
-        MP = {c: f_mp[c].result()[c] for c in my_sel}
+        MP = dict(f_mp_all.result())
         EV = {c: f_ev[c].result() for c in my_sel}
         # ---- search -> prune -> p-values (grouped) -> prune by p-value -> stripiness
         kept, pend, f_pv = [], [], []      # kept: (chrom, records, positions)

@@ -273,6 +273,22 @@ int snn_quantiles(snn_ctx* ctx, int chrom_id, int nq, const double* q, double* o
     return snn_quantiles_impl(ctx, c, nq, q, out);
 }
 
+int snn_quantiles_multi(snn_ctx* ctx, int nchrom, const int32_t* chrom_ids, int nq, const double* q, double* out) {
+    if (!ctx) return snn_fail(nullptr, SNN_EINVAL, "ctx is NULL");
+    if (nchrom < 0 || (nchrom > 0 && !chrom_ids) || nq < 1 || nq > 64 || !q || !out)
+        return snn_fail(ctx, SNN_EINVAL, "snn_quantiles_multi: bad arguments");
+    for (int i = 0; i < nq; ++i)
+        if (!(q[i] >= 0.0 && q[i] <= 1.0)) return snn_fail(ctx, SNN_EINVAL, "Quantiles must be in the range [0, 1]");
+    SNN_CUDA(cudaSetDevice(ctx->device));
+    std::vector<SnnChrom*> cs;
+    for (int k = 0; k < nchrom; ++k) {
+        SnnChrom* c = snn_find_chrom(ctx, chrom_ids[k]);
+        if (!c) return snn_fail(ctx, SNN_ESTATE, "chromosome %d is not loaded", chrom_ids[k]);
+        cs.push_back(c);
+    }
+    return snn_quantiles_multi_impl(ctx, cs, nq, q, out);
+}
+
 int snn_expected(snn_ctx* ctx, int chrom_id, double* out) {
     GET_CHROM(c);
     if (!out) return snn_fail(ctx, SNN_EINVAL, "snn_expected: out is NULL");

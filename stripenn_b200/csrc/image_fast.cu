@@ -252,7 +252,9 @@ __global__ void __launch_bounds__(128) k_gauss_vm(const float* __restrict__ in_a
 // row out of shared memory (odd pitch: the 32 lanes hit 32 banks) into a second tile, and a
 // coalesced pass divides by the bleed-over image and stores.  37 KB per CTA: 6 CTAs per SM.
 #define GH_ROWS 32
+#ifndef GH_WARPS
 #define GH_WARPS 4
+#endif
 template <int R>
 __global__ void __launch_bounds__(GH_WARPS * 32) k_gauss_hm(const float* __restrict__ in_all,
                                                             const FrameInfo* __restrict__ info, int passes_per_frame,

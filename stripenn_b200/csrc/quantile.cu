@@ -17,159 +17,250 @@
 
 #define QMAXK 32  // ranks handled per sweep (2 per quantile)
 
-__device__ __forceinline__ bool pixel_key(const int32_t* b1, const int32_t* b2, const int32_t* cnt,
-                                          const double* w, int64_t t, unsigned long long* key, unsigned* mult) {
-    int32_t a = b1[t], b = b2[t];
-    double v = (double)cnt[t];
-    if (w) v = v * (w[a] * w[b]);
+// One chromosome's pixel table and its slice of the per-chromosome work arrays.
+struct QChrom {
+    const int32_t* b1;
+    const int32_t* b2;
+    const int32_t* cnt;
+    const double* w;
+    int64_t nnz;
+};
+// Per-chromosome work area (device): total, state[2*QMAXK], group[QMAXK+1] (+pad), hist[QMAXK*256]
+#define QW_TOTAL 0
+#define QW_STATE 1
+#define QW_GROUP (1 + 2 * QMAXK)                       /* ints packed in 64-bit words */
+#define QW_HIST (1 + 2 * QMAXK + (QMAXK + 2) / 2)
+#define QW_WORDS (QW_HIST + QMAXK * 256)
+
+__device__ __forceinline__ bool pixel_key(const QChrom& c, int64_t t, unsigned long long* key, unsigned* mult) {
+    int32_t a = c.b1[t], b = c.b2[t];
+    double v = (double)c.cnt[t];
+    if (c.w) v = v * (c.w[a] * c.w[b]);
     if (!(v > 0.0)) return false;  // also drops NaN
     *key = (unsigned long long)__double_as_longlong(v);
     *mult = (a == b) ? 1u : 2u;
     return true;
 }
 
-__global__ void k_count_positive(const int32_t* __restrict__ b1, const int32_t* __restrict__ b2,
-                                 const int32_t* __restrict__ cnt, const double* __restrict__ w, int64_t nnz,
-                                 unsigned long long* __restrict__ total) {
+// grid = (blocks per chromosome, chromosomes): every kernel below handles all chromosomes of a
+// call in ONE launch (a chromosome's table is only ~35 MB: per-chromosome launches were
+// latency-bound, 18 launches of ~15 us each).
+__global__ void k_count_positive(const QChrom* __restrict__ chroms, unsigned long long* __restrict__ work) {
+    const QChrom c = chroms[blockIdx.y];
     unsigned long long local = 0;
-    int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < nnz; t += stride) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < c.nnz; t += stride) {
         unsigned long long key;
         unsigned mult;
-        if (pixel_key(b1, b2, cnt, w, t, &key, &mult)) local += mult;
+        if (pixel_key(c, t, &key, &mult)) local += mult;
     }
     for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
-    if ((threadIdx.x & 31) == 0 && local) atomicAdd(total, local);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(work + (size_t)blockIdx.y * QW_WORDS + QW_TOTAL, local);
 }
 
-// state[k] = {prefix, remaining rank}; hist[k][256] global 64-bit counters.
-__global__ void k_radix_hist(const int32_t* __restrict__ b1, const int32_t* __restrict__ b2,
-                             const int32_t* __restrict__ cnt, const double* __restrict__ w, int64_t nnz, int K,
-                             int shift, const unsigned long long* __restrict__ state,
-                             unsigned long long* __restrict__ hist) {
+// state[k] = {prefix, remaining rank}; hist[g][256] 64-bit counters, one histogram per GROUP of
+// ranks that still share their prefix (group[k], group[QMAXK] = number of groups: written by
+// k_radix_pick — the ranks of neighbouring quantiles walk down the same digits for most of the
+// passes, and in the first pass all of them share the empty prefix).  Lanes of a warp that hit
+// the same (group, digit) counter are merged with __match_any_sync before the shared-memory
+// atomic.
+__global__ void k_radix_hist(const QChrom* __restrict__ chroms, int K, int shift,
+                             unsigned long long* __restrict__ work) {
     __shared__ unsigned sh[QMAXK * 256];
-    __shared__ unsigned long long pre[QMAXK];
-    for (int t = threadIdx.x; t < K * 256; t += blockDim.x) sh[t] = 0;
-    if (threadIdx.x < K) pre[threadIdx.x] = state[2 * threadIdx.x];
+    __shared__ unsigned long long pre[QMAXK];   // prefix (bits above the current digit) of each group
+    const QChrom c = chroms[blockIdx.y];
+    unsigned long long* wk = work + (size_t)blockIdx.y * QW_WORDS;
+    const unsigned long long* state = wk + QW_STATE;
+    const int* group = (const int*)(wk + QW_GROUP);
+    unsigned long long* hist = wk + QW_HIST;
+    const int ng = group[QMAXK];
+    if (ng == 0) return;                         // chromosome without positive pixels
+    for (int t = threadIdx.x; t < ng * 256; t += blockDim.x) sh[t] = 0;
+    if (threadIdx.x < K) {
+        const unsigned long long p = state[2 * threadIdx.x];
+        pre[group[threadIdx.x]] = (shift == 56) ? 0ull : (p >> (shift + 8));   // same value from every member
+    }
     __syncthreads();
-    int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < nnz; t += stride) {
-        unsigned long long key;
-        unsigned mult;
-        if (!pixel_key(b1, b2, cnt, w, t, &key, &mult)) continue;
-        unsigned digit = (unsigned)(key >> shift) & 255u;
-        unsigned long long hi = (shift == 56) ? 0ull : (key >> (shift + 8));
-        for (int k = 0; k < K; ++k) {
-            unsigned long long ph = (shift == 56) ? 0ull : (pre[k] >> (shift + 8));
-            if (hi == ph) atomicAdd(&sh[k * 256 + digit], mult);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t nround = (c.nnz + stride - 1) / stride;
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int64_t it = 0; it < nround; ++it, t += stride) {     // whole warps stay in the loop (match_any)
+        unsigned long long key = 0;
+        unsigned mult = 0;
+        const bool ok = t < c.nnz && pixel_key(c, t, &key, &mult);
+        const unsigned digit = (unsigned)(key >> shift) & 255u;
+        const unsigned long long hi = (shift == 56) ? 0ull : (key >> (shift + 8));
+        for (int g = 0; g < ng; ++g) {
+            const bool hit = ok && hi == pre[g];
+            const unsigned act = __ballot_sync(0xffffffffu, hit);
+            if (!act) continue;
+            if (hit) {
+                const unsigned peers = __match_any_sync(act, digit);
+                const unsigned twos = __ballot_sync(act, mult == 2u) & peers;
+                if ((int)(threadIdx.x & 31) == __ffs(peers) - 1)
+                    atomicAdd(&sh[g * 256 + digit], (unsigned)__popc(peers) + (unsigned)__popc(twos));
+            }
         }
     }
     __syncthreads();
-    for (int t = threadIdx.x; t < K * 256; t += blockDim.x)
-        if (sh[t]) atomicAdd(&hist[t], (unsigned long long)sh[t]);
+    for (int q = threadIdx.x; q < ng * 256; q += blockDim.x)
+        if (sh[q]) atomicAdd(&hist[q], (unsigned long long)sh[q]);
 }
 
-__global__ void k_radix_pick(int K, int shift, unsigned long long* __restrict__ state,
-                             unsigned long long* __restrict__ hist) {
-    int k = threadIdx.x;
+// One CTA per chromosome: one thread per rank picks its digit from its group's histogram;
+// thread 0 then regroups the ranks by their (longer) prefixes for the next pass.
+__global__ void k_radix_pick(int K, int shift, unsigned long long* __restrict__ work) {
+    __shared__ unsigned long long npre[QMAXK];
+    unsigned long long* wk = work + (size_t)blockIdx.x * QW_WORDS;
+    unsigned long long* state = wk + QW_STATE;
+    int* group = (int*)(wk + QW_GROUP);
+    unsigned long long* hist = wk + QW_HIST;
+    if (group[QMAXK] == 0) return;
+    const int k = threadIdx.x;
     if (k < K) {
+        const unsigned long long* h = hist + (size_t)group[k] * 256;
         unsigned long long rank = state[2 * k + 1], cum = 0;
         int digit = 255;
         for (int d = 0; d < 256; ++d) {
-            unsigned long long h = hist[k * 256 + d];
-            if (cum + h > rank) { digit = d; break; }
-            cum += h;
+            const unsigned long long cc = h[d];
+            if (cum + cc > rank) { digit = d; break; }
+            cum += cc;
         }
-        state[2 * k] |= ((unsigned long long)digit) << shift;
+        npre[k] = state[2 * k] | (((unsigned long long)digit) << shift);
+        state[2 * k] = npre[k];
         state[2 * k + 1] = rank - cum;
     }
     __syncthreads();
-    for (int t = threadIdx.x; t < K * 256; t += blockDim.x) hist[t] = 0;
+    if (k == 0) {
+        int ng = 0;
+        for (int a = 0; a < K; ++a) {
+            int g = -1;
+            for (int b = 0; b < a; ++b)
+                if (npre[b] == npre[a]) { g = group[b]; break; }
+            if (g < 0) g = ng++;
+            group[a] = g;
+        }
+        group[QMAXK] = ng;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < QMAXK * 256; t += blockDim.x) hist[t] = 0;
 }
 
-int snn_quantiles_impl(snn_ctx* ctx, SnnChrom* c, int nq, const double* q, double* out) {
+int snn_quantiles_multi_impl(snn_ctx* ctx, const std::vector<SnnChrom*>& cs, int nq, const double* q,
+                             double* out) {
+    const int nc = (int)cs.size();
+    if (nc == 0) return SNN_OK;
     void* scratch = nullptr;
-    size_t bytes = (1 + 2 * QMAXK + (size_t)QMAXK * 256) * sizeof(unsigned long long);
-    int rc = snn_scratch(ctx, bytes, &scratch);
+    const size_t wbytes = (size_t)nc * QW_WORDS * sizeof(unsigned long long);
+    const size_t cbytes = (((size_t)nc * sizeof(QChrom)) + 255) & ~(size_t)255;
+    int rc = snn_scratch(ctx, cbytes + wbytes, &scratch);
     if (rc) return rc;
-    unsigned long long* d_total = (unsigned long long*)scratch;
-    unsigned long long* d_state = d_total + 1;
-    unsigned long long* d_hist = d_state + 2 * QMAXK;
-    int threads = 256;
-    int blocks = (int)((c->nnz + threads - 1) / threads);
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    QChrom* d_chroms = (QChrom*)scratch;
+    unsigned long long* d_work = (unsigned long long*)((char*)scratch + cbytes);
+    std::vector<QChrom> hc((size_t)nc);
+    int64_t maxnnz = 1;
+    for (int i = 0; i < nc; ++i) {
+        hc[i].b1 = cs[i]->bin1;
+        hc[i].b2 = cs[i]->bin2;
+        hc[i].cnt = cs[i]->count;
+        hc[i].w = cs[i]->weight;
+        hc[i].nnz = cs[i]->nnz;
+        if (cs[i]->nnz > maxnnz) maxnnz = cs[i]->nnz;
+    }
+    const int threads = 256;
+    int blocks = (int)((maxnnz + threads * 8 - 1) / (threads * 8));    // ~8 pixels per thread
+    const int cap = (148 * 8 + nc - 1) / nc;
+    if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
+    const dim3 grid(blocks, nc);
 
-    SNN_CUDA(cudaMemsetAsync(scratch, 0, bytes, ctx->stream));
-    unsigned long long n = 0;
+    SNN_CUDA(cudaMemcpyAsync(d_chroms, hc.data(), (size_t)nc * sizeof(QChrom), cudaMemcpyHostToDevice, ctx->stream));
+    SNN_CUDA(cudaMemsetAsync(d_work, 0, wbytes, ctx->stream));
     {
         SnnScope scope(ctx, ST_QUANTILE, 1);
-        k_count_positive<<<blocks, threads, 0, ctx->stream>>>(c->bin1, c->bin2, c->count, c->weight, c->nnz,
-                                                              d_total);
+        k_count_positive<<<grid, threads, 0, ctx->stream>>>(d_chroms, d_work);
         SNN_LAUNCH_CHECK("k_count_positive");
     }
-    SNN_CUDA(cudaMemcpyAsync(&n, d_total, sizeof n, cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<unsigned long long> hw((size_t)nc * QW_WORDS);
+    // only the heads of the work areas travel: total, state, group
+    SNN_CUDA(cudaMemcpy2DAsync(hw.data(), QW_WORDS * 8, d_work, QW_WORDS * 8, QW_HIST * 8, nc, cudaMemcpyDeviceToHost,
+                               ctx->stream));
     SNN_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (n == 0) {  // np.quantile of an empty array
-        for (int i = 0; i < nq; ++i) out[i] = NAN;
-        return SNN_OK;
-    }
     for (int base = 0; base < nq; base += QMAXK / 2) {
-        int m = nq - base < QMAXK / 2 ? nq - base : QMAXK / 2;
-        int K = 2 * m;
-        std::vector<unsigned long long> state(2 * K, 0ull);
-        std::vector<double> gamma(m);
-        std::vector<char> top(m, 0);
-        for (int i = 0; i < m; ++i) {
-            // 'linear': virtual index (n - 1) * q ; _get_indexes: floor, +1, clipped to the ends
-            double vi = (double)(long long)(n - 1) * q[base + i];
-            double fl = floor(vi);
-            unsigned long long prev, next;
-            if (vi >= (double)(long long)(n - 1)) {
-                prev = next = n - 1;
-                top[i] = 1;
-            } else if (vi < 0) {
-                prev = next = 0;
-            } else {
-                prev = (unsigned long long)fl;
-                next = prev + 1;
+        const int m = nq - base < QMAXK / 2 ? nq - base : QMAXK / 2;
+        const int K = 2 * m;
+        std::vector<double> gamma((size_t)nc * m);
+        std::vector<char> top((size_t)nc * m, 0);
+        for (int ci = 0; ci < nc; ++ci) {
+            unsigned long long* wk = hw.data() + (size_t)ci * QW_WORDS;
+            const unsigned long long n = wk[QW_TOTAL];
+            unsigned long long* state = wk + QW_STATE;
+            int* group = (int*)(wk + QW_GROUP);
+            for (int i = 0; i < 2 * QMAXK; ++i) state[i] = 0ull;
+            for (int i = 0; i < QMAXK; ++i) group[i] = 0;      // every rank starts with the empty prefix
+            group[QMAXK] = n ? 1 : 0;
+            if (!n) continue;
+            for (int i = 0; i < m; ++i) {
+                // 'linear': virtual index (n - 1) * q ; _get_indexes: floor, +1, clipped to the ends
+                double vi = (double)(long long)(n - 1) * q[base + i];
+                double fl = floor(vi);
+                unsigned long long prev, next;
+                if (vi >= (double)(long long)(n - 1)) {
+                    prev = next = n - 1;
+                    top[(size_t)ci * m + i] = 1;
+                } else if (vi < 0) {
+                    prev = next = 0;
+                } else {
+                    prev = (unsigned long long)fl;
+                    next = prev + 1;
+                }
+                gamma[(size_t)ci * m + i] = vi - fl;
+                state[2 * (2 * i) + 1] = prev;
+                state[2 * (2 * i + 1) + 1] = next;
             }
-            gamma[i] = vi - fl;
-            state[2 * (2 * i) + 1] = prev;
-            state[2 * (2 * i + 1) + 1] = next;
         }
-        SNN_CUDA(cudaMemcpyAsync(d_state, state.data(), state.size() * sizeof(unsigned long long),
-                                 cudaMemcpyHostToDevice, ctx->stream));
+        SNN_CUDA(cudaMemcpy2DAsync(d_work, QW_WORDS * 8, hw.data(), QW_WORDS * 8, QW_HIST * 8, nc,
+                                   cudaMemcpyHostToDevice, ctx->stream));
         {
             SnnScope scope(ctx, ST_QUANTILE, 16);
             for (int shift = 56; shift >= 0; shift -= 8) {
-                k_radix_hist<<<blocks, threads, 0, ctx->stream>>>(c->bin1, c->bin2, c->count, c->weight, c->nnz,
-                                                                  K, shift, d_state, d_hist);
+                k_radix_hist<<<grid, threads, 0, ctx->stream>>>(d_chroms, K, shift, d_work);
                 SNN_LAUNCH_CHECK("k_radix_hist");
-                k_radix_pick<<<1, 256, 0, ctx->stream>>>(K, shift, d_state, d_hist);
+                k_radix_pick<<<nc, 256, 0, ctx->stream>>>(K, shift, d_work);
                 SNN_LAUNCH_CHECK("k_radix_pick");
             }
         }
-        SNN_CUDA(cudaMemcpyAsync(state.data(), d_state, state.size() * sizeof(unsigned long long),
-                                 cudaMemcpyDeviceToHost, ctx->stream));
+        SNN_CUDA(cudaMemcpy2DAsync(hw.data(), QW_WORDS * 8, d_work, QW_WORDS * 8, QW_HIST * 8, nc,
+                                   cudaMemcpyDeviceToHost, ctx->stream));
         SNN_CUDA(cudaStreamSynchronize(ctx->stream));
-        for (int i = 0; i < m; ++i) {
-            double a, b;
-            memcpy(&a, &state[2 * (2 * i)], 8);
-            memcpy(&b, &state[2 * (2 * i + 1)], 8);
-            double t = gamma[i];
-            if (top[i]) t = 0.0, b = a;
-            // numpy _lerp
-            volatile double diff = b - a;
-            volatile double prod = diff * t;
-            double r = a + prod;
-            if (t >= 0.5) {
-                volatile double omt = 1 - t;
-                volatile double prod2 = diff * omt;
-                r = b - prod2;
+        for (int ci = 0; ci < nc; ++ci) {
+            const unsigned long long* wk = hw.data() + (size_t)ci * QW_WORDS;
+            const unsigned long long* state = wk + QW_STATE;
+            for (int i = 0; i < m; ++i) {
+                double* dst = out + (size_t)ci * nq + base + i;
+                if (!wk[QW_TOTAL]) { *dst = NAN; continue; }   // np.quantile of an empty array
+                double a, b;
+                memcpy(&a, &state[2 * (2 * i)], 8);
+                memcpy(&b, &state[2 * (2 * i + 1)], 8);
+                double t = gamma[(size_t)ci * m + i];
+                if (top[(size_t)ci * m + i]) t = 0.0, b = a;
+                // numpy _lerp
+                volatile double diff = b - a;
+                volatile double prod = diff * t;
+                double r = a + prod;
+                if (t >= 0.5) {
+                    volatile double omt = 1 - t;
+                    volatile double prod2 = diff * omt;
+                    r = b - prod2;
+                }
+                *dst = r;
             }
-            out[base + i] = r;
         }
     }
     return SNN_OK;
+}
+
+int snn_quantiles_impl(snn_ctx* ctx, SnnChrom* c, int nq, const double* q, double* out) {
+    std::vector<SnnChrom*> one(1, c);
+    return snn_quantiles_multi_impl(ctx, one, nq, q, out);
 }

@@ -173,6 +173,7 @@ __host__ __device__ __forceinline__ void snn_pyslice(int64_t a, int64_t b, int64
 // ---- per-TU entry points used by api.cu ---------------------------------------------------
 int snn_band_build(snn_ctx* ctx, SnnChrom* c);
 int snn_quantiles_impl(snn_ctx* ctx, SnnChrom* c, int nq, const double* q, double* out);
+int snn_quantiles_multi_impl(snn_ctx* ctx, const std::vector<SnnChrom*>& cs, int nq, const double* q, double* out);
 int snn_expected_impl(snn_ctx* ctx, SnnChrom* c, double* out);
 int snn_row_flags_impl(snn_ctx* ctx, SnnChrom* c, int nunits, const int64_t* geom, uint8_t* avail,
                        uint8_t* live);

@@ -120,6 +120,16 @@ class Device:
         check(self.lib.snn_quantiles(self.h, int(chrom_id), int(q.shape[0]), ptr(q), ptr(out)), self.h)
         return out
 
+    def quantiles_multi(self, chrom_ids, qs: Sequence[float]):
+        """snn_quantiles for several resident chromosomes in one call -> (len(chrom_ids), len(qs))."""
+        ids = np.ascontiguousarray(chrom_ids, dtype=np.int32)
+        q = np.ascontiguousarray(qs, dtype=np.float64)
+        out = np.empty((ids.shape[0], q.shape[0]), dtype=np.float64)
+        if ids.shape[0]:
+            check(self.lib.snn_quantiles_multi(self.h, int(ids.shape[0]), ptr(ids), int(q.shape[0]), ptr(q), ptr(out)),
+                  self.h)
+        return out
+
     def expected(self, chrom_id):
         out = np.empty(NDIST, dtype=np.float64)
         check(self.lib.snn_expected(self.h, int(chrom_id), ptr(out)), self.h)

@@ -92,11 +92,10 @@ class getStripe:
     # ------------------------------------------------------------------ a2
     def getQuantile_original(self, coolinfo, ChrList, quantile):
         """getStripe.py:160-176 -> {chrom: ndarray[len(quantile)]}."""
-        out = {}
-        for c in ChrList:
-            cid = self.unbalLib.ensure(c)
-            out[c] = self.dev.quantiles(cid, quantile)
-        return out
+        ChrList = list(ChrList)
+        ids = [self.unbalLib.ensure(c) for c in ChrList]
+        vals = self.dev.quantiles_multi(ids, quantile)      # one device call for the whole list
+        return {c: vals[i] for i, c in enumerate(ChrList)}
 
     def getQuantile_slow(self, coolinfo, ChrList, quantile):
         raise NotImplementedError(

@@ -36,6 +36,9 @@ class FakeDevice:
     def quantiles(self, cid, qs):
         return np.quantile(self.mat.positive_population(self._name(cid)), qs)
 
+    def quantiles_multi(self, cids, qs):
+        return np.array([self.quantiles(c, qs) for c in cids]).reshape(len(cids), len(qs))
+
     def expected(self, cid):
         c = self._name(cid)
         return np.array(bgm.expected_by_distance(self.mat, [c])[c])
