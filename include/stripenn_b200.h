@@ -102,6 +102,19 @@ int snn_quantiles(snn_ctx* ctx, int chrom_id, int nq, const double* q, double* o
 int snn_quantiles_multi(snn_ctx* ctx, int nchrom, const int32_t* chrom_ids, int nq, const double* q,
                         double* out);
 
+/* -s / getStripe.getQuantile_slow (getStripe.py:107-158): np.quantile over a ROW/COLUMN-SELECTED
+ * population.  The reference slices the matrix selector in genome-wide bin coordinates, block by
+ * block: rows r_start + [k*w, min((k+1)*w - 1, floor(chromsize/r))) (the last row of every block is
+ * lost), columns [r_start, r_end), with r_start = ceil(cumsize_before/r) + 1 — which skips the
+ * first bin and, after several chromosomes, starts inside the PREVIOUS chromosome.  The host
+ * (stripenn_b200.getstripe.getQuantile_slow) turns that into sources: source k adds to job[k] the
+ * positive entries (row i, column j) — both triangles of the symmetric matrix — of resident
+ * chromosome chrom_ids[k] with c0 <= j < c1 and a = i - s satisfying 0 <= a < F and
+ * a % w != w - 1; sel = nsrc x 5 int64 {s, w, F, c0, c1} in chromosome-local bins (s may be
+ * negative).  out = njob x nq (NaN for an empty population). */
+int snn_quantiles_select(snn_ctx* ctx, int nsrc, const int32_t* chrom_ids, const int32_t* job,
+                         const int64_t* sel, int njob, int nq, const double* q, double* out);
+
 /* ---- a3: getStripe.mpmean (getStripe.py:178-235): expected value per diagonal. */
 int snn_expected(snn_ctx* ctx, int chrom_id, double* out /* [SNN_NDIST] */);
 
@@ -160,6 +173,17 @@ int snn_score_multi(snn_ctx* ctx, int nchrom, const int32_t* chrom_ids, const do
                     int64_t n, const int32_t* chrom_index, const int64_t* pos, const int32_t* stale,
                     double* pvalue, double* stripiness, double* oe_mean, double* oe_total,
                     double* o_mean, double* o_sum);
+
+/* ---- --mask chr:start-end of scoringstripes (getStripe.py:612-639, 701-707): while a mask is set,
+ * snn_score / snn_score_multi treat the O/E values of the masked bins [int(start/r), int(end/r)]
+ * as NaN for every stripe of chromosome `chrom_id` with
+ * start > min(pos1 - 50000, pos3) and start < max(pos2 + 50000, pos4) — columns of the centre,
+ * left and right parts and rows of all three, with the reference's index arithmetic (the right
+ * part is shifted by one bin; a masked bin equal to int(pos1/r), int(pos2/r) or int(pos4/r)
+ * indexes one past the part and raises IndexError in the reference: such stripes get NaN
+ * Stripiness and O/E outputs).  p-values and the observed mean/sum are not affected.
+ * chrom_id < 0 clears the mask. */
+int snn_set_mask(snn_ctx* ctx, int chrom_id, int64_t start_bp, int64_t end_bp);
 
 /* ---- a15: getStripe.RemoveRedundant (:1116-1196) — host code (C++), no device work.
  * group = chromosome index per row, num = window id, pos = n x 4, h/w = the size columns,

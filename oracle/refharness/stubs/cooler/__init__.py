@@ -142,6 +142,48 @@ class _Selector:
             return arr * np.outer(w[i0:i1], w[j0:j1])
 
 
+    def __getitem__(self, key):
+        """``matrix(...)[a:b, c:d]`` — GENOME-WIDE bin coordinates (the bins of all chromosomes
+        of the file concatenated, chromosome k starting at sum(ceil(size_j / binsize), j < k)),
+        used only by getStripe.getQuantile_slow (getStripe.py:122).  The .npz contact maps are
+        cis-only, so blocks between different chromosomes are zero; balancing multiplies by the
+        outer product of the concatenated weight vector like ``fetch``.  Slices clip like numpy."""
+        d = _load(self._path)
+        rs, cs = key
+        r = d["binsize"]
+        nbs = [int(math.ceil(int(sz) / r)) for sz in d["sizes"]]
+        offs = np.concatenate([[0], np.cumsum(nbs)]).astype(np.int64)
+        total = int(offs[-1])
+
+        def rng(sl):
+            a, b, step = sl.indices(total)
+            if step != 1:
+                raise IndexError("slice step is not supported")
+            return a, max(a, b)
+        i0, i1 = rng(rs)
+        j0, j1 = rng(cs)
+        self.nfetch += 1
+        arr = np.zeros((i1 - i0, j1 - j0), dtype=np.int32)
+        bal = self._balance
+        col = None if (bal is False or bal is None) else ("weight" if bal is True else str(bal))
+        wg = np.full(total, np.nan) if col else None
+        for k, name in enumerate(d["names"]):
+            o, n = int(offs[k]), nbs[k]
+            if col and name in d["weights"][col]:
+                wg[o:o + n] = d["weights"][col][name]
+            a0, a1 = max(i0, o), min(i1, o + n)
+            b0, b1 = max(j0, o), min(j1, o + n)
+            if a0 < a1 and b0 < b1 and name in d["mats"]:
+                arr[a0 - i0:a1 - i0, b0 - j0:b1 - j0] = d["mats"][name][a0 - o:a1 - o, b0 - o:b1 - o].toarray()
+        if not col:
+            return arr
+        if col in _DIVISIVE:
+            with np.errstate(divide="ignore", invalid="ignore"):
+                wg = 1.0 / wg
+        with np.errstate(invalid="ignore"):
+            return arr * np.outer(wg[i0:i1], wg[j0:j1])
+
+
 class Cooler:
     def __init__(self, path):
         self._path = str(path)

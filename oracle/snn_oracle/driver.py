@@ -57,12 +57,12 @@ def score_chromosomes(cm):
 
 def compute(cm, norm="None", chrom="all", canny=2.0, minL=10, maxW=8,
             maxpixel="0.95,0.96,0.97,0.98,0.99", pvalue=0.1, mask="0", bfilter=3,
-            seed=123456789, gray_variant=0, return_stages=False, frame_filter=None):
+            seed=123456789, gray_variant=0, return_stages=False, frame_filter=None, slow=False):
     qs = list(map(float, maxpixel.split(",")))
     bal = resolve_norm(cm, norm)
     all_names, all_sizes, names, sizes = compute_chromosomes(cm, chrom)
     mat = OracleMatrix(cm, bal)
-    MP = pl.quantiles(mat, names, qs)
+    MP = pl.quantiles_slow(mat, names, qs) if slow else pl.quantiles(mat, names, qs)
     EV = bgm.expected_by_distance(mat, names)
     bg = bgm.null_distribution(mat, all_names, all_sizes, seed)
     per_q = []

@@ -75,6 +75,38 @@ class OracleMatrix:
         return np.concatenate([v[pos], v[off]])
 
 
+    def genome_window(self, i0, i1, j0, j1):
+        """``selector[i0:i1, j0:j1]`` in GENOME-WIDE bin coordinates (cooler RangeSelector2D
+        indexing, used only at getStripe.py:122): chromosome k occupies bins
+        [sum(ceil(size_j/r), j<k), ...); numpy-style clipping; blocks between different
+        chromosomes are zero (a ContactMap is cis-only) times the weights' outer product."""
+        r = self.binsize
+        names = list(self.cm.chromnames)
+        nbs = [int(math.ceil(int(sz) / r)) for sz in self.cm.chromsizes]
+        offs = np.concatenate([[0], np.cumsum(nbs)]).astype(np.int64)
+        total = int(offs[-1])
+        i0, i1, _ = slice(i0, i1).indices(total)
+        j0, j1, _ = slice(j0, j1).indices(total)
+        i1, j1 = max(i0, i1), max(j0, j1)
+        arr = np.zeros((i1 - i0, j1 - j0), dtype=np.float64)
+        wg = np.ones(total)
+        for k, name in enumerate(names):
+            o, n = int(offs[k]), nbs[k]
+            if name not in self.cm.chroms:
+                if self.balance is not False and self.balance is not None:
+                    wg[o:o + n] = np.nan
+                continue
+            m, w = self._mat(name)
+            if w is not None:
+                wg[o:o + n] = w
+            a0, a1 = max(i0, o), min(i1, o + n)
+            b0, b1 = max(j0, o), min(j1, o + n)
+            if a0 < a1 and b0 < b1:
+                arr[a0 - i0:a1 - i0, b0 - j0:b1 - j0] = m[a0 - o:a1 - o, b0 - o:b1 - o].toarray()
+        with np.errstate(invalid="ignore"):
+            return arr * np.outer(wg[i0:i1], wg[j0:j1])
+
+
 def nan0(a):
     a = np.array(a, dtype=np.float64, copy=True)
     a[np.isnan(a)] = 0.0

@@ -52,6 +52,38 @@ def quantiles(mat, chroms, qs):
     return out
 
 
+def quantiles_slow(mat, chroms, qs):
+    """getQuantile_slow (getStripe.py:107-158, the -s flag), literally: genome-wide row blocks of
+    w = floor(25e6 / L) rows whose slice end (k+1)*w - 1 drops each block's last row, r_start =
+    ceil(cumsize_before / r) + 1, r_end = ceil(cumsize / r).  Its values differ from
+    quantiles() by construction."""
+    names = list(mat.cm.chromnames)
+    sizes = np.asarray(mat.cm.chromsizes)
+    nbin = mat.binsize
+    cum = np.nancumsum(sizes)
+    out = {}
+    for ci in sorted(c for c in range(len(names)) if names[c] in chroms):
+        CHROMSIZE = sizes[ci]
+        L = int(np.ceil(CHROMSIZE / nbin))
+        r_start = 0 if ci == 0 else cum[ci - 1]
+        r_end = cum[ci]
+        r_start = np.ceil(r_start / nbin) + 1
+        r_end = np.ceil(r_end / nbin)
+        hs = np.empty(0)
+        w = int(np.floor(25000000 / L))
+        for k in range(int(np.ceil(L / w))):
+            w_start = k * w + r_start
+            w_end = (k + 1) * w - 1
+            if w_end >= np.floor(CHROMSIZE / nbin):
+                w_end = int(np.floor(CHROMSIZE / nbin))
+            w_end += r_start
+            blk = mat.genome_window(int(w_start), int(w_end), int(r_start), int(r_end))
+            with np.errstate(invalid="ignore"):
+                hs = np.concatenate((hs, blk[blk > 0]))
+        out[names[ci]] = np.quantile(hs, qs)
+    return out
+
+
 def maxpixel_label(q):
     return str(q * 100) + "%"   # getStripe.py:1096
 

@@ -63,7 +63,9 @@ def _expected(ex, x0, x1, y0, y1):
 
 
 def _mask_cols(m, ms, me, start, end, direc):
-    """masking() (getStripe.py:620-639)."""
+    """masking() (getStripe.py:620-639): the index list runs over range(end - start + 1), one
+    longer than the part, and the element loops raise IndexError exactly where the reference's do
+    (only when the other axis is non-empty)."""
     m = m.astype(float)
     rel0 = ms - start
     rel1 = rel0 + (me - ms)
@@ -71,9 +73,13 @@ def _mask_cols(m, ms, me, start, end, direc):
     idx = [x for x in range(rel0, rel1 + 1) if 0 <= x < L]
     if idx:
         if direc == 1:
-            m[:, idx] = np.nan      # raises IndexError like the reference if idx is out of range
+            if m.shape[0] > 0 and max(idx) >= m.shape[1]:
+                raise IndexError("masking(): column %d out of bounds for axis 1 with size %d" % (max(idx), m.shape[1]))
+            m[:, idx] = np.nan
         else:
-            m[idx, :] = np.nan
+            if m.shape[1] > 0 and max(idx) >= m.shape[0]:
+                raise IndexError("masking(): row %d out of bounds for axis 0 with size %d" % (max(idx), m.shape[0]))
+            m[[x for x in idx if x < m.shape[0]], :] = np.nan
     return m
 
 
@@ -96,8 +102,10 @@ K_XR = np.array([[1, -1], [2, -2], [1, -1]])
 K_Y = np.array([[1, 2, 1], [0, 0, 0], [-1, -2, -1]])
 
 
-def stripiness(mat, table, expected, mask="0"):
-    """scoringstripes() -> (Stripiness, O/E mean, O/E total) lists."""
+def stripiness(mat, table, expected, mask="0", on_index_error="raise"):
+    """scoringstripes() -> (Stripiness, O/E mean, O/E total) lists.  on_index_error="nan": rows on
+    which masking() raises IndexError (the reference run dies there) get NaN instead — the
+    convention of the CUDA path."""
     r = mat.binsize
     bs = int(50000 / r)
     n = len(table["pos1"])
@@ -126,12 +134,18 @@ def stripiness(mat, table, expected, mask="0"):
             r_obs = mat.fetch_bp(chrom, int(ys), int(ye), int(xei * r), int(rm * r))
             right = r_obs / (_expected(ex, xei + 1, rm + 1, ysi, yei) + .00000001)
         if is_mask and ms > np.min([xs - 50000, ys]) and ms < np.max([xe + 50000, ye]):
-            center = _mask_cols(center, mxs, mxe, xsi, xei, 1)
-            center = _mask_cols(center, mxs, mxe, ysi, yei, 2)
-            left = _mask_cols(left, mxs, mxe, lm, xsi, 1)
-            left = _mask_cols(left, mxs, mxe, ysi, yei, 2)
-            right = _mask_cols(right, mxs, mxe, xei + 1, rm, 1)
-            right = _mask_cols(right, mxs, mxe, ysi, yei, 2)
+            try:
+                center = _mask_cols(center, mxs, mxe, xsi, xei, 1)
+                center = _mask_cols(center, mxs, mxe, ysi, yei, 2)
+                left = _mask_cols(left, mxs, mxe, lm, xsi, 1)
+                left = _mask_cols(left, mxs, mxe, ysi, yei, 2)
+                right = _mask_cols(right, mxs, mxe, xei + 1, rm, 1)
+                right = _mask_cols(right, mxs, mxe, ysi, yei, 2)
+            except IndexError:
+                if on_index_error != "nan":
+                    raise
+                g_out[i], m_out[i], t_out[i] = float("nan"), float("nan"), float("nan")
+                continue
         parts = [center.astype(float), left.astype(float), right.astype(float)]
         rowdel = []
         for k, p in enumerate(parts):

@@ -59,6 +59,7 @@ SIGNATURES = {
     "snn_fetch": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _P]),
     "snn_quantiles": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
     "snn_quantiles_multi": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, _P]),
+    "snn_quantiles_select": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, _P, _P]),
     "snn_expected": (C.c_int, [_P, C.c_int, _P]),
     "snn_row_flags": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P]),
     "snn_background": (C.c_int, [_P, C.c_int, C.c_int64, _P, _P]),
@@ -69,6 +70,7 @@ SIGNATURES = {
                                    C.c_int, _i32p, _P, _P, _P, _P, _P, _P, _P]),
     "snn_score": (C.c_int, [_P, C.c_int, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "snn_score_multi": (C.c_int, [_P, C.c_int, _P, _P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "snn_set_mask": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int64]),
     "snn_remove_redundant": (C.c_int, [C.c_int64, _P, _P, _P, _P, _P, _P, C.c_int, _P]),
     "snn_stage_times": (C.c_int, [_P, C.c_int, C.POINTER(C.c_char_p), _f64p, _i64p]),
     "snn_reset_stage_times": (C.c_int, [_P]),

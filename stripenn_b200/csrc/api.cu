@@ -4,6 +4,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <math.h>
 #include <string.h>
 
 #include "score_warp.cuh"
@@ -289,6 +290,36 @@ int snn_quantiles_multi(snn_ctx* ctx, int nchrom, const int32_t* chrom_ids, int 
     return snn_quantiles_multi_impl(ctx, cs, nq, q, out);
 }
 
+int snn_quantiles_select(snn_ctx* ctx, int nsrc, const int32_t* chrom_ids, const int32_t* job, const int64_t* sel,
+                         int njob, int nq, const double* q, double* out) {
+    if (!ctx) return snn_fail(nullptr, SNN_EINVAL, "ctx is NULL");
+    if (nsrc < 0 || njob < 0 || (nsrc > 0 && (!chrom_ids || !job || !sel)) || nq < 1 || nq > 64 || !q || !out)
+        return snn_fail(ctx, SNN_EINVAL, "snn_quantiles_select: bad arguments");
+    for (int i = 0; i < nq; ++i)
+        if (!(q[i] >= 0.0 && q[i] <= 1.0)) return snn_fail(ctx, SNN_EINVAL, "Quantiles must be in the range [0, 1]");
+    SNN_CUDA(cudaSetDevice(ctx->device));
+    std::vector<QSource> src((size_t)nsrc);
+    for (int k = 0; k < nsrc; ++k) {
+        SnnChrom* c = snn_find_chrom(ctx, chrom_ids[k]);
+        if (!c) return snn_fail(ctx, SNN_ESTATE, "chromosome %d is not loaded", chrom_ids[k]);
+        if (job[k] < 0 || job[k] >= njob) return snn_fail(ctx, SNN_EINVAL, "snn_quantiles_select: job out of range");
+        if (sel[k * 5 + 1] < 1) return snn_fail(ctx, SNN_EINVAL, "snn_quantiles_select: block height must be >= 1");
+        src[k].c = c;
+        src[k].job = job[k];
+        src[k].sel = true;
+        src[k].s = sel[k * 5 + 0];
+        src[k].wrows = sel[k * 5 + 1];
+        src[k].F = sel[k * 5 + 2];
+        src[k].c0 = sel[k * 5 + 3];
+        src[k].c1 = sel[k * 5 + 4];
+    }
+    if (nsrc == 0) {   // every job is empty: np.quantile of an empty array
+        for (int64_t i = 0; i < (int64_t)njob * nq; ++i) out[i] = NAN;
+        return SNN_OK;
+    }
+    return snn_quantiles_sources_impl(ctx, src, njob, nq, q, out);
+}
+
 int snn_expected(snn_ctx* ctx, int chrom_id, double* out) {
     GET_CHROM(c);
     if (!out) return snn_fail(ctx, SNN_EINVAL, "snn_expected: out is NULL");
@@ -378,6 +409,16 @@ int snn_score_multi(snn_ctx* ctx, int nchrom, const int32_t* chrom_ids, const do
         return snn_fail(ctx, SNN_ESTATE, "snn_score_multi: p-values requested before snn_set_background");
     return snn_score_multi_impl(ctx, slots, n, chrom_index, pos, stale, pvalue, stripiness, oe_mean, oe_total,
                                 o_mean, o_sum);
+}
+
+int snn_set_mask(snn_ctx* ctx, int chrom_id, int64_t start_bp, int64_t end_bp) {
+    if (!ctx) return snn_fail(nullptr, SNN_EINVAL, "ctx is NULL");
+    if (chrom_id >= 0 && (start_bp < 0 || end_bp < 0))
+        return snn_fail(ctx, SNN_EINVAL, "snn_set_mask: negative mask coordinates");
+    ctx->mask_chrom = chrom_id < 0 ? -1 : chrom_id;
+    ctx->mask_start = start_bp;
+    ctx->mask_end = end_bp;
+    return SNN_OK;
 }
 
 int snn_stage_times(snn_ctx* ctx, int cap, const char** names, double* ms, int64_t* launches) {

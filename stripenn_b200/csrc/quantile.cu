@@ -24,7 +24,18 @@ struct QChrom {
     const int32_t* cnt;
     const double* w;
     int64_t nnz;
+    int job;            // work area this source adds to (several sources may share one)
+    int sel;            // 0: the whole symmetric matrix; 1: the row/column selection below
+    // getQuantile_slow (getStripe.py:107-158): matrix entry (row i, column j) belongs to the
+    // population iff c0 <= j < c1 and a = i - s satisfies 0 <= a < F and a % w != w - 1
+    // (blocks of w rows, the last row of every block is dropped by the reference's slices)
+    int64_t s, wrows, F, c0, c1;
 };
+
+__device__ __forceinline__ unsigned slow_in(const QChrom& c, int64_t row, int64_t col) {
+    const int64_t a = row - c.s;
+    return (col >= c.c0 && col < c.c1 && a >= 0 && a < c.F && (a % c.wrows) != c.wrows - 1) ? 1u : 0u;
+}
 // Per-chromosome work area (device): total, state[2*QMAXK], group[QMAXK+1] (+pad), hist[QMAXK*256]
 #define QW_TOTAL 0
 #define QW_STATE 1
@@ -38,6 +49,10 @@ __device__ __forceinline__ bool pixel_key(const QChrom& c, int64_t t, unsigned l
     if (c.w) v = v * (c.w[a] * c.w[b]);
     if (!(v > 0.0)) return false;  // also drops NaN
     *key = (unsigned long long)__double_as_longlong(v);
+    if (c.sel) {
+        *mult = slow_in(c, a, b) + ((a != b) ? slow_in(c, b, a) : 0u);
+        return *mult != 0u;
+    }
     *mult = (a == b) ? 1u : 2u;
     return true;
 }
@@ -55,7 +70,7 @@ __global__ void k_count_positive(const QChrom* __restrict__ chroms, unsigned lon
         if (pixel_key(c, t, &key, &mult)) local += mult;
     }
     for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
-    if ((threadIdx.x & 31) == 0 && local) atomicAdd(work + (size_t)blockIdx.y * QW_WORDS + QW_TOTAL, local);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(work + (size_t)c.job * QW_WORDS + QW_TOTAL, local);
 }
 
 // state[k] = {prefix, remaining rank}; hist[g][256] 64-bit counters, one histogram per GROUP of
@@ -69,7 +84,7 @@ __global__ void k_radix_hist(const QChrom* __restrict__ chroms, int K, int shift
     __shared__ unsigned sh[QMAXK * 256];
     __shared__ unsigned long long pre[QMAXK];   // prefix (bits above the current digit) of each group
     const QChrom c = chroms[blockIdx.y];
-    unsigned long long* wk = work + (size_t)blockIdx.y * QW_WORDS;
+    unsigned long long* wk = work + (size_t)c.job * QW_WORDS;
     const unsigned long long* state = wk + QW_STATE;
     const int* group = (const int*)(wk + QW_GROUP);
     unsigned long long* hist = wk + QW_HIST;
@@ -146,35 +161,44 @@ __global__ void k_radix_pick(int K, int shift, unsigned long long* __restrict__ 
     for (int t = threadIdx.x; t < QMAXK * 256; t += blockDim.x) hist[t] = 0;
 }
 
-int snn_quantiles_multi_impl(snn_ctx* ctx, const std::vector<SnnChrom*>& cs, int nq, const double* q,
-                             double* out) {
-    const int nc = (int)cs.size();
-    if (nc == 0) return SNN_OK;
+int snn_quantiles_sources_impl(snn_ctx* ctx, const std::vector<QSource>& src, int njob, int nq, const double* q,
+                               double* out) {
+    const int ns = (int)src.size();
+    const int nc = njob;
+    if (ns == 0 || nc == 0) return SNN_OK;
     void* scratch = nullptr;
     const size_t wbytes = (size_t)nc * QW_WORDS * sizeof(unsigned long long);
-    const size_t cbytes = (((size_t)nc * sizeof(QChrom)) + 255) & ~(size_t)255;
+    const size_t cbytes = (((size_t)ns * sizeof(QChrom)) + 255) & ~(size_t)255;
     int rc = snn_scratch(ctx, cbytes + wbytes, &scratch);
     if (rc) return rc;
     QChrom* d_chroms = (QChrom*)scratch;
     unsigned long long* d_work = (unsigned long long*)((char*)scratch + cbytes);
-    std::vector<QChrom> hc((size_t)nc);
+    std::vector<QChrom> hc((size_t)ns);
     int64_t maxnnz = 1;
-    for (int i = 0; i < nc; ++i) {
-        hc[i].b1 = cs[i]->bin1;
-        hc[i].b2 = cs[i]->bin2;
-        hc[i].cnt = cs[i]->count;
-        hc[i].w = cs[i]->weight;
-        hc[i].nnz = cs[i]->nnz;
-        if (cs[i]->nnz > maxnnz) maxnnz = cs[i]->nnz;
+    for (int i = 0; i < ns; ++i) {
+        const SnnChrom* c = src[i].c;
+        hc[i].b1 = c->bin1;
+        hc[i].b2 = c->bin2;
+        hc[i].cnt = c->count;
+        hc[i].w = c->weight;
+        hc[i].nnz = c->nnz;
+        hc[i].job = src[i].job;
+        hc[i].sel = src[i].sel ? 1 : 0;
+        hc[i].s = src[i].s;
+        hc[i].wrows = src[i].wrows > 0 ? src[i].wrows : 1;
+        hc[i].F = src[i].F;
+        hc[i].c0 = src[i].c0;
+        hc[i].c1 = src[i].c1;
+        if (c->nnz > maxnnz) maxnnz = c->nnz;
     }
     const int threads = 256;
     int blocks = (int)((maxnnz + threads * 8 - 1) / (threads * 8));    // ~8 pixels per thread
-    const int cap = (148 * 8 + nc - 1) / nc;
+    const int cap = (148 * 8 + ns - 1) / ns;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    const dim3 grid(blocks, nc);
+    const dim3 grid(blocks, ns);
 
-    SNN_CUDA(cudaMemcpyAsync(d_chroms, hc.data(), (size_t)nc * sizeof(QChrom), cudaMemcpyHostToDevice, ctx->stream));
+    SNN_CUDA(cudaMemcpyAsync(d_chroms, hc.data(), (size_t)ns * sizeof(QChrom), cudaMemcpyHostToDevice, ctx->stream));
     SNN_CUDA(cudaMemsetAsync(d_work, 0, wbytes, ctx->stream));
     {
         SnnScope scope(ctx, ST_QUANTILE, 1);
@@ -258,6 +282,16 @@ int snn_quantiles_multi_impl(snn_ctx* ctx, const std::vector<SnnChrom*>& cs, int
         }
     }
     return SNN_OK;
+}
+
+int snn_quantiles_multi_impl(snn_ctx* ctx, const std::vector<SnnChrom*>& cs, int nq, const double* q,
+                             double* out) {
+    std::vector<QSource> src(cs.size());
+    for (size_t i = 0; i < cs.size(); ++i) {
+        src[i].c = cs[i];
+        src[i].job = (int)i;
+    }
+    return snn_quantiles_sources_impl(ctx, src, (int)cs.size(), nq, q, out);
 }
 
 int snn_quantiles_impl(snn_ctx* ctx, SnnChrom* c, int nq, const double* q, double* out) {

@@ -23,6 +23,9 @@ struct ScoreParams {
     int bs;
     int hmax;  // shared-memory capacity in rows
     int64_t bg_ncol;
+    // --mask (getStripe.py:612-639): mask_on for this chromosome; start in bp; masked bins [mxs, mxe]
+    int mask_on;
+    int64_t mask_start, mxs, mxe;
 };
 
 __device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
@@ -86,6 +89,7 @@ __global__ void __launch_bounds__(SCORE_THREADS) k_score(MatView m, const int64_
     unsigned char* rdel = (unsigned char*)(ridx + P.hmax);   // row deleted          [hmax]
     __shared__ double rex[SNN_NDIST];   // 1 / (expected[d] + 1e-8)
     __shared__ unsigned char dead[SCORE_MAXCOLS];
+    __shared__ unsigned char cmask[SCORE_MAXCOLS];   // --mask: column of its part is masked
     __shared__ double slot;
     __shared__ double red[8];
     __shared__ int redi[4];
@@ -230,17 +234,45 @@ __global__ void __launch_bounds__(SCORE_THREADS) k_score(MatView m, const int64_
         wc + wl + wr > SCORE_MAXCOLS || R0 != ysi)
         return;
     const int ncols = wc + wl + wr;  // column order: centre | left | right
+    // ---- --mask (masking(), getStripe.py:620-639, applied at :701-707): a masked bin b in [mxs, mxe]
+    // hits index b - start of a part iff 0 <= b - start < end - start + 1; for the centre columns
+    // (start xsi, end xei), the rows (ysi, yei) and the left columns (lm, xsi) that range is one
+    // longer than the part, so b == xei / yei / xsi raises IndexError in the reference -> NaN here.
+    // The right part is called with start xei + 1, end rm: its column x is masked iff xei + 1 + x is.
+    bool masked = false, mask_bad = false;
+    if (P.mask_on) {
+        const int64_t lo = (p1 - 50000 < p3) ? p1 - 50000 : p3, hi = (p2 + 50000 > p4) ? p2 + 50000 : p4;
+        masked = P.mask_start > lo && P.mask_start < hi;
+    }
+    if (masked) {
+        const bool in_xei = P.mxs <= xei && xei <= P.mxe;
+        const bool in_yei = P.mxs <= yei && yei <= P.mxe;
+        const bool in_xsi = P.mxs <= xsi && xsi <= P.mxe;
+        // centre cols (h > 0), centre rows (wc > 0), left cols (h > 0): the reference raises
+        mask_bad = in_xei || in_yei || in_xsi;
+        if (mask_bad) masked = false;    // carry on unmasked for the observed mean/sum, drop the O/E outputs
+    }
+    if (masked) {
+        for (int c = threadIdx.x; c < ncols; c += SCORE_THREADS) {
+            int64_t b = c < wc ? xsi + c : (c < wc + wl ? lmb + (c - wc) : xei + 1 + (c - wc - wl));
+            cmask[c] = (b >= P.mxs && b <= P.mxe) ? 1 : 0;
+        }
+    }
+    for (int j = threadIdx.x; j < h; j += SCORE_THREADS)
+        rdel[j] = (masked && ysi + j >= P.mxs && ysi + j <= P.mxe) ? 2 : 0;   // bit 1 = masked row, bit 0 = deleted
+    __syncthreads();
     // ---- pass 1: all-NaN columns of the O/E parts (division keeps NaN of the observed value)
     for (int c = threadIdx.x; c < ncols; c += SCORE_THREADS) {
         int64_t gc = c < wc ? cC0 + c : (c < wc + wl ? lC0 + (c - wc) : rC0 + (c - wc - wl));
         bool all = true;
-        for (int j = 0; j < h && all; ++j) {
-            const double v = W.at(j, gc);
-            if (v == v) all = false;  // observed finite or inf -> O/E not NaN (expected + 1e-8 is finite)
+        if (!(masked && cmask[c])) {
+            for (int j = 0; j < h && all; ++j) {
+                const double v = W.at(j, gc);
+                if (v == v && rdel[j] == 0) all = false;  // observed finite or inf -> O/E not NaN (expected + 1e-8 is finite)
+            }
         }
         dead[c] = all ? 1 : 0;
     }
-    for (int j = threadIdx.x; j < h; j += SCORE_THREADS) rdel[j] = 0;
     __syncthreads();
     // rows deleted together with dead columns: index x (column index inside its part) when
     // xs == ys, else shape[0]-1-x  (getStripe.py:713-731); np.delete wraps negatives
@@ -257,7 +289,7 @@ __global__ void __launch_bounds__(SCORE_THREADS) k_score(MatView m, const int64_
                     int idx = diag ? x : h - 1 - x;
                     if (idx < 0) idx += h;
                     if (idx < 0 || idx >= h) { bad_flag = 1; continue; }  // IndexError in the reference
-                    rdel[idx] = 1;
+                    rdel[idx] |= 1;
                 }
             }
         }
@@ -269,7 +301,7 @@ __global__ void __launch_bounds__(SCORE_THREADS) k_score(MatView m, const int64_
         if (threadIdx.x == 0) {
             int k = 0;
             for (int j = 0; j < h; ++j)
-                if (!rdel[j]) ridx[k++] = j;
+                if (!(rdel[j] & 1)) ridx[k++] = j;
             redi[0] = k;
         }
     } else {
@@ -289,8 +321,10 @@ __global__ void __launch_bounds__(SCORE_THREADS) k_score(MatView m, const int64_
         const int j = ridx[k];
         const int64_t row = R0 + j;
         double sc = 0.0, sl = 0.0, sr = 0.0;
+        const bool rowm = masked && (rdel[j] & 2);
         for (int c = 0; c < ncols; ++c) {
             if (dead[c]) continue;
+            if (rowm || (masked && cmask[c])) continue;     // masked O/E value: NaN -> 0
             int64_t gc, ecol;
             if (c < wc) { gc = cC0 + c; ecol = xsi + c; }
             else if (c < wc + wl) { gc = lC0 + (c - wc); ecol = lmb + (c - wc); }
@@ -327,8 +361,10 @@ __global__ void __launch_bounds__(SCORE_THREADS) k_score(MatView m, const int64_
         int n = 0;
         for (int w = 0; w < nwarp; ++w) { a += red[w]; b += red[4 + w]; n += redi[w]; }
         // centerMean = mean(center[rows_rep]) = sum / (h' * w') ; centerTotal = w' * sum  (quirk :747)
-        o[2] = (hk > 0 && lc > 0) ? a / ((double)hk * (double)lc) : qnan();
-        o[3] = (double)lc * a;
+        if (!mask_bad) {
+            o[2] = (hk > 0 && lc > 0) ? a / ((double)hk * (double)lc) : qnan();
+            o[3] = (double)lc * a;
+        }
         o[4] = n ? b / (double)n : qnan();
         o[5] = b;
     }
@@ -381,7 +417,7 @@ __global__ void __launch_bounds__(SCORE_THREADS) k_score(MatView m, const int64_
         const double b = select_kth(pv, nm, nm / 2, &slot);
         med = (a + b) / 2.0;
     }
-    if (threadIdx.x == 0) o[1] = med * avgdiff;
+    if (threadIdx.x == 0 && !mask_bad) o[1] = med * avgdiff;
 }
 
 // slot y: ex[y*1024 + t] -> ex[y*1024 + 512 + t] = 1 / (expected + 1e-8)   (getStripe.py:650)
@@ -425,8 +461,11 @@ int snn_score_multi_impl(snn_ctx* ctx, const std::vector<ScoreSlot>& slots, int6
         const SnnChrom* c = slots[sl].c;
         const int64_t p1 = pos[i * 4], p2 = pos[i * 4 + 1], p3 = pos[i * 4 + 2], p4 = pos[i * 4 + 3];
         const bool valid = p1 >= 1 && p3 >= 1 && p2 >= p1 && p4 >= p3 && p2 <= c->chromsize && p4 <= c->chromsize;
+        // --mask: stripes the mask may touch take the CTA kernel (it holds the masking logic)
+        const bool mask_hit = want_s && ctx->mask_chrom >= 0 && c->id == ctx->mask_chrom &&
+                              ctx->mask_start > std::min(p1 - 50000, p3) && ctx->mask_start < std::max(p2 + 50000, p4);
         int wk = -1;
-        if (valid && !ctx->force_generic && bs <= 64 && wmaxbp >= 0 && (p2 - p1) <= wmaxbp) {
+        if (valid && !mask_hit && !ctx->force_generic && bs <= 64 && wmaxbp >= 0 && (p2 - p1) <= wmaxbp) {
             const int64_t reach = (int64_t)(c->bw - 1 - bs) * r;   // |row - col| < bw for the whole window
             if ((p2 - p3) < reach && (p4 - p1) < reach) {
                 for (int k = 0; k < 3 && wk < 0; ++k)
@@ -524,6 +563,10 @@ int snn_score_multi_impl(snn_ctx* ctx, const std::vector<ScoreSlot>& slots, int6
             P.bs = bs;
             P.hmax = cls[k].hcap;
             P.bg_ncol = ctx->bg_ncol;
+            P.mask_on = (ctx->mask_chrom >= 0 && c->id == ctx->mask_chrom) ? 1 : 0;
+            P.mask_start = ctx->mask_start;
+            P.mxs = ctx->mask_start / c->binsize;     // int(mask_start / resol), getStripe.py:617-618
+            P.mxe = ctx->mask_end / c->binsize;
             const size_t smem = (size_t)cls[k].hcap * per_row + (size_t)cls[k].wcap * sizeof(double) + 64;
             k_score<<<(unsigned)ord.size(), SCORE_THREADS, smem, ctx->stream>>>(
                 snn_view(c), dpos, dstale, dorder + gstart[(size_t)sl * 3 + k], hcd[sl].rex, ctx->bg_sorted,

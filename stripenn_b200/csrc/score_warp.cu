@@ -94,6 +94,41 @@ __device__ double warp_median(const double* a, int n, int lane) {
     return (n & 1) ? vhi : (vlo + vhi) / 2.0;
 }
 
+// np.median of a[0..n) for n > 32: bitonic sort of a padded copy in `buf` (shared, >= 512 doubles,
+// the window tile is free by then) instead of the O(n^2 / 32) rank counting above — 45 compare-
+// exchange sweeps for 512 values against ~20k comparisons per lane for a 300-row stripe
+// (ncu r01p: rank counting was 52 % of the instructions of the tall-stripe launch).
+__device__ double warp_median_sort(double* buf, const double* a, int n, int lane) {
+    int P = 64;
+    while (P < n) P <<= 1;
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    for (int i = lane; i < P; i += 32) buf[i] = i < n ? a[i] : inf;
+    __syncwarp();
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = lane; t < (P >> 1); t += 32) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int l = i | j;
+                const bool up = (i & k) == 0;
+                const double x = buf[i], y = buf[l];
+                if ((x > y) == up) { buf[i] = y; buf[l] = x; }
+            }
+            __syncwarp();
+        }
+    }
+    const double hi = buf[n >> 1], lo = buf[(n - 1) >> 1];
+    __syncwarp();
+    return (n & 1) ? hi : (lo + hi) / 2.0;
+}
+
+__device__ __forceinline__ double warp_median_any(double* buf, const double* a, int n, int lane) {
+    return n <= 32 ? warp_median(a, n, lane) : warp_median_sort(buf, a, n, lane);
+}
+
+__device__ __forceinline__ void cp_async8(double* sdst, const double* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc));
+}
+
 __device__ __forceinline__ uint64_t low_mask64(int n) { return n >= 64 ? ~0ull : ((1ull << n) - 1ull); }
 
 __global__ void __launch_bounds__(SW_WARPS * 32, SW_MINB) k_score_warp(const ChromDev* __restrict__ cds,
@@ -144,7 +179,8 @@ __global__ void __launch_bounds__(SW_WARPS * 32, SW_MINB) k_score_warp(const Chr
             case 9: num = p3 - 1; break;
             default: break;
         }
-        const int qv = (int)(num / r);
+        // coordinates below 2^32 bp (every real genome) take the 32-bit divider (~4x fewer instructions)
+        const int qv = ((uint64_t)(num | r) >> 32) == 0 ? (int)((uint32_t)num / (uint32_t)r) : (int)(num / r);
         const int R0 = __shfl_sync(FULL, qv, 0), R1 = __shfl_sync(FULL, qv, 1);
         const int C0 = __shfl_sync(FULL, qv, 2), C1 = __shfl_sync(FULL, qv, 3);
         const int xsi = __shfl_sync(FULL, qv, 4), xei = __shfl_sync(FULL, qv, 5);
@@ -194,17 +230,19 @@ __global__ void __launch_bounds__(SW_WARPS * 32, SW_MINB) k_score_warp(const Chr
             const int row0 = R0 + j0;
             __syncwarp();
             // Element (row, col) of the symmetric matrix sits at band[min*(bw-1) + max]: both loops
-            // below walk that address linearly, one pointer bump per iteration.
+            // below walk that address linearly.  The copies are cp.async (global -> shared without
+            // a register stop): every cell of the tile is in flight before the first one is
+            // awaited (ncu r01p: the load-then-store loops exposed one DRAM round trip per row).
             // cells on/above the diagonal: by window row, lanes along the band row
             {
                 const int nU = min(nr, cmax - row0);                  // rows that reach the diagonal
                 const double* __restrict__ g = band + (int64_t)row0 * bwm1 + cmin + lane;
                 double* sdst = win + lane;
                 int d = row0 - cmin - lane;                           // row - col of this lane's first cell
-                #pragma unroll 1
+                #pragma unroll 4
                 for (int rr = 0; rr < nU; ++rr) {
                     for (int cc = 0; cc + lane < ncw; cc += 32)
-                        if (d - cc <= 0) sdst[cc] = __ldg(g + cc);
+                        if (d - cc <= 0) cp_async8(sdst + cc, g + cc);
                     g += bwm1;
                     sdst += pitch;
                     ++d;
@@ -217,14 +255,16 @@ __global__ void __launch_bounds__(SW_WARPS * 32, SW_MINB) k_score_warp(const Chr
                 double* sdst = win + lane * pitch;
                 int d = row0 + lane - cmin;                           // row - col
                 const bool rowok = lane < nr;
-                #pragma unroll 2
+                #pragma unroll 4
                 for (int cc = 0; cc < nL; ++cc) {
-                    if (rowok && d > 0) *sdst = __ldg(g);
+                    if (rowok && d > 0) cp_async8(sdst, g);
                     g += bwm1;
                     ++sdst;
                     --d;
                 }
             }
+            asm volatile("cp.async.commit_group;");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
             __syncwarp();
             const bool act = lane < nr;
             const int j = j0 + lane;
@@ -305,7 +345,7 @@ __global__ void __launch_bounds__(SW_WARPS * 32, SW_MINB) k_score_warp(const Chr
             #pragma unroll 1
             for (int j = lane; j < h; j += 32) anynan |= (pv[j] != pv[j]);
             anynan = __any_sync(FULL, anynan);
-            res0 = anynan ? w_qnan() : warp_median(pv, h, lane);
+            res0 = anynan ? w_qnan() : warp_median_any(win, pv, h, lane);
         }
 
         // ================================ stripiness ================================================
@@ -414,7 +454,7 @@ __global__ void __launch_bounds__(SW_WARPS * 32, SW_MINB) k_score_warp(const Chr
                     nm += __popc(b);
                 }
                 __syncwarp();
-                const double med = nm ? warp_median(pv, nm, lane) : w_qnan();
+                const double med = nm ? warp_median_any(win, pv, nm, lane) : w_qnan();
                 res1 = med * avgdiff;
             }
         }

@@ -90,6 +90,9 @@ struct snn_ctx {
     double* bg_sorted = nullptr;
     int32_t* bg_valid = nullptr;
     int64_t bg_ncol = 0;
+    // --mask of scoringstripes (snn_set_mask): chromosome id (< 0: none), start/end in bp
+    int mask_chrom = -1;
+    int64_t mask_start = 0, mask_end = 0;
     // scratch of snn_extract, grown on demand
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
@@ -173,6 +176,16 @@ __host__ __device__ __forceinline__ void snn_pyslice(int64_t a, int64_t b, int64
 // ---- per-TU entry points used by api.cu ---------------------------------------------------
 int snn_band_build(snn_ctx* ctx, SnnChrom* c);
 int snn_quantiles_impl(snn_ctx* ctx, SnnChrom* c, int nq, const double* q, double* out);
+// One source of a quantile job: the positive pixels of chromosome c, whole (sel = false) or
+// restricted like getQuantile_slow's genome-wide slices (quantile.cu: QChrom).
+struct QSource {
+    SnnChrom* c = nullptr;
+    int job = 0;
+    bool sel = false;
+    int64_t s = 0, wrows = 1, F = 0, c0 = 0, c1 = 0;
+};
+int snn_quantiles_sources_impl(snn_ctx* ctx, const std::vector<QSource>& src, int njob, int nq, const double* q,
+                               double* out);
 int snn_quantiles_multi_impl(snn_ctx* ctx, const std::vector<SnnChrom*>& cs, int nq, const double* q, double* out);
 int snn_expected_impl(snn_ctx* ctx, SnnChrom* c, double* out);
 int snn_row_flags_impl(snn_ctx* ctx, SnnChrom* c, int nunits, const int64_t* geom, uint8_t* avail,

@@ -130,6 +130,17 @@ class Device:
                   self.h)
         return out
 
+    def quantiles_select(self, chrom_ids, jobs, sel, njob, qs: Sequence[float]):
+        """snn_quantiles_select (the -s populations of getQuantile_slow) -> (njob, len(qs))."""
+        ids = np.ascontiguousarray(chrom_ids, dtype=np.int32)
+        jb = np.ascontiguousarray(jobs, dtype=np.int32)
+        sl = np.ascontiguousarray(sel, dtype=np.int64).reshape(-1, 5)
+        q = np.ascontiguousarray(qs, dtype=np.float64)
+        out = np.empty((int(njob), q.shape[0]), dtype=np.float64)
+        check(self.lib.snn_quantiles_select(self.h, int(ids.shape[0]), ptr(ids), ptr(jb), ptr(sl), int(njob),
+                                            int(q.shape[0]), ptr(q), ptr(out)), self.h)
+        return out
+
     def expected(self, chrom_id):
         out = np.empty(NDIST, dtype=np.float64)
         check(self.lib.snn_expected(self.h, int(chrom_id), ptr(out)), self.h)
@@ -249,6 +260,11 @@ class Device:
         self.h2d_bytes += p.nbytes + ci.nbytes + (0 if ex is None else ex.nbytes)
         self.d2h_bytes += n * 48
         return res
+
+    def set_mask(self, chrom_id: Optional[int], start_bp: int = 0, end_bp: int = 0):
+        """--mask of scoringstripes (getStripe.py:612-639) for the following score calls; None clears it."""
+        check(self.lib.snn_set_mask(self.h, -1 if chrom_id is None else int(chrom_id), int(start_bp), int(end_bp)),
+              self.h)
 
     # ------------------------------------------------------------------ timers
     def enable_timing(self, on=True):

@@ -97,11 +97,54 @@ class getStripe:
         vals = self.dev.quantiles_multi(ids, quantile)      # one device call for the whole list
         return {c: vals[i] for i, c in enumerate(ChrList)}
 
+    def slow_selection(self, ChrList):
+        """The populations getQuantile_slow (getStripe.py:107-158) builds, as (chromosomes, sources):
+        sources = [(source chromosome, job, s, w, F, c0, c1)] in the terms of snn_quantiles_select.
+        The reference slices the selector in GENOME-WIDE bins: rows r_start + [k*w, min((k+1)*w-1,
+        floor(size/r))) for k < ceil(L/w), w = floor(25e6/L); columns [r_start, r_end) with r_start =
+        ceil(cumsize_before/r) + 1, r_end = ceil(cumsize/r) — not the chromosome's own bin offset
+        sum(ceil(size_j/r)), so the first bin is skipped and the window can begin in the previous
+        chromosome(s).  Pixels between different chromosomes are not part of a ContactMap (cis
+        only), like in the oracle's selector."""
+        cm = self.unbalLib.cm
+        names = list(cm.chromnames)
+        sizes = np.asarray(cm.chromsizes)
+        nbin = cm.binsize
+        cum = np.nancumsum(sizes)
+        nb = [int(np.ceil(sz / nbin)) for sz in sizes]
+        offs = np.concatenate([[0], np.cumsum(nb)]).astype(np.int64)
+        chridx = sorted(c for c in range(len(names)) if names[c] in ChrList)
+        jobs, sources = [], []
+        for ci in chridx:
+            CHROMSIZE = sizes[ci]
+            L = int(np.ceil(CHROMSIZE / nbin))
+            r_start = 0 if ci == 0 else cum[ci - 1]
+            r_end = cum[ci]
+            r_start = int(np.ceil(r_start / nbin) + 1)
+            r_end = int(np.ceil(r_end / nbin))
+            w = int(np.floor(25000000 / L))
+            F = int(np.floor(CHROMSIZE / nbin))
+            job = len(jobs)
+            jobs.append(names[ci])
+            for p in range(ci + 1):
+                if offs[p + 1] <= r_start and p != ci:
+                    continue        # the window starts after this chromosome
+                if r_end <= offs[p]:
+                    continue
+                if names[p] not in cm.chroms:
+                    continue        # no pixels stored for it
+                sources.append((names[p], job, r_start - int(offs[p]), w, F, r_start - int(offs[p]),
+                                r_end - int(offs[p])))
+        return jobs, sources
+
     def getQuantile_slow(self, coolinfo, ChrList, quantile):
-        raise NotImplementedError(
-            "-s/--slow (getStripe.getQuantile_slow, getStripe.py:107-158) is not built yet: in the "
-            "reference it returns DIFFERENT maxpixel values than the default path (SURVEY.md §8f "
-            "row 2); the B200 path needs no memory-saving mode, run without -s")
+        """getStripe.py:107-158 (-s) -> {chrom: ndarray[len(quantile)]}.  NOT the values of
+        getQuantile_original: see slow_selection."""
+        jobs, sources = self.slow_selection(list(ChrList))
+        ids = [self.unbalLib.ensure(s[0]) for s in sources]
+        sel = np.array([s[2:] for s in sources], dtype=np.int64).reshape(-1, 5)
+        vals = self.dev.quantiles_select(ids, [s[1] for s in sources], sel, len(jobs), quantile)
+        return {c: vals[i] for i, c in enumerate(jobs)}
 
     # ------------------------------------------------------------------ a3
     def mpmean(self):
@@ -420,10 +463,24 @@ class getStripe:
         ids, index = self._slots(chrs, groups)
         return self.dev.score_multi(ids, index, pos, None, True, stale)["pvalue"].tolist()
 
+    def _apply_mask(self, mask):
+        """--mask 'chr:start-end' (getStripe.py:612-618) -> device state; '0' clears it.  A mask on a
+        chromosome that is not in the contact map never matches (`mask_chr == c` is False)."""
+        if mask == '0':
+            self.dev.set_mask(None)
+            return
+        parts = mask.split(':')
+        mask_chr = parts[0]
+        mask_start = int(parts[1].split('-')[0])
+        mask_end = int(parts[1].split('-')[1])
+        if mask_chr in self.unbalLib.cm.chromnames:
+            self.dev.set_mask(self.unbalLib.chrom_id(mask_chr), mask_start, mask_end)
+        else:
+            self.dev.set_mask(None)
+
     def scoringstripes(self, df, expecVal, mask='0'):
-        """getStripe.py:608-788 -> (Stripiness, O/E mean, O/E total) lists."""
-        if mask != '0':
-            raise NotImplementedError("--mask (getStripe.py:612-639) is not built yet (SURVEY.md §8f row 3)")
+        """getStripe.py:608-788 -> (Stripiness, O/E mean, O/E total) lists.  With a mask, stripes
+        on which the reference's masking() raises IndexError get NaN."""
         n = len(df)
         g, m, t = np.zeros(n), np.zeros(n), np.zeros(n)
         if n == 0:
@@ -431,20 +488,28 @@ class getStripe:
         chrs, pos, groups = self._by_chrom(df)
         ids, index = self._slots(chrs, groups)
         ex = np.stack([np.asarray(expecVal[c], dtype=np.float64) for c in groups])
-        res = self.dev.score_multi(ids, index, pos, ex, False)
+        self._apply_mask(mask)
+        try:
+            res = self.dev.score_multi(ids, index, pos, ex, False)
+        finally:
+            if mask != '0':
+                self.dev.set_mask(None)
         return res["stripiness"].tolist(), res["oe_mean"].tolist(), res["oe_total"].tolist()
 
     def stripiness_of(self, parts, expecVal, mask='0'):
         """scoringstripes for [(chrom, n x 4 positions)] in one device call -> Stripiness array."""
-        if mask != '0':
-            raise NotImplementedError("--mask (getStripe.py:612-639) is not built yet (SURVEY.md §8f row 3)")
         parts = [(c, pos) for c, pos in parts if len(pos)]
         if not parts:
             return np.zeros(0)
         ids = np.array([self.unbalLib.ensure(c) for c, _ in parts], dtype=np.int32)
         index = np.concatenate([np.full(len(pos), k, dtype=np.int32) for k, (_, pos) in enumerate(parts)])
         ex = np.stack([np.asarray(expecVal[c], dtype=np.float64) for c, _ in parts])
-        return self.dev.score_multi(ids, index, np.concatenate([pos for _, pos in parts]), ex, False)["stripiness"]
+        self._apply_mask(mask)
+        try:
+            return self.dev.score_multi(ids, index, np.concatenate([pos for _, pos in parts]), ex, False)["stripiness"]
+        finally:
+            if mask != '0':
+                self.dev.set_mask(None)
 
     def getMean(self, df):
         """getStripe.py:501-534 -> (nanmean, nansum) lists of the stripe bodies."""

@@ -22,6 +22,10 @@ class FakeDevice:
         self.mat = OracleMatrix(cm, balance)
         self.loaded = {}
         self.bg = None
+        self.mask = "0"
+
+    def set_mask(self, cid, start_bp=0, end_bp=0):
+        self.mask = "0" if cid is None else "%s:%d-%d" % (self._name(cid), start_bp, end_bp)
 
     def close(self):
         pass
@@ -107,7 +111,7 @@ class FakeDevice:
         if want_pvalue:
             res["pvalue"] = np.array(sc.pvalues(self.mat, self.bg, table), dtype=float)
         if expected is not None:
-            s, m, t = sc.stripiness(self.mat, table, {c: expected})
+            s, m, t = sc.stripiness(self.mat, table, {c: expected}, self.mask, on_index_error="nan")
             res["stripiness"], res["oe_mean"], res["oe_total"] = (np.array(v, dtype=float) for v in (s, m, t))
             om, osum = sc.observed_mean(self.mat, table)
             res["o_mean"], res["o_sum"] = np.array(om, dtype=float), np.array(osum, dtype=float)
