@@ -121,6 +121,30 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+NCU_FAMILY = {"gaussian": ("k_gauss_vm", "k_gauss_hm"), "sobel_nms": ("k_sobel_nms",), "gray": ("k_gray6",),
+              "search": ("k_search",), "score": ("k_score_warp",), "background": ("k_background",),
+              "quantile_select": ("k_radix_hist",)}
+
+
+def ncu_traffic(family):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of a kernel family from
+    the newest committed `ncu --set full` summary under profiles/ (one capture per kernel, taken on
+    a full 51-window batch like the launches of this benchmark); mean over the family's kernels."""
+    import glob
+    best = None
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_summary.json"))):
+        try:
+            k = json.load(open(f)).get("kernels", {})
+        except Exception:
+            continue
+        if all(n in k and "dram_read" in k[n] for n in NCU_FAMILY.get(family, ("?",))):
+            unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            tot = [k[n]["dram_read"] * unit.get(k[n].get("dram_read_unit", "Mbyte"), 1e6) +
+                   k[n]["dram_write"] * unit.get(k[n].get("dram_write_unit", "Mbyte"), 1e6) for n in NCU_FAMILY[family]]
+            best = (sum(tot) / len(tot), os.path.basename(f))
+    return best
+
+
 # ------------------------------------------------------------------------------------------ CPU arm
 def _cpu_window(args):
     """One search window x all maxpixel values with the oracle port (worker process)."""
@@ -476,8 +500,14 @@ def native_arm(args):
                          "achieved_gbs": (alg[k] / 1e9) / (kern_ms[k] / 1e3) if k in alg and kern_ms[k] > 0 else None}
                      for k in kern_ms}
         ach = per_stage[top]["achieved_gbs"]
+        nl = max(stages[top]["launches"] / steps, 1)
+        tr = ncu_traffic(top)
         roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                    "frac": (ach / peak) if ach else None, "traffic": None, "peak_source": peak_src,
+                    "frac": (ach / peak) if ach else None, "traffic": tr[0] if tr else None,
+                    "traffic_source": ("%s: dram read+write per launch, mean over %s" % (tr[1], "+".join(NCU_FAMILY[top])))
+                    if tr else None,
+                    "launches_per_step": nl, "algorithmic_bytes_per_launch": alg.get(top, 0) / nl,
+                    "avg_launch_ms": kern_ms[top] / nl, "peak_source": peak_src,
                     "share_of_step": kern_ms[top] / (ms_dev / steps), "stages": per_stage,
                     "gpu_ms_per_step": sum(kern_ms.values())}
         cpu = None
