@@ -36,7 +36,7 @@ def main():
             continue
         if re.match(r"\s+/\*[0-9a-f]{4,}\*/\s", ln):
             lines_of.append(cur)
-    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + (["--launch-skip", os.environ["NCU_SKIP"], "--launch-count", "1"] if os.environ.get("NCU_SKIP") else []), capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr = next(r for r in rows if "Instructions Executed" in r)
     start = rows.index(hdr) + 1
