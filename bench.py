@@ -121,6 +121,9 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+CONFIG_TEXT = {"cfg1": "synthetic chr16-sized map at 5 kb", "cfg2": "synthetic mouse whole genome at 10 kb (chr1-19+X)",
+               "cfg3": "synthetic human whole genome at 5 kb, KR-balanced (chrY dropped by the chromosome filter)",
+               "cfg4": "synthetic human chr1 at 1 kb"}
 NCU_FAMILY = {"gaussian": ("k_gauss_vm", "k_gauss_hm"), "sobel_nms": ("k_sobel_nms",), "gray": ("k_gray6",),
               "search": ("k_search",), "score": ("k_score_warp",), "background": ("k_background",),
               "quantile_select": ("k_radix_hist",)}
@@ -348,7 +351,6 @@ def native_arm(args):
     mpix_rank = genome_mpixels(cm, [c for c in chromnames if c in cm.chroms])
     nnz_rank = sum(cm.chroms[c].nnz for c in cm.chroms)
 
-    os.environ["NCCL_DEBUG"] = os.environ.get("SNN_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
     nstreams = 1 if strong else max(1, args.streams)
     stream = torch.cuda.current_stream()
     devs, tstreams = [], []
@@ -520,10 +522,11 @@ def native_arm(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
                 "ms_per_step": ms_dev / steps, "higher_is_better": True, "scaling": args.scaling,
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "%s: synthetic mouse whole genome at 10 kb (chr1-19+X, %d bins, %.0f Mpixels "
-                                       "per genome), --norm None, -m %s, stages 1-5 of compute" %
-                                       (args.config, sum(int(math.ceil(s / binsize)) for s in sizes),
-                                        mpix_rank if not strong else mpix_total, QS),
+                "config": {"workload": "%s: %s (%d chromosomes, %d bins, %.0f Mpixels per genome), --norm %s, "
+                                       "-m %s, stages 1-5 of compute" %
+                                       (args.config, CONFIG_TEXT.get(args.config, "synthetic map at %d bp" % binsize),
+                                        len(sizes), sum(int(math.ceil(s / binsize)) for s in sizes),
+                                        mpix_rank if not strong else mpix_total, norm, QS),
                            "host_threads_per_gpu": nstreams,
                            "parallelism": ("1 genome per GPU (independent samples)" if not strong else
                                            "1 genome sharded by chromosome (LPT) over %d GPUs" % world),
@@ -543,7 +546,14 @@ def native_arm(args):
 
 if __name__ == "__main__":
     a = parse()
+    # stdout carries exactly ONE JSON line: anything else a library prints there (NCCL's version
+    # banner, warnings of child processes) is sent to stderr; the line goes to the real stdout
+    sys.stdout.flush()
+    _real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = _real_stdout
     if a.impl == "reference":
         reference_arm(a)
     else:
         native_arm(a)
+    _real_stdout.flush()
