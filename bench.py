@@ -336,8 +336,12 @@ def native_arm(args):
     names = [c[0] for c in chroms]
     sizes = [c[1] for c in chroms]
     if strong:
-        owner = cp.lpt_partition(names, sizes, world)
-        mine = [c for c in names if owner[c] == rank]
+        # the same plan run_pipeline derives: whole chromosomes longest-first, window ranges of an
+        # over-sized chromosome (single-chromosome configs) spread over several ranks
+        shell = synth.make_map(chroms, binsize, only=[])
+        f_names, f_sizes, _, _ = cp.compute_chromosomes(shell, ["all"])
+        units = cp.plan_units(f_names, f_sizes, binsize, world)
+        mine = [c for c in names if any(u["chrom"] == c and u["rank"] == rank for u in units)]
         seed = synth.DEFAULT_SEED
     else:
         mine = names
@@ -348,7 +352,11 @@ def native_arm(args):
     norm = "KR" if balanced else "None"
     bal = cp.resolve_norm(cm, norm, "compute", False)
     all_names, all_sizes, chromnames, chromsizes = cp.compute_chromosomes(cm, ["all"])
-    mpix_rank = genome_mpixels(cm, [c for c in chromnames if c in cm.chroms])
+    if strong:   # pixels of the windows THIS rank searches (a cut chromosome is shared)
+        mpix_rank = NQ * sum(synth.frame_pixels_range(cm.nbins(u["chrom"]), u["lo"], u["hi"]) for u in units
+                             if u["rank"] == rank and u["chrom"] in chromnames) / 1e6
+    else:
+        mpix_rank = genome_mpixels(cm, [c for c in chromnames if c in cm.chroms])
     nnz_rank = sum(cm.chroms[c].nnz for c in cm.chroms)
 
     nstreams = 1 if strong else max(1, args.streams)

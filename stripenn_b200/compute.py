@@ -224,6 +224,34 @@ def lpt_partition(names, sizes, world):
     return owner
 
 
+def plan_units(names, sizes_bp, binsize, world, split=True):
+    """Work units of the sharded pipeline: whole chromosomes, except that a chromosome holding
+    more than 1.25 x its fair share of the bins (total / world) is cut into window ranges
+    (getStripe.py:841-842: windows of one chromosome are independent tasks) — a single-chromosome
+    run (BASELINE configs 1 and 4) then still uses every GPU.  Units are assigned longest first
+    (work ~ windows).  Returns a list of dicts {chrom, piece, npieces, lo, hi, rank}; piece 0's
+    rank is the chromosome's PRIMARY (it runs the chromosome-wide stages and the host steps)."""
+    import math
+    nb = [int(math.ceil(int(s) / binsize)) for s in sizes_bp]
+    total = max(sum(nb), 1)
+    fair = total / max(world, 1)
+    units = []
+    for i, c in enumerate(names):
+        nfr = max(1, int(math.ceil(nb[i] / 200)))
+        k = 1
+        if split and world > 1 and nb[i] > 1.25 * fair:
+            k = max(1, min(world, nfr, int(round(nb[i] / fair))))
+        for p in range(k):
+            lo, hi = (nfr * p) // k, (nfr * (p + 1)) // k
+            units.append(dict(chrom=c, piece=p, npieces=k, lo=lo, hi=hi, order=i, rank=0))
+    load = [0] * world
+    for u in sorted(units, key=lambda u: (-(u["hi"] - u["lo"]), u["order"], u["piece"])):
+        r = min(range(world), key=lambda k: (load[k], k))
+        u["rank"] = r
+        load[r] += u["hi"] - u["lo"]
+    return units
+
+
 def make_object(cm, bal, dev, all_names, all_sizes, chromnames, chromsizes, minL, maxW, canny, numcores,
                 bfilter, seed, gray_variant):
     lib = gs.DeviceMatrix(cm, bal, dev)
@@ -251,8 +279,10 @@ class DeviceQueue:
 
 def run_pipeline(obj, cm, qs, chromnames, pvalue, mask, slow, comm=None, say=lambda *a, **k: None,
                  return_stages=False, group=5, ahead=2):
-    """Stages 1-5 of compute (stripenn.py:120-152) for the chromosomes this rank owns, with the
-    two host-side exchanges the background needs.  `obj` is a getStripe-shaped object.
+    """Stages 1-5 of compute (stripenn.py:120-152) for the units this rank owns (plan_units:
+    whole chromosomes, window ranges of over-sized ones), with the two host-side exchanges the
+    background needs (+ one for the window ranges of cut chromosomes).  `obj` is a
+    getStripe-shaped object.
 
     Every device call goes through one DeviceQueue in an order that keeps the GPU busy while this
     thread does the host steps: maxpixel values, expected values and row flags of all
@@ -265,28 +295,37 @@ def run_pipeline(obj, cm, qs, chromnames, pvalue, mask, slow, comm=None, say=lam
     comm = comm or LocalComm()
     clock = StageClock()
     all_names = list(obj.all_chromnames)
-    owner = lpt_partition(all_names, obj.all_chromsizes, comm.world)
-    mine = lambda c: owner.get(c, 0) == comm.rank
+    units = plan_units(all_names, obj.all_chromsizes, obj.resol, comm.world)
+    primary = {u["chrom"]: u["rank"] for u in units if u["piece"] == 0}
+    mine = lambda c: primary.get(c, 0) == comm.rank
     my_sel = [c for c in chromnames if mine(c)]
+    # search units of this rank, in -k order; a split chromosome's windows are searched by several
+    # ranks (each holds the chromosome and derives the same maxpixel values) and merged by its primary
+    my_units = sorted((u for u in units if u["rank"] == comm.rank and u["chrom"] in chromnames),
+                      key=lambda u: (list(chromnames).index(u["chrom"]), u["piece"]))
+    split_chroms = [c for c in chromnames if any(u["chrom"] == c and u["npieces"] > 1 for u in units)]
+    quant_sel = list(dict.fromkeys(my_sel + [u["chrom"] for u in my_units]))
     labels = [str(q * 100) + '%' for q in qs]
     dq = DeviceQueue()
     try:
         say('1. Maximum pixel value calculation ...')
         quant = obj.getQuantile_slow if slow else obj.getQuantile_original
-        f_mp_all = dq.submit(quant, cm, my_sel, qs)
+        f_mp_all = dq.submit(quant, cm, quant_sel, qs)
         say('2. Expected value calculation ...')
         f_ev = {c: dq.submit(obj.expected_values, c) for c in my_sel}
         say('3. Background distribution estimation ...')
         names2 = obj.background_chromosomes()
         f_avail = dq.submit(obj.available_counts, [c for c in names2 if mine(c)])
         say('4. Finding candidate stripes from each chromosome ...')
-        todo = list(my_sel)
+        todo = list(my_units)
         f_cand = []
 
         def submit_search():
             if todo:
-                c = todo.pop(0)
-                f_cand.append((c, dq.submit(lambda c=c: obj.search_candidates(c, f_mp_all.result()[c]))))
+                u = todo.pop(0)
+                rng = None if u["npieces"] == 1 else (u["lo"], u["hi"])
+                f_cand.append((u, dq.submit(lambda u=u, rng=rng: obj.search_candidates(
+                    u["chrom"], f_mp_all.result()[u["chrom"]], rng))))
         for _ in range(ahead):
             submit_search()
         avail = {}
@@ -315,18 +354,36 @@ def run_pipeline(obj, cm, qs, chromnames, pvalue, mask, slow, comm=None, say=lam
                 grp = list(pend)
                 del pend[:]
                 f_pv.append((grp, dq.submit(obj.candidate_pvalues, grp, bg)))
-        i = 0
-        while i < len(f_cand):
-            c, f = f_cand[i]
-            i += 1
-            raw = f.result()
-            submit_search()
+        def take(c, raw):
             cand, pos = obj.prune_candidates(raw)
             if len(cand):
                 kept.append((c, cand, pos))
                 pend.append((c, cand, pos))
             if len(pend) >= group:
                 flush_group()
+        i = 0
+        pieces = {}
+        while i < len(f_cand):
+            u, f = f_cand[i]
+            i += 1
+            raw = f.result()
+            submit_search()
+            if u["npieces"] == 1:
+                take(u["chrom"], raw)
+            else:
+                pieces[(u["chrom"], u["piece"])] = raw
+        if split_chroms:
+            # third host-side exchange (only when a chromosome was cut): the window ranges of a
+            # chromosome meet at its primary, in window order, before the cross-window pruning
+            gathered = {}
+            for part in comm.all_gather(pieces):
+                gathered.update(part)
+            for c in split_chroms:
+                if not mine(c):
+                    continue
+                k = max(u["npieces"] for u in units if u["chrom"] == c)
+                raw = np.concatenate([gathered[(c, p)] for p in range(k)])
+                take(c, raw[np.argsort(raw["q"], kind="stable")])   # (q, window, ...) order of one call
         flush_group()
         f_bg.result()
         clock.lap('search+prune')

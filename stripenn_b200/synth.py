@@ -177,6 +177,16 @@ def frame_pixels(nbins: int) -> int:
     return tot
 
 
+def frame_pixels_range(nbins: int, lo: int, hi: int) -> int:
+    """frame_pixels restricted to the windows [lo, hi)."""
+    tot = 0
+    for idx in range(lo, min(hi, math.ceil(nbins / 200))):
+        start = 0 if idx == 0 else idx * 200 - 100
+        end = min((idx + 1) * 200 + 99, nbins - 1)
+        tot += (end - start + 1) ** 2
+    return tot
+
+
 def make_stripe_table(cm: ContactMap, n: int, seed: int = DEFAULT_SEED,
                       chroms: Optional[Sequence[str]] = None) -> Dict[str, np.ndarray]:
     """Candidate table for ``score`` mode (config 5): chromosome ∝ size, anchor uniform,

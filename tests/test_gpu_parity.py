@@ -393,3 +393,19 @@ def test_host_threads_give_identical_tables(tiny2_cm):
     assert len(a_unf) > 0
     assert a_unf.reset_index(drop=True).equals(b_unf.reset_index(drop=True))
     assert a_fil.reset_index(drop=True).equals(b_fil.reset_index(drop=True))
+
+
+def test_window_ranges_of_one_chromosome_on_three_contexts(tiny_cm, golden_dir):
+    """plan_units cuts a single chromosome into window ranges (BASELINE configs 1 and 4 on several
+    GPUs); here three contexts on one GPU: tables identical to the single-context run and to the
+    reference's golden tables."""
+    g = np.load(os.path.join(golden_dir, "tiny_compute.npz"))
+    a_unf, a_fil = cp.run_stages(tiny_cm, norm="None", streams=1)
+    b_unf, b_fil = cp.run_stages(tiny_cm, norm="None", streams=3)
+    assert a_unf.reset_index(drop=True).equals(b_unf.reset_index(drop=True))
+    assert a_fil.reset_index(drop=True).equals(b_fil.reset_index(drop=True))
+    for k in ("pos1", "pos2", "pos3", "pos4"):
+        assert b_unf[k].astype(np.int64).tolist() == g["unf_" + k].tolist()
+    assert b_unf["maxpixel"].tolist() == g["unf_maxpixel"].tolist()
+    for k in ("Mean", "pvalue", "Stripiness"):
+        np.testing.assert_allclose(b_unf[k].to_numpy(dtype=float), g["unf_" + k], rtol=RTOL, equal_nan=True)

@@ -125,3 +125,51 @@ def test_pipeline_on_fake_device_matches_golden(tiny_cm, golden_dir):
     for k in ("Mean", "pvalue", "Stripiness"):
         np.testing.assert_allclose(np.array(unf[k], float), np.array(ounf[k], float), rtol=1e-12)
     assert list(fil["pos1"]) == list(ofil["pos1"])
+
+
+def test_plan_units_cuts_oversized_chromosomes():
+    # whole genomes: nothing to cut, same assignment idea as lpt_partition
+    names = ["a", "b", "c", "d"]
+    sizes = [50_000_000, 30_000_000, 30_000_000, 20_000_000]
+    units = cp.plan_units(names, sizes, 10000, 2)
+    assert all(u["npieces"] == 1 for u in units)
+    load = [sum(u["hi"] - u["lo"] for u in units if u["rank"] == r) for r in (0, 1)]
+    assert abs(load[0] - load[1]) <= 0.25 * sum(load)
+    # one chromosome, 8 ranks: 8 contiguous window ranges covering every window once
+    units = cp.plan_units(["16"], [98_207_768], 5000, 8)
+    assert len(units) == 8 and sorted(u["rank"] for u in units) == list(range(8))
+    spans = sorted((u["lo"], u["hi"]) for u in units)
+    assert spans[0][0] == 0 and spans[-1][1] == 99
+    assert all(spans[i][1] == spans[i + 1][0] for i in range(7))
+    assert cp.plan_units(["16"], [98_207_768], 5000, 1)[0]["npieces"] == 1
+    assert cp.plan_units(names, sizes, 10000, 2) == cp.plan_units(names, sizes, 10000, 2)
+
+
+def test_window_range_sharding_matches_reference(tiny_cm, golden_dir):
+    """One chromosome on three (virtual) ranks: its 12 windows are searched in three ranges and
+    merged by the primary; the maxpixel-0.97 candidate table must equal the reference's."""
+    g = np.load(os.path.join(golden_dir, "tiny_compute.npz"))
+    cm = tiny_cm
+    bal = cp.resolve_norm(cm, "None", "compute", False)
+    all_names, all_sizes, names, sizes = cp.compute_chromosomes(cm, ["all"])
+    assert sorted(u["npieces"] for u in cp.plan_units(all_names, all_sizes, cm.binsize, 3)) == [3, 3, 3]
+    searched = {}
+
+    def one(tc):
+        dev = FakeDevice(cm, bal)
+        real = dev.extract
+
+        def spy(cid, mp, *a, **k):
+            searched[tc.rank] = (k.get("frame_lo"), k.get("frame_hi")) if "frame_lo" in k else a[5:7]
+            return real(cid, mp, *a, **k)
+        dev.extract = spy
+        o = cp.make_object(cm, bal, dev, all_names, all_sizes, names, sizes, 10, 8, 2.0, 1, 3, 123456789, 0)
+        return cp.run_pipeline(o, cm, [0.97], names, 0.1, '0', False, tc, return_stages=True)
+    res = cp.run_threads(one, 3)
+    assert sorted(searched.values()) == [(0, 4), (4, 8), (8, 12)]
+    for unf, fil, st in res:                       # every rank returns the full tables
+        assert list(unf["pos1"]) == list(res[0][0]["pos1"])
+    t = res[0][2]["per_q"][0]                      # the primary holds the per-maxpixel stage table
+    for k in ("pos1", "pos2", "pos3", "pos4"):
+        assert t[k].astype(np.int64).tolist() == g["q2_" + k].tolist(), k
+    np.testing.assert_allclose(t["pvalue"].to_numpy(float), g["q2_pvalue"], rtol=1e-12)
