@@ -182,6 +182,22 @@ class ThreadComm:
         sh["barrier"].wait()
         return out
 
+    def once(self, fn):
+        """fn() evaluated by rank 0 only; every rank gets the same object (threads share memory,
+        and the GIL would serialise identical copies of the work anyway)."""
+        sh = self._sh
+        if self.rank == 0:
+            try:
+                sh["once"] = (fn(), None)
+            except BaseException as e:  # noqa: BLE001 - re-raised on every rank
+                sh["once"] = (None, e)
+        sh["barrier"].wait()
+        val, err = sh["once"]
+        sh["barrier"].wait()
+        if err is not None:
+            raise err
+        return val
+
 
 def run_threads(fn, world):
     """Run fn(comm) on `world` host threads (one ThreadComm each); returns the per-rank results
@@ -412,38 +428,46 @@ def run_pipeline(obj, cm, qs, chromnames, pvalue, mask, slow, comm=None, say=lam
         clock.lap('stripiness')
     finally:
         dq.close()
+    # ---- result tables.  Ranks exchange plain arrays (maxpixel index, chromosome index, bp
+    # coordinates, window sum, size, p-value, Stripiness); the DataFrames are built ONCE from the
+    # merged arrays (by one thread when the ranks are host threads of one process).
     final = [r for r in final if len(r[1])]
+    cidx = {c: i for i, c in enumerate(chromnames)}
     if final:
         allc = np.concatenate([r[1] for r in final])
-        alln = np.concatenate([np.full(len(r[1]), r[0], dtype=object) for r in final])
-        allp = np.concatenate([r[2] for r in final])
-        alls = np.concatenate([r[3] for r in final])
+        part = dict(q=allc["q"].astype(np.int64),
+                    ck=np.concatenate([np.full(len(r[1]), cidx[r[0]], dtype=np.int64) for r in final]),
+                    pos=np.stack([allc["pos1"], allc["pos2"], allc["pos3"], allc["pos4"]], axis=1),
+                    total=allc["total"].astype(np.float64), h=allc["h"].astype(np.int64),
+                    w=allc["w"].astype(np.int64), pvalue=np.concatenate([r[2] for r in final]),
+                    s=np.concatenate([r[3] for r in final]))
+    else:
+        part = None
+    parts = [p for p in (comm.all_gather(part) if comm.world > 1 else [part]) if p is not None]
+
+    def build():
+        if not parts:
+            empty = pd.DataFrame(columns=[k for k in gs.RESULT_COLUMNS if k not in
+                                          ('total', 'num', 'start', 'end', 'x', 'y', 'h', 'w', 'medpixel')] +
+                                 ['pvalue', 'Stripiness'])
+            return empty, empty[empty['pvalue'] < pvalue]
+        m = {k: np.concatenate([p[k] for p in parts]) for k in parts[0]}
         # reference row order: maxpixel-major, then chromosomes in -k order, then emission order
-        order = np.argsort(allc["q"], kind="stable")
-        allc, alln, allp, alls = allc[order], alln[order], allp[order], alls[order]
-        local = obj._candidate_frame(allc, alln, 0.0)
-        local['maxpixel'] = np.array(labels, dtype=object)[allc["q"]]
-        local['pvalue'] = allp
-        local = local.drop(columns=['total', 'num', 'start', 'end', 'x', 'y', 'h', 'w', 'medpixel'])
-        local.insert(local.shape[1], 'Stripiness', alls, True)
-    else:
-        local = pd.DataFrame(columns=[k for k in gs.RESULT_COLUMNS if k not in
-                                      ('total', 'num', 'start', 'end', 'x', 'y', 'h', 'w', 'medpixel')] +
-                             ['pvalue', 'Stripiness'])
-    if comm.world > 1:
-        parts = comm.all_gather(local)
-        merged = pd.concat([p for p in parts if len(p)]) if any(len(p) for p in parts) else local
-        if len(merged):
-            qk = merged['maxpixel'].map({l: i for i, l in enumerate(labels)}).to_numpy()
-            ck = merged['chr'].astype(str).map({c: i for i, c in enumerate(chromnames)}).to_numpy()
-            order = np.lexsort((np.arange(len(merged)), ck, qk))
-            merged = merged.iloc[order]
-        result_table = merged
-    else:
-        result_table = local
-    result_table = result_table.reset_index(drop=True)
-    res_filter = result_table[result_table['pvalue'] < pvalue]
-    res_filter = res_filter.sort_values(by=['Stripiness'], ascending=False)
+        # (rows of one chromosome come from one rank, already in emission order)
+        order = np.lexsort((np.arange(len(m["q"])), m["ck"], m["q"]))
+        m = {k: v[order] for k, v in m.items()}
+        chrs = np.array(list(chromnames), dtype=object)[m["ck"]]
+        pos = m["pos"]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            mean = m["total"] / m["h"] / m["w"]                     # getStripe.py:1097
+        table = pd.DataFrame({
+            'chr': chrs, 'pos1': pos[:, 0], 'pos2': pos[:, 1], 'chr2': chrs, 'pos3': pos[:, 2], 'pos4': pos[:, 3],
+            'length': pos[:, 3] - pos[:, 2] + 1, 'width': pos[:, 1] - pos[:, 0] + 1, 'Mean': mean,
+            'maxpixel': np.array(labels, dtype=object)[m["q"]], 'pvalue': m["pvalue"], 'Stripiness': m["s"]},
+            copy=False)
+        filt = table[table['pvalue'] < pvalue].sort_values(by=['Stripiness'], ascending=False)
+        return table, filt
+    result_table, res_filter = comm.once(build) if hasattr(comm, "once") else build()
     clock.lap('tables')
     obj.last_host_ms = clock.ms
     if return_stages:
