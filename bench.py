@@ -382,27 +382,20 @@ def native_arm(args):
 
     class ResidentMatrix(gs.DeviceMatrix):  # noqa: E306
         """DeviceMatrix whose chromosomes are built from pixel tables already in HBM."""
-        def ensure(self, chrom, band_width=None):
-            cid = self.chrom_id(chrom)
-            if cid in self.dev.loaded:
-                return cid
+        def _upload(self, chrom, cid, need, async_):
             px = self.cm.chroms[str(chrom)]
             b1, b2, ct = resident[str(chrom)]
             self.dev.load_chrom_device(cid, px.nbins, self.binsize, px.size_bp, px.nnz, b1.data_ptr(),
-                                       b2.data_ptr(), ct.data_ptr(), None, band_width or self.band_width)
-            return cid
+                                       b2.data_ptr(), ct.data_ptr(), None, need or self.band_width)
 
     class PinnedMatrix(gs.DeviceMatrix):
-        """DeviceMatrix fed from pinned host buffers (the H2D copies happen inside ensure)."""
-        def ensure(self, chrom, band_width=None):
-            cid = self.chrom_id(chrom)
-            if cid in self.dev.loaded:
-                return cid
+        """DeviceMatrix fed from pinned host buffers: the H2D copies happen inside the timed step
+        (asynchronously on the library's copy stream when the pipeline prefetches)."""
+        def _upload(self, chrom, cid, need, async_):
             px = self.cm.chroms[str(chrom)]
             b1, b2, ct = (t.numpy() for t in pinned[str(chrom)])
             self.dev.load_chrom(cid, px.nbins, self.binsize, px.size_bp, b1, b2, ct, None,
-                                band_width or self.band_width)
-            return cid
+                                need or self.band_width, async_=async_)
 
     qs = list(map(float, QS.split(",")))
 

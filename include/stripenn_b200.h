@@ -82,6 +82,15 @@ int snn_synchronize(snn_ctx* ctx);
 int snn_load_chrom(snn_ctx* ctx, int chrom_id, int64_t nbins, int64_t binsize,
                    int64_t chromsize_bp, int64_t nnz, const int32_t* bin1, const int32_t* bin2,
                    const int32_t* count, const double* weight, int band_width);
+/* Asynchronous snn_load_chrom: the pixel arrays are copied on the context's own copy stream and
+ * the call returns at once, so the upload of the next chromosomes overlaps the kernels of the
+ * first ones (the band is built on the compute stream the first time the chromosome is used).
+ * The caller must keep the four host arrays alive and unchanged until a later call that uses
+ * this chromosome has returned data, or until snn_synchronize / snn_unload_chrom; pinned host
+ * memory is what makes the copy truly asynchronous. */
+int snn_load_chrom_async(snn_ctx* ctx, int chrom_id, int64_t nbins, int64_t binsize,
+                         int64_t chromsize_bp, int64_t nnz, const int32_t* bin1, const int32_t* bin2,
+                         const int32_t* count, const double* weight, int band_width);
 int snn_unload_chrom(snn_ctx* ctx, int chrom_id);
 /* Same, but the four arrays are DEVICE pointers already resident in HBM (zero-copy: the
  * library keeps using them, the caller must keep them alive until snn_unload_chrom). */

@@ -53,6 +53,8 @@ SIGNATURES = {
     "snn_synchronize": (C.c_int, [_P]),
     "snn_load_chrom": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _P, _P,
                                  _P, _P, C.c_int]),
+    "snn_load_chrom_async": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _P, _P,
+                                       _P, _P, C.c_int]),
     "snn_load_chrom_device": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                         _P, _P, _P, _P, C.c_int]),
     "snn_unload_chrom": (C.c_int, [_P, C.c_int]),

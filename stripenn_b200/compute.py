@@ -326,23 +326,35 @@ def run_pipeline(obj, cm, qs, chromnames, pvalue, mask, slow, comm=None, say=lam
     try:
         say('1. Maximum pixel value calculation ...')
         quant = obj.getQuantile_slow if slow else obj.getQuantile_original
-        f_mp_all = dq.submit(quant, cm, quant_sel, qs)
-        say('2. Expected value calculation ...')
-        f_ev = {c: dq.submit(obj.expected_values, c) for c in my_sel}
-        say('3. Background distribution estimation ...')
         names2 = obj.background_chromosomes()
-        f_avail = dq.submit(obj.available_counts, [c for c in names2 if mine(c)])
-        say('4. Finding candidate stripes from each chromosome ...')
         todo = list(my_units)
-        f_cand = []
+        f_cand, f_mp = [], {}
 
         def submit_search():
             if todo:
                 u = todo.pop(0)
                 rng = None if u["npieces"] == 1 else (u["lo"], u["hi"])
                 f_cand.append((u, dq.submit(lambda u=u, rng=rng: obj.search_candidates(
-                    u["chrom"], f_mp_all.result()[u["chrom"]], rng))))
-        for _ in range(ahead):
+                    u["chrom"], f_mp[u["chrom"]].result()[u["chrom"]], rng))))
+        # Every upload starts now, on the copy stream.  The maxpixel values of the chromosome that is
+        # searched first come from a call of their own and its search is queued right behind them:
+        # those kernels run while the other chromosomes are still arriving.
+        first = [my_units[0]["chrom"]] if my_units else quant_sel[:1]
+        rest = [c for c in quant_sel if c not in first]
+        dq.submit(obj.prefetch, list(dict.fromkeys(first + rest + [c for c in names2 if mine(c)])))
+        if first:
+            f_mp[first[0]] = dq.submit(quant, cm, first, qs)
+        say('4. Finding candidate stripes from each chromosome ...')
+        submit_search()
+        if rest:
+            f = dq.submit(quant, cm, rest, qs)
+            for c in rest:
+                f_mp[c] = f
+        say('2. Expected value calculation ...')
+        f_ev = {c: dq.submit(obj.expected_values, c) for c in my_sel}
+        say('3. Background distribution estimation ...')
+        f_avail = dq.submit(obj.available_counts, [c for c in names2 if mine(c)])
+        for _ in range(ahead - 1):
             submit_search()
         avail = {}
         for part in comm.all_gather(f_avail.result()):
@@ -360,7 +372,7 @@ def run_pipeline(obj, cm, qs, chromnames, pvalue, mask, slow, comm=None, say=lam
         bg = (full[0], full[1], full[2], full[3])
         f_bg = dq.submit(obj._install_background, bg)
         clock.lap('background')
-        MP = dict(f_mp_all.result())
+        MP = {c: f_mp[c].result()[c] for c in quant_sel}
         EV = {c: f_ev[c].result() for c in my_sel}
         # ---- search -> prune -> p-values (grouped) -> prune by p-value -> stripiness
         kept, pend, f_pv = [], [], []      # kept: (chrom, records, positions)

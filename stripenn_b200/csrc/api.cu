@@ -32,6 +32,16 @@ SnnChrom* snn_find_chrom(snn_ctx* ctx, int chrom_id) {
     return it == ctx->chroms.end() ? nullptr : &it->second;
 }
 
+int snn_materialize(snn_ctx* ctx, SnnChrom* c) {
+    if (!c->pending) return SNN_OK;
+    SNN_CUDA(cudaStreamWaitEvent(ctx->stream, c->ready, 0));
+    cudaEventDestroy(c->ready);
+    c->ready = nullptr;
+    c->pending = false;
+    SNN_CUDA(cudaMallocAsync(&c->band, (size_t)c->nbins * c->bw * sizeof(double), ctx->stream));
+    return snn_band_build(ctx, c);
+}
+
 int snn_scratch(snn_ctx* ctx, size_t bytes, void** out) {
     if (bytes > ctx->scratch_bytes) {
         if (ctx->scratch) cudaFree(ctx->scratch);
@@ -126,6 +136,12 @@ int snn_create(int device, snn_ctx** out) {
         return snn_cuda_fail(nullptr, e, "cudaStreamCreate");
     }
     ctx->stream = ctx->own_stream;
+    if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        cudaStreamDestroy(ctx->own_stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+        delete ctx;
+        return snn_cuda_fail(nullptr, e, "cudaStreamCreate");
+    }
     {
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -145,6 +161,12 @@ int snn_create(int device, snn_ctx** out) {
 // release threshold lifted, so re-loading chromosomes re-uses HBM instead of paying a
 // synchronising cudaFree/cudaMalloc (~10 ms per 70 MB band) each time.
 static void free_chrom(snn_ctx* ctx, SnnChrom& c) {
+    if (c.ready) {   // copies of an asynchronous load may still be in flight
+        cudaStreamWaitEvent(ctx->stream, c.ready, 0);
+        cudaEventDestroy(c.ready);
+        c.ready = nullptr;
+        c.pending = false;
+    }
     if (c.own_coo) {
         if (c.bin1) cudaFreeAsync(c.bin1, ctx->stream);
         if (c.bin2) cudaFreeAsync(c.bin2, ctx->stream);
@@ -159,6 +181,7 @@ void snn_destroy(snn_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     drain_timers(ctx);
     for (auto& kv : ctx->chroms) free_chrom(ctx, kv.second);
     cudaStreamSynchronize(ctx->stream);
@@ -181,12 +204,13 @@ int snn_synchronize(snn_ctx* ctx) {
     if (!ctx) return snn_fail(nullptr, SNN_EINVAL, "ctx is NULL");
     SNN_CUDA(cudaSetDevice(ctx->device));
     SNN_CUDA(cudaStreamSynchronize(ctx->stream));
+    SNN_CUDA(cudaStreamSynchronize(ctx->copy_stream));
     return SNN_OK;
 }
 
 static int load_common(snn_ctx* ctx, int chrom_id, int64_t nbins, int64_t binsize, int64_t chromsize,
                        int64_t nnz, const int32_t* b1, const int32_t* b2, const int32_t* cnt,
-                       const double* w, int bw, bool device_ptrs) {
+                       const double* w, int bw, bool device_ptrs, bool async = false) {
     if (!ctx) return snn_fail(nullptr, SNN_EINVAL, "ctx is NULL");
     if (nbins <= 0 || binsize <= 0 || chromsize <= 0 || nnz < 0 || bw < 1)
         return snn_fail(ctx, SNN_EINVAL, "snn_load_chrom: bad sizes (nbins=%lld binsize=%lld nnz=%lld bw=%d)",
@@ -215,15 +239,29 @@ static int load_common(snn_ctx* ctx, int chrom_id, int64_t nbins, int64_t binsiz
         SNN_CUDA(cudaMallocAsync(&c.bin1, nb, ctx->stream));
         SNN_CUDA(cudaMallocAsync(&c.bin2, nb, ctx->stream));
         SNN_CUDA(cudaMallocAsync(&c.count, nb, ctx->stream));
-        if (nnz > 0) {
-            SNN_CUDA(cudaMemcpyAsync(c.bin1, b1, nb, cudaMemcpyHostToDevice, ctx->stream));
-            SNN_CUDA(cudaMemcpyAsync(c.bin2, b2, nb, cudaMemcpyHostToDevice, ctx->stream));
-            SNN_CUDA(cudaMemcpyAsync(c.count, cnt, nb, cudaMemcpyHostToDevice, ctx->stream));
+        if (w) SNN_CUDA(cudaMallocAsync(&c.weight, (size_t)nbins * sizeof(double), ctx->stream));
+        cudaStream_t cs = ctx->stream;
+        if (async) {
+            // the allocations are ordered on the compute stream: the copy stream starts after them
+            cudaEvent_t alloc_done;
+            SNN_CUDA(cudaEventCreateWithFlags(&alloc_done, cudaEventDisableTiming));
+            SNN_CUDA(cudaEventRecord(alloc_done, ctx->stream));
+            SNN_CUDA(cudaStreamWaitEvent(ctx->copy_stream, alloc_done, 0));
+            cudaEventDestroy(alloc_done);
+            cs = ctx->copy_stream;
         }
-        if (w) {
-            SNN_CUDA(cudaMallocAsync(&c.weight, (size_t)nbins * sizeof(double), ctx->stream));
-            SNN_CUDA(cudaMemcpyAsync(c.weight, w, (size_t)nbins * sizeof(double), cudaMemcpyHostToDevice,
-                                     ctx->stream));
+        if (nnz > 0) {
+            SNN_CUDA(cudaMemcpyAsync(c.bin1, b1, nb, cudaMemcpyHostToDevice, cs));
+            SNN_CUDA(cudaMemcpyAsync(c.bin2, b2, nb, cudaMemcpyHostToDevice, cs));
+            SNN_CUDA(cudaMemcpyAsync(c.count, cnt, nb, cudaMemcpyHostToDevice, cs));
+        }
+        if (w) SNN_CUDA(cudaMemcpyAsync(c.weight, w, (size_t)nbins * sizeof(double), cudaMemcpyHostToDevice, cs));
+        if (async) {
+            SNN_CUDA(cudaEventCreateWithFlags(&c.ready, cudaEventDisableTiming));
+            SNN_CUDA(cudaEventRecord(c.ready, ctx->copy_stream));
+            c.pending = true;
+            ctx->chroms[chrom_id] = c;      // the band is built on first use (snn_materialize)
+            return SNN_OK;
         }
     }
     SNN_CUDA(cudaMallocAsync(&c.band, (size_t)nbins * c.bw * sizeof(double), ctx->stream));
@@ -241,6 +279,12 @@ int snn_load_chrom(snn_ctx* ctx, int chrom_id, int64_t nbins, int64_t binsize, i
                    int64_t nnz, const int32_t* b1, const int32_t* b2, const int32_t* cnt, const double* w,
                    int bw) {
     return load_common(ctx, chrom_id, nbins, binsize, chromsize, nnz, b1, b2, cnt, w, bw, false);
+}
+
+int snn_load_chrom_async(snn_ctx* ctx, int chrom_id, int64_t nbins, int64_t binsize, int64_t chromsize,
+                         int64_t nnz, const int32_t* b1, const int32_t* b2, const int32_t* cnt, const double* w,
+                         int bw) {
+    return load_common(ctx, chrom_id, nbins, binsize, chromsize, nnz, b1, b2, cnt, w, bw, false, true);
 }
 
 int snn_load_chrom_device(snn_ctx* ctx, int chrom_id, int64_t nbins, int64_t binsize, int64_t chromsize,
@@ -263,7 +307,11 @@ int snn_unload_chrom(snn_ctx* ctx, int chrom_id) {
     if (!ctx) return snn_fail(nullptr, SNN_EINVAL, "ctx is NULL");                       \
     SnnChrom* name = snn_find_chrom(ctx, chrom_id);                                      \
     if (!name) return snn_fail(ctx, SNN_ESTATE, "chromosome %d is not loaded", chrom_id); \
-    SNN_CUDA(cudaSetDevice(ctx->device));
+    SNN_CUDA(cudaSetDevice(ctx->device));                                                 \
+    if (name->pending) {                                                                  \
+        int rc__ = snn_materialize(ctx, name);                                            \
+        if (rc__) return rc__;                                                            \
+    }
 
 int snn_quantiles(snn_ctx* ctx, int chrom_id, int nq, const double* q, double* out) {
     GET_CHROM(c);
@@ -285,6 +333,7 @@ int snn_quantiles_multi(snn_ctx* ctx, int nchrom, const int32_t* chrom_ids, int 
     for (int k = 0; k < nchrom; ++k) {
         SnnChrom* c = snn_find_chrom(ctx, chrom_ids[k]);
         if (!c) return snn_fail(ctx, SNN_ESTATE, "chromosome %d is not loaded", chrom_ids[k]);
+        if (int rc = snn_materialize(ctx, c)) return rc;
         cs.push_back(c);
     }
     return snn_quantiles_multi_impl(ctx, cs, nq, q, out);
@@ -302,6 +351,7 @@ int snn_quantiles_select(snn_ctx* ctx, int nsrc, const int32_t* chrom_ids, const
     for (int k = 0; k < nsrc; ++k) {
         SnnChrom* c = snn_find_chrom(ctx, chrom_ids[k]);
         if (!c) return snn_fail(ctx, SNN_ESTATE, "chromosome %d is not loaded", chrom_ids[k]);
+        if (int rc = snn_materialize(ctx, c)) return rc;
         if (job[k] < 0 || job[k] >= njob) return snn_fail(ctx, SNN_EINVAL, "snn_quantiles_select: job out of range");
         if (sel[k * 5 + 1] < 1) return snn_fail(ctx, SNN_EINVAL, "snn_quantiles_select: block height must be >= 1");
         src[k].c = c;
@@ -401,6 +451,7 @@ int snn_score_multi(snn_ctx* ctx, int nchrom, const int32_t* chrom_ids, const do
     for (int k = 0; k < nchrom; ++k) {
         SnnChrom* c = snn_find_chrom(ctx, chrom_ids[k]);
         if (!c) return snn_fail(ctx, SNN_ESTATE, "chromosome %d is not loaded", chrom_ids[k]);
+        if (int rc = snn_materialize(ctx, c)) return rc;
         slots[k].c = c;
         slots[k].expected = expected ? expected + (size_t)k * SNN_NDIST : nullptr;
     }

@@ -114,6 +114,8 @@ extern "C" int snn_fetch(snn_ctx* ctx, int chrom_id, int64_t i0, int64_t i1, int
     if (!ctx) return snn_fail(nullptr, SNN_EINVAL, "ctx is NULL");
     SnnChrom* c = snn_find_chrom(ctx, chrom_id);
     if (!c) return snn_fail(ctx, SNN_ESTATE, "chromosome %d is not loaded", chrom_id);
+    SNN_CUDA(cudaSetDevice(ctx->device));
+    if (int rc = snn_materialize(ctx, c)) return rc;
     if (i0 < 0 || j0 < 0 || i1 > c->nbins || j1 > c->nbins || i1 < i0 || j1 < j0 || !out)
         return snn_fail(ctx, SNN_EINVAL, "snn_fetch: bad window");
     int64_t far = (j1 - 1 - i0) > (i1 - 1 - j0) ? (j1 - 1 - i0) : (i1 - 1 - j0);

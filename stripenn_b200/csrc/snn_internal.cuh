@@ -43,6 +43,10 @@ struct SnnChrom {
     double* weight = nullptr;  // device or null
     double* band = nullptr;    // device, nbins * bw
     int64_t* rowptr = nullptr; // device, nbins + 1: CSR row pointers into the (bin1, bin2)-sorted pixels
+    // snn_load_chrom_async: the pixel arrays are still travelling on the copy stream; `ready` fires
+    // when they have landed and the band is built on first use (snn_materialize)
+    bool pending = false;
+    cudaEvent_t ready = nullptr;
 };
 
 // Read-only view of one chromosome's matrix for kernels that may touch ANY pixel: the band
@@ -83,6 +87,7 @@ struct snn_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // H2D copies of snn_load_chrom_async
     std::map<int, SnnChrom> chroms;
     mutable std::string err;
     // background tables, sorted per (table, distance): 4 * 400 rows of `bg_ncol` doubles,
@@ -107,6 +112,8 @@ struct snn_ctx {
 int snn_fail(const snn_ctx* ctx, int code, const char* fmt, ...);
 int snn_cuda_fail(const snn_ctx* ctx, cudaError_t e, const char* what);
 SnnChrom* snn_find_chrom(snn_ctx* ctx, int chrom_id);
+// Finish an asynchronous load: make the compute stream wait for the copy, build the band.
+int snn_materialize(snn_ctx* ctx, SnnChrom* c);
 int snn_scratch(snn_ctx* ctx, size_t bytes, void** out);
 
 #define SNN_CUDA(call)                                                   \

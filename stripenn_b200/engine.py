@@ -46,6 +46,7 @@ class Device:
         self.h = h
         self.device = int(device)
         self.loaded: Dict[int, dict] = {}
+        self._keep: Dict[int, tuple] = {}   # host arrays of asynchronous uploads still in flight
         self.h2d_bytes = 0   # host<->device payload bytes moved by this object's calls
         self.d2h_bytes = 0
         if timing:
@@ -54,8 +55,9 @@ class Device:
     # ------------------------------------------------------------------ life cycle
     def close(self):
         if getattr(self, "h", None) is not None and self.h:
-            self.lib.snn_destroy(self.h)
+            self.lib.snn_destroy(self.h)    # synchronises both streams
             self.h = None
+            self._keep = {}
 
     def __del__(self):
         try:
@@ -78,7 +80,9 @@ class Device:
 
     # ------------------------------------------------------------------ a1
     def load_chrom(self, chrom_id: int, nbins: int, binsize: int, chromsize: int, bin1, bin2, count,
-                   weight=None, band_width: Optional[int] = None):
+                   weight=None, band_width: Optional[int] = None, async_: bool = False):
+        """async_=True: snn_load_chrom_async — the copies run on the context's copy stream while
+        this call returns; the arrays are kept alive here until the chromosome is unloaded."""
         bw = int(band_width or default_band_width(binsize))
         b1 = np.ascontiguousarray(bin1, dtype=np.int32)
         b2 = np.ascontiguousarray(bin2, dtype=np.int32)
@@ -86,8 +90,11 @@ class Device:
         w = None if weight is None else np.ascontiguousarray(weight, dtype=np.float64)
         if w is not None and w.shape[0] != nbins:
             raise ValueError("weight vector has %d entries, chromosome has %d bins" % (w.shape[0], nbins))
-        check(self.lib.snn_load_chrom(self.h, int(chrom_id), int(nbins), int(binsize), int(chromsize),
-                                      int(b1.shape[0]), ptr(b1), ptr(b2), ptr(ct), ptr(w), bw), self.h)
+        fn = self.lib.snn_load_chrom_async if async_ else self.lib.snn_load_chrom
+        check(fn(self.h, int(chrom_id), int(nbins), int(binsize), int(chromsize),
+                 int(b1.shape[0]), ptr(b1), ptr(b2), ptr(ct), ptr(w), bw), self.h)
+        if async_:
+            self._keep[int(chrom_id)] = (b1, b2, ct, w)
         self.h2d_bytes += b1.nbytes * 3 + (0 if w is None else w.nbytes)
         self.loaded[int(chrom_id)] = dict(nbins=int(nbins), binsize=int(binsize),
                                           chromsize=int(chromsize), bw=min(bw, int(nbins)),
@@ -107,6 +114,9 @@ class Device:
     def unload_chrom(self, chrom_id: int):
         check(self.lib.snn_unload_chrom(self.h, int(chrom_id)), self.h)
         self.loaded.pop(int(chrom_id), None)
+        if int(chrom_id) in self._keep:
+            self.synchronize()               # the copy may still be reading the host arrays
+            self._keep.pop(int(chrom_id), None)
 
     def fetch(self, chrom_id, i0, i1, j0, j1):
         out = np.empty((int(i1 - i0), int(j1 - j0)), dtype=np.float64)

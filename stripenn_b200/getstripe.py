@@ -51,12 +51,23 @@ class DeviceMatrix:
         have = self.dev.loaded.get(cid)
         if have is not None and (need is None or have["bw"] >= min(need, have["nbins"])):
             return cid
+        self._upload(chrom, cid, need, False)
+        return cid
+
+    def prefetch(self, chroms) -> None:
+        """Start the uploads of several chromosomes (snn_load_chrom_async): the copies overlap the
+        kernels of whatever is used first; a chromosome's band is built when it is first used."""
+        for chrom in chroms:
+            cid = self.chrom_id(chrom)
+            if cid not in self.dev.loaded:
+                self._upload(chrom, cid, self.band_width, True)
+
+    def _upload(self, chrom, cid, need, async_):
         if str(chrom) not in self.cm.chroms:
             raise KeyError("chromosome %r has no pixels in the contact map" % chrom)
         c = self.cm.chroms[str(chrom)]
         w = self.cm.weight_vector(str(chrom), self.balance)
-        self.dev.load_chrom(cid, c.nbins, self.binsize, c.size_bp, c.bin1, c.bin2, c.count, w, need)
-        return cid
+        self.dev.load_chrom(cid, c.nbins, self.binsize, c.size_bp, c.bin1, c.bin2, c.count, w, need, async_=async_)
 
 
 def _bins_of(start: int, end: int, size: int, r: int):
@@ -88,6 +99,13 @@ class getStripe:
         self.chromnames2sizes = {self.all_chromnames[i]: int(self.all_chromsizes[i])
                                  for i in range(len(self.all_chromnames))}
         self._bg_installed = None
+
+    def prefetch(self, chroms):
+        """Begin uploading the chromosomes the following stages will touch (no-op for matrix
+        objects without asynchronous uploads)."""
+        fn = getattr(self.unbalLib, "prefetch", None)
+        if fn is not None:
+            fn(list(chroms))
 
     # ------------------------------------------------------------------ a2
     def getQuantile_original(self, coolinfo, ChrList, quantile):

@@ -33,7 +33,7 @@ class FakeDevice:
     def _name(self, cid):
         return self.cm.chromnames[cid]
 
-    def load_chrom(self, cid, nbins, binsize, chromsize, b1, b2, cnt, w=None, band_width=None):
+    def load_chrom(self, cid, nbins, binsize, chromsize, b1, b2, cnt, w=None, band_width=None, async_=False):
         self.loaded[cid] = dict(nbins=nbins, binsize=binsize, chromsize=chromsize, bw=band_width or 10 ** 9,
                                 nnz=len(b1))
 

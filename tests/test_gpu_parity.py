@@ -409,3 +409,53 @@ def test_window_ranges_of_one_chromosome_on_three_contexts(tiny_cm, golden_dir):
     assert b_unf["maxpixel"].tolist() == g["unf_maxpixel"].tolist()
     for k in ("Mean", "pvalue", "Stripiness"):
         np.testing.assert_allclose(b_unf[k].to_numpy(dtype=float), g["unf_" + k], rtol=RTOL, equal_nan=True)
+
+
+@pytest.mark.parametrize("cfg,norm", [("tiny2", "KR"), ("tiny10k", "None")])
+def test_stripes_at_chromosome_ends_match_oracle(dev, cfg, norm):
+    """flanks clamped to bp 1 / the chromosome length, bin 1 / Nbins-1 in
+    scoringstripes, stripes touching the first and last bins — each stripe scored by the oracle
+    on its own; where the oracle (like the reference) raises, the CUDA path answers NaN."""
+    cm = synth.make_config(cfg)
+    bal = cp.resolve_norm(cm, norm, "compute", False)
+    names = [c for c in cm.chromnames if c in cm.chroms]
+    r = cm.binsize
+    rows, chrs = [], []
+    for c in names:
+        nb, size = cm.nbins(c), cm.chroms[c].size_bp
+        for a, w, hh in ((0, 3, 30), (1, 5, 70), (2, 8, 150), (3, 2, 12), (nb - 40, 4, 39), (nb - 200, 6, 199),
+                         (nb - 13, 3, 12), (nb - 31, 9, 30), (nb - 120, 5, 119)):
+            p1, p2 = a * r + 1, min((a + w) * r, size)
+            rows.append((p1, p2, p1, min((a + hh) * r, size)))               # down
+            if a + w - hh >= 0:
+                rows.append((p1, p2, (a + w - hh) * r + 1, p2))              # up
+            chrs += [c] * (len(rows) - len(chrs))
+    pos = np.array(rows, dtype=np.int64)
+    obj, mat, names_, all_names, all_sizes = _obj(cm, norm, dev)
+    bg = obj.nulldist()
+    EV = obj.mpmean()
+    df = pd.DataFrame({"chr": chrs, "pos1": pos[:, 0], "pos2": pos[:, 1], "pos3": pos[:, 2], "pos4": pos[:, 3]})
+    got = dict(pvalue=np.array(obj.pvalue(*bg, df), float))
+    got["stripiness"], got["oe_mean"], got["oe_total"] = (np.array(v, float) for v in obj.scoringstripes(df, EV))
+    got["o_mean"], got["o_sum"] = (np.array(v, float) for v in obj.getMean(df))
+    bgo = bgm.null_distribution(mat, all_names, all_sizes, 123456789)
+    EVo = bgm.expected_by_distance(mat, names)
+    want = {k: np.full(len(pos), np.nan) for k in got}
+    from snn_oracle import scoring as osc
+    raised = 0
+    for i in range(len(pos)):
+        one = {"chr": [chrs[i]], "pos1": [int(pos[i, 0])], "pos2": [int(pos[i, 1])], "pos3": [int(pos[i, 2])],
+               "pos4": [int(pos[i, 3])]}
+        for keys, fn in ((("pvalue",), lambda: (osc.pvalues(mat, bgo, one),)),
+                         (("stripiness", "oe_mean", "oe_total"), lambda: osc.stripiness(mat, one, EVo)),
+                         (("o_mean", "o_sum"), lambda: osc.observed_mean(mat, one))):
+            try:
+                vals = fn()
+            except (ValueError, IndexError):
+                raised += 1
+                continue
+            for k, v in zip(keys, vals):
+                want[k][i] = float(v[0])
+    assert np.isfinite(want["pvalue"]).sum() > len(pos) // 2
+    for k in got:
+        np.testing.assert_allclose(got[k], want[k], rtol=RTOL, atol=0, equal_nan=True, err_msg=k)
