@@ -228,6 +228,33 @@ __global__ void __launch_bounds__(SCORE_THREADS) k_score(MatView m, const int64_
     const int64_t lC0 = lmb, lC1 = xsi;                   // left:   "chr:lm*r - xsi*r"
     const int64_t rC0 = xei, rC1 = rmb;                   // right:  "chr:xei*r - rm*r"
     const int wc = (int)(cC1 - cC0), wl = (int)(lC1 - lC0), wr = (int)(rC1 - rC0);
+    // ---- getMean (getStripe.py:501-534): nanmean / nansum of fetch(rows pos3..pos4, cols pos1..pos2).
+    // A function of its own in the reference: it does not depend on the flank geometry below
+    // (a stripe in the first bins has no valid left flank, but it has a mean).
+    {
+        double tot_obs = 0.0;
+        int n_obs = 0;
+        for (int j = threadIdx.x; j < h; j += SCORE_THREADS) {
+            for (int c = 0; c < wc; ++c) {
+                const double obs = W.at(j, cC0 + c);
+                if (obs == obs) { tot_obs += obs; ++n_obs; }
+            }
+        }
+        for (int off = 16; off > 0; off >>= 1) {
+            tot_obs += __shfl_xor_sync(0xffffffffu, tot_obs, off);
+            n_obs += __shfl_xor_sync(0xffffffffu, n_obs, off);
+        }
+        if (lane == 0) { red[4 + warp] = tot_obs; redi[warp] = n_obs; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double b = 0.0;
+            int n = 0;
+            for (int w = 0; w < nwarp; ++w) { b += red[4 + w]; n += redi[w]; }
+            o[4] = n ? b / (double)n : qnan();
+            o[5] = b;
+        }
+        __syncthreads();
+    }
     // shapes must agree with expecMatrix (else numpy raises in the reference) and the regions
     // must be valid for cooler (end >= start)
     if (wc != (int)(xei - xsi) || h != (int)(yei - ysi) || wc <= 0 || wl < 0 || wr < 0 ||
@@ -340,33 +367,15 @@ __global__ void __launch_bounds__(SCORE_THREADS) k_score(MatView m, const int64_
         rm[k] = lr ? sr / (double)lr : qnan();
         tot_oe += sc;
     }
-    // getMean: nanmean / nansum of the observed centre window (all rows, all columns)
-    double tot_obs = 0.0;
-    int n_obs = 0;
-    for (int j = threadIdx.x; j < h; j += SCORE_THREADS) {
-        for (int c = 0; c < wc; ++c) {
-            const double obs = W.at(j, cC0 + c);
-            if (obs == obs) { tot_obs += obs; ++n_obs; }
-        }
-    }
-    for (int off = 16; off > 0; off >>= 1) {
-        tot_oe += __shfl_xor_sync(0xffffffffu, tot_oe, off);
-        tot_obs += __shfl_xor_sync(0xffffffffu, tot_obs, off);
-        n_obs += __shfl_xor_sync(0xffffffffu, n_obs, off);
-    }
-    if (lane == 0) { red[warp] = tot_oe; red[4 + warp] = tot_obs; redi[warp] = n_obs; }
+    for (int off = 16; off > 0; off >>= 1) tot_oe += __shfl_xor_sync(0xffffffffu, tot_oe, off);
+    if (lane == 0) red[warp] = tot_oe;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        double a = 0.0, b = 0.0;
-        int n = 0;
-        for (int w = 0; w < nwarp; ++w) { a += red[w]; b += red[4 + w]; n += redi[w]; }
+    if (threadIdx.x == 0 && !mask_bad) {
+        double a = 0.0;
+        for (int w = 0; w < nwarp; ++w) a += red[w];
         // centerMean = mean(center[rows_rep]) = sum / (h' * w') ; centerTotal = w' * sum  (quirk :747)
-        if (!mask_bad) {
-            o[2] = (hk > 0 && lc > 0) ? a / ((double)hk * (double)lc) : qnan();
-            o[3] = (double)lc * a;
-        }
-        o[4] = n ? b / (double)n : qnan();
-        o[5] = b;
+        o[2] = (hk > 0 && lc > 0) ? a / ((double)hk * (double)lc) : qnan();
+        o[3] = (double)lc * a;
     }
     __syncthreads();
     // ---- pass 3: Sobel-like sums (stats.elementwise_product_sum) and the score

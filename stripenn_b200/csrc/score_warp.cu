@@ -335,6 +335,13 @@ __global__ void __launch_bounds__(SW_WARPS * 32, SW_MINB) k_score_warp(const Chr
                     sr += snn_nan0(v * __ldg(rex + dd));
                 }
                 if (act) { scA[j] = sc; slA[j] = sl; srA[j] = sr; }
+            } else if (want_s && wc > 0) {
+                // getMean alone (getStripe.py:501-534): it needs no valid flank geometry
+                #pragma unroll 1
+                for (int c = 0; c < wc; ++c) {
+                    const double v = wrow[cC0 + c];
+                    if (act && (v == v)) { tot_obs += v; ++n_obs; }
+                }
             }
         }
         __syncwarp();
@@ -415,12 +422,8 @@ __global__ void __launch_bounds__(SW_WARPS * 32, SW_MINB) k_score_warp(const Chr
                     srA[k] = lr ? sr / (double)lr : w_qnan();
                 }
                 tot_oe = warp_sum(tot_oe);
-                tot_obs = warp_sum(tot_obs);
-                n_obs = warp_sum(n_obs);
                 res2 = (hk > 0 && lc > 0) ? tot_oe / ((double)hk * (double)lc) : w_qnan();
                 res3 = (double)lc * tot_oe;           // centerTotal quirk (getStripe.py:747)
-                res4 = n_obs ? tot_obs / (double)n_obs : w_qnan();
-                res5 = tot_obs;
                 __syncwarp();
                 // Sobel-like sums (stats.elementwise_product_sum) and the score
                 double acc = 0.0;
@@ -457,6 +460,12 @@ __global__ void __launch_bounds__(SW_WARPS * 32, SW_MINB) k_score_warp(const Chr
                 const double med = nm ? warp_median_any(win, pv, nm, lane) : w_qnan();
                 res1 = med * avgdiff;
             }
+        }
+        if (want_s) {      // getMean: independent of the stripiness shape checks
+            tot_obs = warp_sum(tot_obs);
+            n_obs = warp_sum(n_obs);
+            res4 = n_obs ? tot_obs / (double)n_obs : w_qnan();
+            res5 = tot_obs;
         }
         if (lane < 6) {
             const double v = lane == 0 ? res0 : lane == 1 ? res1 : lane == 2 ? res2 : lane == 3 ? res3

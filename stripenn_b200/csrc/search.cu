@@ -411,7 +411,6 @@ __global__ void __launch_bounds__(NTHR) k_search(const uint32_t* __restrict__ lo
             int prev = -1, prevlen = 0;
             bool open_ = false;
             bool have_ln = false;
-            double tot = 0.0;   // running description of the open group: we keep the lists
             int gcol[SNN_SMAX];
             int glen[SNN_SMAX];
             int gn = 0;
@@ -435,7 +434,6 @@ __global__ void __launch_bounds__(NTHR) k_search(const uint32_t* __restrict__ lo
                 double rv = rint(acc);
                 X[nx++] = (int)rv;
             };
-            (void)tot;
             for (int wq = 0; wq < SNN_WPR; ++wq) {      // columns with >= 3 ones, ascending
                 uint32_t okm = colOK[wq];
                 while (okm) {

@@ -10,6 +10,7 @@ bookkeeping and file I/O.
 from __future__ import annotations
 
 import math
+import os
 import random
 from typing import Dict, List, Optional, Sequence
 
@@ -104,7 +105,7 @@ class getStripe:
         """Begin uploading the chromosomes the following stages will touch (no-op for matrix
         objects without asynchronous uploads)."""
         fn = getattr(self.unbalLib, "prefetch", None)
-        if fn is not None:
+        if fn is not None and not os.environ.get("SNN_NO_PREFETCH"):   # A/B switch: uploads at first use
             fn(list(chroms))
 
     # ------------------------------------------------------------------ a2
