@@ -102,6 +102,15 @@ int snn_load_chrom_device(snn_ctx* ctx, int chrom_id, int64_t nbins, int64_t bin
 int snn_fetch(snn_ctx* ctx, int chrom_id, int64_t i0, int64_t i1, int64_t j0, int64_t j1,
               double* out);
 
+/* seeimage (src/stripenn/seeimage.py:77-90): saturated heat map of the square
+ * window of bins [i0,i1): blue = 255*(M - A)/M, negatives -> 0, img = (1, blue/255, blue/255)
+ * clipped to [0,1].  chan (may be NULL) receives the green/blue channel as float64, row-major
+ * n x n, NaN kept; rgb (may be NULL) the n x n x 3 uint8 image as matplotlib's imshow quantises
+ * it ((255*v) truncated, NaN -> 0).  Any window of the chromosome (far pixels read from the
+ * pixel table). */
+int snn_heatmap(snn_ctx* ctx, int chrom_id, int64_t i0, int64_t i1, double maxpixel_value,
+                double* chan, unsigned char* rgb);
+
 /* ---- a2: getStripe.getQuantile_original (getStripe.py:160-176):
  * np.quantile(mat[mat > 0], q) over the full symmetric matrix (off-diagonal pixels count
  * twice), numpy 'linear' interpolation reproduced bit-exactly. */

@@ -45,6 +45,12 @@ class _SizeArray(np.ndarray):
     def keys(self):
         return list(self._names)
 
+    def __getitem__(self, key):
+        # a pandas Series is also indexed by chromosome NAME (seeimage.py:63)
+        if isinstance(key, str):
+            return np.int64(np.asarray(self)[self._names.index(key)])
+        return super().__getitem__(key)
+
 
 class _Columns(list):
     pass

@@ -99,3 +99,30 @@ def score(cm, table, norm="None", seed=123456789, mask="0"):
     s, moe, toe = sc.stripiness(mat, table, EV, mask)
     return {"pvalue_added": pv, "Stripiness_added": s, "O_Mean_added": mean,
             "O_Sum_added": total, "O/E_Mean_added": moe, "O/E_Total_added": toe}
+
+
+def seeimage(cm, position, maxpixel="0.95,0.96,0.97,0.98,0.99", norm="KR", slow=False):
+    """seeimage.py:32-97 restated: -> [(file-name suffix "_<position>_<q>qt.png", green(=blue)
+    channel float64)] per maxpixel value; the red channel is 1.0 everywhere.  Norm resolution
+    :41-50 (no 'weight' -> True special case), chromosome filter :59-62 (> 500 kb, nothing else),
+    quantiles of the position's chromosome only :70-74, window = fetch(position, position) :75,
+    saturation :79-88 (same arithmetic as image.saturate)."""
+    import sys
+    from . import image as im
+    qs = list(map(float, maxpixel.split(",")))
+    bal = resolve_norm(cm, norm, mode="seeimage")
+    chrom = position.split(":")[0]
+    if chrom not in cm.chromnames:
+        sys.exit("Invalid chromosome name.")
+    if not np.any(np.asarray(cm.chromsizes) > 500000):
+        sys.exit("Exit: All chromosomes are shorter than 50kb.")
+    mat = OracleMatrix(cm, bal)
+    MP = pl.quantiles_slow(mat, [chrom], qs) if slow else pl.quantiles(mat, [chrom], qs)
+    if ":" in position:
+        s, e = position.rsplit(":", 1)[1].split("-")
+        start, end = int(s.replace(",", "")), int(e.replace(",", ""))
+    else:
+        start, end = 0, mat.chromsize(chrom)
+    A = mat.fetch_bp(chrom, start, end, start, end)
+    return [("_" + position + "_" + str(q) + "qt.png", im.saturate(A, MP[chrom][i]))
+            for i, q in enumerate(qs)]

@@ -59,6 +59,7 @@ SIGNATURES = {
                                         _P, _P, _P, _P, C.c_int]),
     "snn_unload_chrom": (C.c_int, [_P, C.c_int]),
     "snn_fetch": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _P]),
+    "snn_heatmap": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int64, C.c_double, _P, _P]),
     "snn_quantiles": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
     "snn_quantiles_multi": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, _P]),
     "snn_quantiles_select": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, _P, _P]),

@@ -1,5 +1,5 @@
 """Command line — same commands, flags and defaults as reference src/stripenn/cli.py:8-58
-(`stripenn compute`, `stripenn score`; `seeimage` is a plotting helper outside the hot path).
+(`stripenn compute`, `stripenn seeimage`, `stripenn score`).
 Additive flags: --gpu (device index) and --yes (answer the overwrite prompt)."""
 from __future__ import annotations
 
@@ -9,6 +9,7 @@ import typer
 
 from . import compute as _compute
 from . import score as _score
+from . import seeimage as _seeimage
 
 app = typer.Typer()
 
@@ -35,6 +36,22 @@ def execute(
     """Finds stripe coordinates from 3D genomic data"""
     _compute.compute(cool, out, norm, chrom, canny, minL, maxW, maxpixel, numcores, pvalue, mask, slow, bfilter,
                      seed, device_id=gpu, assume_yes=yes)
+
+
+@app.command('seeimage')
+def seeimag(
+    cool: str = typer.Option(..., "--cool", help="Path to cool file"),
+    position: str = typer.Option(..., "--position", '-p', help="Genomic position (e.g., chr1:135010000-136000000)"),
+    maxpixel: str = typer.Option('0.95,0.96,0.97,0.98,0.99', "--maxpixel", '-m', help="Quantile for the pixel saturation. (e.g., 0.95)"),
+    out: str = typer.Option('./heatmap.png', "--out", "-o", help="Path to output directory"),
+    norm: str = typer.Option('KR', "--norm", help="Normalization method. It should be one of the column name of Cooler.bin(). Check it with Cooler.bins().columns (e.g., KR, VC, VC_SQRT)"),
+    slow: bool = typer.Option(False, '-s', help='Use if system memory is low.'),
+    seed: int = typer.Option(123456789, "--seed", help="Seed used to initialize the PRNG."),
+    gpu: int = typer.Option(0, '--gpu', help="CUDA device index."),
+):
+    """ Draws heatmap image of given position and color saturation parameter (maxpixel)."""
+    _seeimage.seeimage(cool, position, maxpixel, norm, out, slow, seed, device_id=gpu)
+    return 0
 
 
 @app.command('score')

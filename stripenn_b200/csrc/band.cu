@@ -136,6 +136,66 @@ extern "C" int snn_fetch(snn_ctx* ctx, int chrom_id, int64_t i0, int64_t i1, int
     return SNN_OK;
 }
 
+// ---- seeimage: saturated heat map of a square window (seeimage.py:77-90) ------------------------
+// blue = 255*(M - A)/M, negatives -> 0; img = (1, blue/255, blue/255) clipped to [0, 1]
+// (same saturation as StripeSearch, getStripe.py:885-895).  `chan` gets the green/blue channel
+// as the reference's float64 (NaN pixels stay NaN), `rgb` the 8-bit image the way matplotlib's
+// imshow quantises a float RGB array ((255*v) truncated; NaN -> 0).  Pixels beyond the band
+// come from the CSR table (snn_mat_at), so any window of the chromosome can be drawn.
+__global__ void k_heatmap(MatView m, int64_t i0, int64_t n, double M, double* __restrict__ chan,
+                          unsigned char* __restrict__ rgb) {
+    const int64_t total = n * n;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = i0 + t / n, j = i0 + t % n;
+        const double a = snn_mat_at(m, i, j);
+        double blue = (255.0 * (M - a)) / M;
+        if (blue < 0.0) blue = 0.0;
+        double v = blue / 255.0;
+        if (v < 0.0) v = 0.0;           // np.clip keeps NaN (both comparisons are false)
+        if (v > 1.0) v = 1.0;
+        if (chan) chan[t] = v;
+        if (rgb) {
+            const unsigned char g = (v != v) ? (unsigned char)0 : (unsigned char)(int)(255.0 * v);
+            rgb[3 * t] = 255;
+            rgb[3 * t + 1] = g;
+            rgb[3 * t + 2] = g;
+        }
+    }
+}
+
+extern "C" int snn_heatmap(snn_ctx* ctx, int chrom_id, int64_t i0, int64_t i1, double maxpixel_value,
+                           double* chan, unsigned char* rgb) {
+    if (!ctx) return snn_fail(nullptr, SNN_EINVAL, "ctx is NULL");
+    SnnChrom* c = snn_find_chrom(ctx, chrom_id);
+    if (!c) return snn_fail(ctx, SNN_ESTATE, "chromosome %d is not loaded", chrom_id);
+    SNN_CUDA(cudaSetDevice(ctx->device));
+    if (int rc = snn_materialize(ctx, c)) return rc;
+    if (i0 < 0 || i1 > c->nbins || i1 < i0 || (!chan && !rgb))
+        return snn_fail(ctx, SNN_EINVAL, "snn_heatmap: bad window");
+    const int64_t n = i1 - i0, total = n * n;
+    if (total == 0) return SNN_OK;
+    double* dch = nullptr;
+    unsigned char* drgb = nullptr;
+    cudaError_t e = cudaSuccess;
+    if (chan) e = cudaMalloc(&dch, total * sizeof(double));
+    if (e == cudaSuccess && rgb) e = cudaMalloc(&drgb, total * 3);
+    if (e == cudaSuccess) {
+        int64_t blocks = (total + 255) / 256;
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        k_heatmap<<<(int)blocks, 256, 0, ctx->stream>>>(snn_view(c), i0, n, maxpixel_value, dch, drgb);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess && chan)
+        e = cudaMemcpyAsync(chan, dch, total * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && rgb) e = cudaMemcpyAsync(rgb, drgb, total * 3, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(dch);
+    cudaFree(drgb);
+    if (e != cudaSuccess) return snn_cuda_fail(ctx, e, "snn_heatmap");
+    return SNN_OK;
+}
+
 // ---- K-mp: expected value per diagonal -----------------------------------------------------
 // ex[d] = sum_i nan0(band[i][d]) / (N - d), d < 400.  Two deterministic stages: per row-chunk
 // partial column sums (coalesced along d), then one fixed-order reduction over chunks.

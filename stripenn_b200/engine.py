@@ -123,6 +123,16 @@ class Device:
         check(self.lib.snn_fetch(self.h, int(chrom_id), int(i0), int(i1), int(j0), int(j1), ptr(out)), self.h)
         return out
 
+    def heatmap(self, chrom_id, i0, i1, maxpixel_value, want_channel=True):
+        """seeimage's image (seeimage.py:77-90) of bins [i0,i1): (float64 green/blue channel or
+        None, uint8 RGB)."""
+        n = int(i1 - i0)
+        chan = np.empty((n, n), dtype=np.float64) if want_channel else None
+        rgb = np.empty((n, n, 3), dtype=np.uint8)
+        check(self.lib.snn_heatmap(self.h, int(chrom_id), int(i0), int(i1), float(maxpixel_value),
+                                   ptr(chan) if want_channel else None, ptr(rgb)), self.h)
+        return chan, rgb
+
     # ------------------------------------------------------------------ a2 / a3
     def quantiles(self, chrom_id, qs: Sequence[float]):
         q = np.ascontiguousarray(qs, dtype=np.float64)

@@ -5,7 +5,7 @@
 BASE=${BASE:-stripenn_b200/lib/libsnn_base.so}
 NEW=${NEW:-stripenn_b200/lib/libstripenn_b200.so}
 mkdir -p gpurun_out
-for rep in 1 2; do
+for rep in ${SCORE_REPS:-1 2}; do
   for v in BASE NEW; do
     lib=${!v}
     STRIPENN_B200_LIB=$PWD/$lib python tools/score_bench.py --config cfg2 --stripes 100000 --reps 5 --tag $v 2>/dev/null \
