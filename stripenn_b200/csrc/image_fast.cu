@@ -215,11 +215,56 @@ __global__ void __launch_bounds__(256) k_gauss_h8(const float* __restrict__ in_a
 // value is ever moved), each input is loaded and widened ONCE, and the loads of the next 2R+1
 // outputs are in flight while the current ones are computed.  What is left per output is the
 // 25 float64 operations of scipy's correlate1d plus ~8 others: the FP64 pipe is the bound.
+// ---- one output of scipy's correlate1d, fused form with an exactness check ------------------------
+// The reference accumulates  t = x_c w_R ;  t = t + (x_-k + x_+k) * w_(R-k)  (k = R..1)  in float64,
+// one rounding per multiply and per add, then stores float32.  The FP64 pipe is what bounds these
+// kernels (profiles/r01p: 81 %), so the common path uses 8 pair sums + 1 multiply + 8 FMAs (17
+// float64 instructions instead of 25).  With non-negative inputs (gray >= 0.299, zero padding,
+// positive weights: no cancellation) both forms are within 9u of the exact sum T relative to T
+// (u = 2^-53; standard gamma_9 bound: the first product passes 9 roundings in the literal form, 9
+// in the fused one), so they differ by < 18u T <= 36 ulps of t however t falls in its binade.  Two
+// float64 values round to different float32 only if a rounding TIE (dropped 29 mantissa bits =
+// 0x10000000) lies between them: when the fused t is farther than tieK = 64 ulps from every tie the
+// literal t rounds to the same float32; otherwise (2.4e-7 of the outputs) the literal form is
+// evaluated.  A negative input (sign bits are OR-ed into `sgn` by the callers, never seen in this
+// pipeline) voids the bound and forces the literal form (tieK = 2^28 matches every t).
+// SNN_GAUSS_TIE_K=268435456 forces the literal form everywhere (tests), 0 disables the check (A/B).
+#define GAUSS_TIE_ALWAYS 0x10000000u
+template <int R>
+__device__ __forceinline__ double gauss_fused(const double* x, const int u, const GaussParams& G) {
+    constexpr int W = 2 * R + 1;
+    double t = x[(u + 1 + R) % W] * G.w[R];
+#pragma unroll
+    for (int k = R; k >= 1; --k) t = __fma_rn(x[(u + 1 + R - k) % W] + x[(u + 1 + R + k) % W], G.w[R - k], t);
+    return t;
+}
+__device__ __forceinline__ bool gauss_near_tie(const double t, const unsigned tieK) {
+    const unsigned d = ((unsigned)__double2loint(t) & 0x1fffffffu) - 0x10000000u + tieK;
+    return d <= 2u * tieK;
+}
+// The literal form, out of line and straight from memory (cold: ~1 output in 4 million): p points
+// at the centre input, `stride` apart along the filter axis, inputs [lo, hi] (relative to the
+// centre) exist, the others are the zero padding of mode 'constant'.
+__device__ __forceinline__ float gauss_literal(const float* p, int stride, int lo, int hi, int R, const GaussParams& G) {
+    double t = (double)p[0] * G.w[R];
+#pragma unroll 1
+    for (int k = R; k >= 1; --k) {
+        const double a = (-k >= lo) ? (double)p[-k * stride] : 0.0;
+        const double b = (k <= hi) ? (double)p[k * stride] : 0.0;
+        t = t + (a + b) * G.w[R - k];
+    }
+    return (float)t;
+}
+
 #define GV_SEG 102   // outputs per thread along axis 0 (6 groups of 17 at the default radius)
+#ifndef GVM_MINB
+#define GVM_MINB 5   // min CTAs per SM asked of the compiler: 96 registers, no spill (6: 80 registers + a 48-byte spill; A/B in DESIGN.md)
+#endif
 
 template <int R>
-__global__ void __launch_bounds__(128) k_gauss_vm(const float* __restrict__ in_all, const FrameInfo* __restrict__ info,
-                                                  int passes_per_frame, GaussParams G, float* __restrict__ out_all) {
+__global__ void __launch_bounds__(128, GVM_MINB) k_gauss_vm(const float* __restrict__ in_all, const FrameInfo* __restrict__ info,
+                                                  int passes_per_frame, GaussParams G, unsigned tieK,
+                                                  float* __restrict__ out_all) {
     constexpr int W = 2 * R + 1;
     const int pass = blockIdx.z;
     const int S = info[pass / passes_per_frame].S;
@@ -231,10 +276,13 @@ __global__ void __launch_bounds__(128) k_gauss_vm(const float* __restrict__ in_a
     float* out = out_all + (int64_t)pass * SNN_SMAX * SNN_SMAX + j;
     double x[W];   // at output row i (slot u = (i - i0) % W): row i - R + k lives in slot (u + 1 + k) % W
     x[0] = 0.0;
+    int sgn = 0;   // OR of the input bit patterns: the sign bit says "a negative input was seen"
 #pragma unroll
     for (int k = 0; k < 2 * R; ++k) {
         const int r = i0 - R + k;
-        x[k + 1] = (r >= 0 && r < S) ? (double)in[r * SNN_SMAX] : 0.0;
+        const float v = (r >= 0 && r < S) ? in[r * SNN_SMAX] : 0.f;
+        sgn |= __float_as_int(v);
+        x[k + 1] = (double)v;
     }
     float nx[W];
 #pragma unroll
@@ -259,12 +307,25 @@ __global__ void __launch_bounds__(128) k_gauss_vm(const float* __restrict__ in_a
         }
         const int left = i1 - base;                 // outputs still wanted (tail group: stores predicated)
 #pragma unroll
+        for (int u = 0; u < W; ++u) sgn |= __float_as_int(cur[u]);
+        const unsigned kk = sgn < 0 ? GAUSS_TIE_ALWAYS : tieK;
+        unsigned redo = 0;                          // outputs of this group that sit next to a rounding tie
+#pragma unroll
         for (int u = 0; u < W; ++u) {
             x[u] = (double)cur[u];
-            double t = x[(u + 1 + R) % W] * G.w[R];
-#pragma unroll
-            for (int k = R; k >= 1; --k) t = t + (x[(u + 1 + R - k) % W] + x[(u + 1 + R + k) % W]) * G.w[R - k];
+            const double t = gauss_fused<R>(x, u, G);
+            redo |= gauss_near_tie(t, kk) ? (1u << u) : 0u;
             if (u < left) pout[u * SNN_SMAX] = (float)t;
+        }
+        // no branch inside the unrolled group (the 17 accumulation chains interleave freely); the
+        // rare near-tie outputs are overwritten afterwards, recomputed literally from memory
+        if (__builtin_expect(redo != 0u, 0)) {
+#pragma unroll 1
+            for (int u = 0; u < W; ++u)
+                if (((redo >> u) & 1u) && u < left) {
+                    const int i = base + u;
+                    pout[u * SNN_SMAX] = gauss_literal(in + (int64_t)i * SNN_SMAX, SNN_SMAX, -i, S - 1 - i, R, G);
+                }
         }
         pin += W * SNN_SMAX;
         pout += W * SNN_SMAX;
@@ -283,7 +344,8 @@ __global__ void __launch_bounds__(128) k_gauss_vm(const float* __restrict__ in_a
 template <int R>
 __global__ void __launch_bounds__(GH_WARPS * 32) k_gauss_hm(const float* __restrict__ in_all,
                                                             const FrameInfo* __restrict__ info, int passes_per_frame,
-                                                            GaussParams G, const float* __restrict__ bleed_all,
+                                                            GaussParams G, unsigned tieK,
+                                                            const float* __restrict__ bleed_all,
                                                             float* __restrict__ out_all) {
     constexpr int W = 2 * R + 1;
     constexpr int TC = 2 * W * GH_WARPS;          // tile columns
@@ -331,17 +393,35 @@ __global__ void __launch_bounds__(GH_WARPS * 32) k_gauss_hm(const float* __restr
         float* pout = tout + lane * POUT + warp * 2 * W;
         double x[W];
         x[0] = 0.0;
+        int sgn = 0;
 #pragma unroll
-        for (int k = 0; k < 2 * R; ++k) x[k + 1] = (double)pin[k];
+        for (int k = 0; k < 2 * R; ++k) {
+            const float v = pin[k];
+            sgn |= __float_as_int(v);
+            x[k + 1] = (double)v;
+        }
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
+            float cur[W];
 #pragma unroll
             for (int u = 0; u < W; ++u) {
-                x[u] = (double)pin[g * W + u + 2 * R];
-                double t = x[(u + 1 + R) % W] * G.w[R];
+                cur[u] = pin[g * W + u + 2 * R];
+                sgn |= __float_as_int(cur[u]);
+            }
+            const unsigned kk = sgn < 0 ? GAUSS_TIE_ALWAYS : tieK;
+            unsigned redo = 0;
 #pragma unroll
-                for (int k = R; k >= 1; --k) t = t + (x[(u + 1 + R - k) % W] + x[(u + 1 + R + k) % W]) * G.w[R - k];
+            for (int u = 0; u < W; ++u) {
+                x[u] = (double)cur[u];
+                const double t = gauss_fused<R>(x, u, G);
+                redo |= gauss_near_tie(t, kk) ? (1u << u) : 0u;
                 pout[g * W + u] = (float)t;
+            }
+            // the tile already holds zeros outside the image: every input "exists"
+            if (__builtin_expect(redo != 0u, 0)) {
+#pragma unroll 1
+                for (int u = 0; u < W; ++u)
+                    if ((redo >> u) & 1u) pout[g * W + u] = gauss_literal(pin + g * W + u + R, 1, -R, R, R, G);
             }
         }
     }
@@ -778,10 +858,12 @@ template <int R>
 static int launch_gauss_march(snn_ctx* ctx, const ExtractPlan& pl, int npass, int ppf) {
     constexpr int TC = 2 * (2 * R + 1) * GH_WARPS;
     const int nseg = (SNN_SMAX + GV_SEG - 1) / GV_SEG;
+    const char* tk = getenv("SNN_GAUSS_TIE_K");     // read per launch: the tests switch it
+    const unsigned tieK = tk ? (unsigned)strtoul(tk, nullptr, 0) : 64u;
     k_gauss_vm<R><<<dim3(13, (nseg + 3) / 4, npass), dim3(32, 4), 0, ctx->stream>>>(pl.bufA, pl.info, ppf, pl.gauss,
-                                                                                   pl.bufB);
+                                                                                   tieK, pl.bufB);
     k_gauss_hm<R><<<dim3((SNN_SMAX + TC - 1) / TC, (SNN_SMAX + GH_ROWS - 1) / GH_ROWS, npass), GH_WARPS * 32, 0,
-                    ctx->stream>>>(pl.bufB, pl.info, ppf, pl.gauss, pl.bleed, pl.bufC);
+                    ctx->stream>>>(pl.bufB, pl.info, ppf, pl.gauss, tieK, pl.bleed, pl.bufC);
     SNN_LAUNCH_CHECK("k_gauss_march");
     return SNN_OK;
 }

@@ -126,7 +126,7 @@ class Device:
     def heatmap(self, chrom_id, i0, i1, maxpixel_value, want_channel=True):
         """seeimage's image (seeimage.py:77-90) of bins [i0,i1): (float64 green/blue channel or
         None, uint8 RGB)."""
-        n = int(i1 - i0)
+        n = max(int(i1 - i0), 0)        # a reversed window is the library's error to report
         chan = np.empty((n, n), dtype=np.float64) if want_channel else None
         rgb = np.empty((n, n, 3), dtype=np.uint8)
         check(self.lib.snn_heatmap(self.h, int(chrom_id), int(i0), int(i1), float(maxpixel_value),

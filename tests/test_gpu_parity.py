@@ -301,6 +301,34 @@ def test_generic_and_specialised_kernels_agree(dev, tiny2_cm, monkeypatch):
         gen.close()
 
 
+def test_fused_gaussian_equals_literal_form(dev, tiny2_cm, monkeypatch):
+    """k_gauss_vm / k_gauss_hm accumulate with FMAs and fall back to scipy's literal
+    multiply-then-add form next to a float32 rounding tie (gauss_near_tie, image_fast.cu).
+    SNN_GAUSS_TIE_K=0x10000000 forces the literal form for every output: the smoothed images of
+    every window and brightness of a chromosome (23 M accumulations, a handful of real near-ties)
+    must be the same bits either way."""
+    obj, mat, names, _, _ = _obj(tiny2_cm, "KR", dev)
+    cid = obj.unbalLib.ensure("chrA")
+    M = float(np.quantile(mat.positive_population("chrA"), 0.97))
+    nwin = pl.n_frames(mat.nbins("chrA"))
+    fused = {}
+    for idx in range(nwin):
+        for b in range(6):
+            fused[idx, b] = dev.debug_stages(cid, M, 2.0, 3, idx, b)["smoothed"]
+    monkeypatch.setenv("SNN_GAUSS_TIE_K", str(0x10000000))
+    npx = 0
+    for (idx, b), sm in fused.items():
+        lit = dev.debug_stages(cid, M, 2.0, 3, idx, b)["smoothed"]
+        assert np.array_equal(sm, lit), (idx, b)
+        npx += sm.size
+    assert npx > 5_000_000
+    # and the whole search of the chromosome agrees as well
+    mp = np.quantile(mat.positive_population("chrA"), [0.95, 0.99])
+    lit_c = dev.extract(cid, mp, 2.0, 10, 8, 3)
+    monkeypatch.delenv("SNN_GAUSS_TIE_K")
+    assert np.array_equal(dev.extract(cid, mp, 2.0, 10, 8, 3), lit_c)
+
+
 @pytest.mark.parametrize("cfg,norm", [("tiny2", "KR"), ("tiny1k", "None"), ("tiny10k", "weight")])
 def test_warp_and_cta_scoring_kernels_agree(dev, cfg, norm, monkeypatch):
     """snn_score routes in-band windows to the warp-per-stripe kernel (score_warp.cu) and the

@@ -2,6 +2,8 @@
 chr16 at 5 kb, 19,642 bins, 99 search windows, 5 maxpixel values) where the oracle is too slow
 to run in full: exact scale invariance, window-range sharding == whole, idempotent dedup,
 quantiles == numpy on the host population, and oracle parity on sampled windows."""
+import os
+
 import numpy as np
 import pytest
 
@@ -39,6 +41,12 @@ def test_cfg1_properties(device, cfg1):
     both = np.concatenate(parts)
     both = both[np.lexsort((both["k"], both["ud"], both["bright"], both["frame"], both["q"]))]
     assert np.array_equal(both, cand)
+    # fused Gaussian accumulation (FMA + tie check) == the literal form, over ~1e9 accumulations
+    os.environ["SNN_GAUSS_TIE_K"] = str(0x10000000)
+    try:
+        assert np.array_equal(device.extract(cid, mp, 2.0, 10, 8, 3), cand)
+    finally:
+        del os.environ["SNN_GAUSS_TIE_K"]
     # oracle parity on a sample of windows (the full chromosome takes ~10 min on one core)
     for idx in (0, 17, 33, 98):
         fr = pl.load_frame(mat, "16", idx)
