@@ -11,6 +11,9 @@
  *  (2) float32 through float64: (float)((double)x * RN64(1/(double)b))  ==  x / b in float32.
  *  (3) float32 Markstein: y = RN32(1/b), q0 = x*y, r = fmaf(-q0, b, x), q = fmaf(r, y, q0)  ==  x / b.
  *      k_gauss_hm: smoothed / bleed on the (idle) FP32 pipe, no MUFU.RCP.
+ *  (4) float32 division by the interior bleed-over constant b0 = 1 + 2^-23: RN(x / b0) is x's bit
+ *      pattern minus 1, or minus 2 when the mantissa field f is 0 or >= 0x400002.  EXHAUSTIVE over
+ *      every positive float with biased exponent 2..254 (2.1e9 values).  k_gauss_hm phase 3.
  *   gcc -O2 -march=native -fopenmp -o /tmp/divchk/chk tools/check_division_identities.c -lm && /tmp/divchk/chk 2000000000
  */
 static inline uint64_t rng(uint64_t* s) {
@@ -75,6 +78,25 @@ int main(int argc, char** argv) {
             }
         }
     }
+    long long bad6 = 0, n6 = 0;
+    {
+        union { uint32_t u; float f; } b0;
+        b0.u = 0x3f800001u;
+        const float B0 = b0.f;
+#pragma omp parallel for reduction(+ : bad6, n6) schedule(static)
+        for (long long bits = 0x01000000LL; bits <= 0x7f7fffffLL; ++bits) {
+            union { uint32_t u; float f; } x, q, w;
+            x.u = (uint32_t)bits;
+            volatile float qv = x.f / B0;
+            q.f = qv;
+            const uint32_t fm = x.u & 0x7fffffu;
+            w.u = x.u - ((fm - 1u >= 0x400001u) ? 2u : 1u);
+            if (w.u != q.u) ++bad6;
+            ++n6;
+        }
+    }
+    printf("division by 1+2^-23 as an integer step: %lld floats checked, %lld bad\n", n6, bad6);
+    if (bad6) return 1;
     printf("cases %lld  markstein(gray M): %lld bad  markstein(/255): %lld bad  markstein(random): %lld bad  f32-via-f64: %lld bad  f32 markstein: %lld bad\n",
            n, bad1, bad2, bad3, bad4, bad5);
     return (bad1 | bad2 | bad3 | bad4 | bad5) ? 1 : 0;
