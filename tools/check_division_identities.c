@@ -13,7 +13,7 @@
  *      k_gauss_hm: smoothed / bleed on the (idle) FP32 pipe, no MUFU.RCP.
  *  (4) float32 division by the interior bleed-over constant b0 = 1 + 2^-23: RN(x / b0) is x's bit
  *      pattern minus 1, or minus 2 when the mantissa field f is 0 or >= 0x400002.  EXHAUSTIVE over
- *      every positive float with biased exponent 2..254 (2.1e9 values).  k_gauss_hm phase 3.
+ *      every positive float with biased exponent 2..254 (2.1e9 values).  Measured in k_gauss_hm phase 3 and not kept.
  *   gcc -O2 -march=native -fopenmp -o /tmp/divchk/chk tools/check_division_identities.c -lm && /tmp/divchk/chk 2000000000
  */
 static inline uint64_t rng(uint64_t* s) {
