@@ -121,8 +121,10 @@ class ContactMap:
 
         Mirrors what the reference gets from ``cooler.Cooler(cool)`` (stripenn.py:80-118):
         chromosome names/sizes, bin size, the ``bins`` weight columns and the upper-triangle
-        pixel table of every cis block.  Lazy import: cooler/h5py are absent from the build
-        image, so this path is exercised only on a user's machine.
+        pixel table of every cis block (pixels whose bin2 lies in another chromosome are
+        dropped: stripenn never fetches a trans window).  Lazy import: cooler/h5py are absent
+        from the build image; tests/test_cooler_adaptor.py drives this code through a stand-in
+        module with cooler's public API (tests/fake_cooler.py).
         """
         try:
             import cooler  # type: ignore
@@ -130,15 +132,15 @@ class ContactMap:
             raise RuntimeError(
                 "reading %r needs the 'cooler' package (not installed); "
                 "convert to the .npz layout of stripenn_b200.contactmap instead" % uri) from e
-        lib = cooler.Cooler(uri)  # pragma: no cover
-        names = list(lib.chromnames)  # pragma: no cover
-        sizes = np.asarray(lib.chromsizes.values, dtype=np.int64)  # pragma: no cover
-        cm = cls(binsize=int(lib.binsize), chromnames=names, chromsizes=sizes)  # pragma: no cover
-        bins = lib.bins()  # pragma: no cover
-        wcols = [c for c in bins.columns if c not in ("chrom", "start", "end")]  # pragma: no cover
-        for col in wcols:  # pragma: no cover
+        lib = cooler.Cooler(uri)
+        names = list(lib.chromnames)
+        sizes = np.asarray(lib.chromsizes.values, dtype=np.int64)
+        cm = cls(binsize=int(lib.binsize), chromnames=names, chromsizes=sizes)
+        bins = lib.bins()
+        wcols = [c for c in bins.columns if c not in ("chrom", "start", "end")]
+        for col in wcols:
             cm.weights[col] = {}
-        for name in names:  # pragma: no cover
+        for name in names:
             if chroms is not None and name not in chroms:
                 continue
             lo, hi = lib.extent(name)
@@ -152,7 +154,7 @@ class ContactMap:
             b = bins.fetch(name)
             for col in wcols:
                 cm.weights[col][name] = b[col].values.astype(np.float64)
-        return cm  # pragma: no cover
+        return cm
 
 
 def open_contact_map(path: str, chroms: Optional[List[str]] = None) -> ContactMap:
