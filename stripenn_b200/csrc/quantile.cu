@@ -11,6 +11,7 @@
 // Roofline: HBM.  Algorithmic bytes: 12 B per stored pixel (one pass); the 8 radix passes and
 // the counting pass re-read the COO arrays (9 x 12 B per pixel of real traffic).
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "snn_internal.cuh"
@@ -122,6 +123,54 @@ __global__ void k_radix_hist(const QChrom* __restrict__ chroms, int K, int shift
         if (sh[q]) atomicAdd(&hist[q], (unsigned long long)sh[q]);
 }
 
+// ---- raw counts (--norm None): one-pass value histogram ----------------------------------------
+// Without weights the population is made of small positive integers, so the order statistics
+// can be read off an exact histogram of the VALUES: one pass over the pixel table instead of
+// the counting pass + 8 radix passes (58 M pixels of the mouse genome: 0.5 instead of 4.3 ms per
+// genome).  Bins 1..QI_NB-1 are exact; larger counts fall into one overflow bin, and a rank that
+// lands there sends the whole call to the radix select.  Lanes of a warp holding the same value
+// (1, 2, 3 dominate away from the diagonal) are merged with __match_any_sync before the
+// shared-memory atomic, like in k_radix_hist.  hist[job][v] (64-bit) lives in the job's work area.
+#define QI_NB 4096
+__global__ void __launch_bounds__(256) k_int_hist(const QChrom* __restrict__ chroms,
+                                                  unsigned long long* __restrict__ work) {
+    __shared__ unsigned sh[QI_NB + 1];
+    const QChrom c = chroms[blockIdx.y];
+    unsigned long long* hist = work + (size_t)c.job * QW_WORDS;
+    for (int t = threadIdx.x; t <= QI_NB; t += blockDim.x) sh[t] = 0;
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t nround = (c.nnz + stride - 1) / stride;
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int64_t it = 0; it < nround; ++it, t += stride) {     // whole warps stay in the loop (match_any)
+        unsigned mult = 0;
+        int v = 0;
+        if (t < c.nnz) {
+            v = c.cnt[t];
+            if (v > 0) {
+                if (c.sel) {
+                    const int32_t a = c.b1[t], b = c.b2[t];
+                    mult = slow_in(c, a, b) + ((a != b) ? slow_in(c, b, a) : 0u);
+                } else {
+                    mult = (c.b1[t] == c.b2[t]) ? 1u : 2u;
+                }
+            }
+        }
+        const bool hit = mult != 0u;
+        const unsigned act = __ballot_sync(0xffffffffu, hit);
+        if (hit) {
+            const unsigned bin = v < QI_NB ? (unsigned)v : (unsigned)QI_NB;
+            const unsigned peers = __match_any_sync(act, bin);
+            const unsigned twos = __ballot_sync(act, mult == 2u) & peers;
+            if ((int)(threadIdx.x & 31) == __ffs(peers) - 1)
+                atomicAdd(&sh[bin], (unsigned)__popc(peers) + (unsigned)__popc(twos));
+        }
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q <= QI_NB; q += blockDim.x)
+        if (sh[q]) atomicAdd(&hist[q], (unsigned long long)sh[q]);
+}
+
 // One CTA per chromosome: one thread per rank picks its digit from its group's histogram;
 // thread 0 then regroups the ranks by their (longer) prefixes for the next pass.
 __global__ void k_radix_pick(int K, int shift, unsigned long long* __restrict__ work) {
@@ -160,6 +209,40 @@ __global__ void k_radix_pick(int K, int shift, unsigned long long* __restrict__ 
     __syncthreads();
     for (int t = threadIdx.x; t < QMAXK * 256; t += blockDim.x) hist[t] = 0;
 }
+
+// numpy 'linear': virtual index (n - 1) * q ; _get_indexes: floor, +1, clipped to the ends
+static void np_ranks(unsigned long long n, double q, unsigned long long* prev, unsigned long long* next,
+                     double* gamma, char* top) {
+    const double vi = (double)(long long)(n - 1) * q;
+    const double fl = floor(vi);
+    *top = 0;
+    if (vi >= (double)(long long)(n - 1)) {
+        *prev = *next = n - 1;
+        *top = 1;
+    } else if (vi < 0) {
+        *prev = *next = 0;
+    } else {
+        *prev = (unsigned long long)fl;
+        *next = *prev + 1;
+    }
+    *gamma = vi - fl;
+}
+
+// numpy _lerp, in its floating-point order
+static double np_lerp(double a, double b, double t, char top) {
+    if (top) t = 0.0, b = a;
+    volatile double diff = b - a;
+    volatile double prod = diff * t;
+    double r = a + prod;
+    if (t >= 0.5) {
+        volatile double omt = 1 - t;
+        volatile double prod2 = diff * omt;
+        r = b - prod2;
+    }
+    return r;
+}
+
+static_assert(QI_NB + 1 <= QW_WORDS, "the value histogram must fit the job's work area");
 
 int snn_quantiles_sources_impl(snn_ctx* ctx, const std::vector<QSource>& src, int njob, int nq, const double* q,
                                double* out) {
@@ -200,6 +283,44 @@ int snn_quantiles_sources_impl(snn_ctx* ctx, const std::vector<QSource>& src, in
 
     SNN_CUDA(cudaMemcpyAsync(d_chroms, hc.data(), (size_t)ns * sizeof(QChrom), cudaMemcpyHostToDevice, ctx->stream));
     SNN_CUDA(cudaMemsetAsync(d_work, 0, wbytes, ctx->stream));
+    bool raw_counts = getenv("SNN_NO_INT_HIST") == nullptr;      // A/B switch and test hook
+    for (int i = 0; i < ns; ++i) raw_counts = raw_counts && hc[i].w == nullptr;
+    if (raw_counts) {
+        {
+            SnnScope scope(ctx, ST_QUANTILE, 1);
+            k_int_hist<<<grid, threads, 0, ctx->stream>>>(d_chroms, d_work);
+            SNN_LAUNCH_CHECK("k_int_hist");
+        }
+        std::vector<unsigned long long> hh((size_t)nc * (QI_NB + 1));
+        SNN_CUDA(cudaMemcpy2DAsync(hh.data(), (QI_NB + 1) * 8, d_work, QW_WORDS * 8, (QI_NB + 1) * 8, nc,
+                                   cudaMemcpyDeviceToHost, ctx->stream));
+        SNN_CUDA(cudaStreamSynchronize(ctx->stream));
+        bool overflow = false;
+        for (int ci = 0; ci < nc && !overflow; ++ci) {
+            const unsigned long long* h = hh.data() + (size_t)ci * (QI_NB + 1);
+            unsigned long long n = 0;
+            for (int v = 1; v <= QI_NB; ++v) n += h[v];
+            for (int i = 0; i < nq; ++i) {
+                double* dst = out + (size_t)ci * nq + i;
+                if (!n) { *dst = NAN; continue; }              // np.quantile of an empty array
+                unsigned long long prev, next;
+                double gamma;
+                char top;
+                np_ranks(n, q[i], &prev, &next, &gamma, &top);
+                unsigned long long cum = 0;
+                int va = -1, vb = -1;
+                for (int v = 1; v < QI_NB && vb < 0; ++v) {
+                    cum += h[v];
+                    if (va < 0 && cum > prev) va = v;
+                    if (cum > next) vb = v;
+                }
+                if (va < 0 || vb < 0) { overflow = true; break; }   // a rank beyond the exact bins
+                *dst = np_lerp((double)va, (double)vb, gamma, top);
+            }
+        }
+        if (!overflow) return SNN_OK;
+        SNN_CUDA(cudaMemsetAsync(d_work, 0, wbytes, ctx->stream));   // large counts: radix select below
+    }
     {
         SnnScope scope(ctx, ST_QUANTILE, 1);
         k_count_positive<<<grid, threads, 0, ctx->stream>>>(d_chroms, d_work);
@@ -225,20 +346,8 @@ int snn_quantiles_sources_impl(snn_ctx* ctx, const std::vector<QSource>& src, in
             group[QMAXK] = n ? 1 : 0;
             if (!n) continue;
             for (int i = 0; i < m; ++i) {
-                // 'linear': virtual index (n - 1) * q ; _get_indexes: floor, +1, clipped to the ends
-                double vi = (double)(long long)(n - 1) * q[base + i];
-                double fl = floor(vi);
                 unsigned long long prev, next;
-                if (vi >= (double)(long long)(n - 1)) {
-                    prev = next = n - 1;
-                    top[(size_t)ci * m + i] = 1;
-                } else if (vi < 0) {
-                    prev = next = 0;
-                } else {
-                    prev = (unsigned long long)fl;
-                    next = prev + 1;
-                }
-                gamma[(size_t)ci * m + i] = vi - fl;
+                np_ranks(n, q[base + i], &prev, &next, &gamma[(size_t)ci * m + i], &top[(size_t)ci * m + i]);
                 state[2 * (2 * i) + 1] = prev;
                 state[2 * (2 * i + 1) + 1] = next;
             }
@@ -266,17 +375,7 @@ int snn_quantiles_sources_impl(snn_ctx* ctx, const std::vector<QSource>& src, in
                 double a, b;
                 memcpy(&a, &state[2 * (2 * i)], 8);
                 memcpy(&b, &state[2 * (2 * i + 1)], 8);
-                double t = gamma[(size_t)ci * m + i];
-                if (top[(size_t)ci * m + i]) t = 0.0, b = a;
-                // numpy _lerp
-                volatile double diff = b - a;
-                volatile double prod = diff * t;
-                double r = a + prod;
-                if (t >= 0.5) {
-                    volatile double omt = 1 - t;
-                    volatile double prod2 = diff * omt;
-                    r = b - prod2;
-                }
+                const double r = np_lerp(a, b, gamma[(size_t)ci * m + i], top[(size_t)ci * m + i]);
                 *dst = r;
             }
         }

@@ -66,6 +66,35 @@ def test_band_quantiles_expected(dev, cfg, norm):
         dev.fetch(obj.unbalLib.chrom_id(names[0]), 0, 10, 1000, 1010)   # outside the band
 
 
+def test_raw_count_quantiles_histogram_and_radix_paths(dev, monkeypatch):
+    """--norm None: quantiles come from a one-pass histogram of the integer values (k_int_hist,
+    exact bins below 4096); a rank beyond the exact bins, or SNN_NO_INT_HIST=1, takes the radix
+    select.  All three must equal numpy on the same population."""
+    qs = [0.0, 0.31, 0.5, 0.95, 0.97, 0.99, 0.9999, 1.0]
+    cm = synth.make_config("tiny2")
+    for step, mult in enumerate((1, 70, 12)):   # max count ~1e2 (all exact) / ~1e4 (top ranks overflow) / ~1e5 (most do)
+        for c in cm.chroms.values():
+            c.count = (c.count.astype(np.int64) * mult).astype(np.int32)
+        obj, mat, names, _, _ = _obj(cm, "None", dev)
+        want = {c: np.quantile(mat.positive_population(c), qs) for c in names}
+        got = obj.getQuantile_original(cm, names, qs)
+        monkeypatch.setenv("SNN_NO_INT_HIST", "1")
+        radix = obj.getQuantile_original(cm, names, qs)
+        monkeypatch.delenv("SNN_NO_INT_HIST")
+        for c in names:
+            assert np.array_equal(got[c], want[c]), (step, c)
+            assert np.array_equal(radix[c], want[c]), (step, c)
+        assert max(int(x.count.max()) for x in cm.chroms.values()) > (0 if step == 0 else 4096)
+        _unload_all(dev)
+    # a chromosome without positive pixels next to a normal one
+    cm = synth.make_config("tiny2")
+    cm.chroms["chrB"].count[:] = 0
+    obj, mat, names, _, _ = _obj(cm, "None", dev)
+    got = obj.getQuantile_original(cm, names, [0.5, 0.99])
+    assert np.all(np.isnan(got["chrB"]))
+    assert np.array_equal(got["chrA"], np.quantile(mat.positive_population("chrA"), [0.5, 0.99]))
+
+
 @pytest.mark.parametrize("cfg,norm", [("tiny", "None"), ("tiny2", "KR")])
 def test_background_exact(dev, cfg, norm):
     cm = synth.make_config(cfg)
