@@ -291,6 +291,42 @@ def test_small_and_empty_windows(dev):
     assert np.array_equal(dev.expected(cid), np.zeros(400))
 
 
+@pytest.mark.parametrize("nkeep,sigma", [(11, 2.0), (13, 2.0), (16, 2.0), (17, 2.0), (18, 2.5), (21, 2.5), (30, 2.0)])
+def test_narrow_windows_match_oracle(dev, nkeep, sigma):
+    """Windows with fewer non-empty columns than the Gaussian kernel is wide (S < 2 radius + 1):
+    k_gauss_hm evaluates the bleed-over definition there instead of its border-distance table;
+    at and above 2 radius + 1 the table is used.  Smoothed image and magnitude bit-exact."""
+    base = synth.make_map([("n", 300 * 5000)], 5000, seed=5)
+    px = base.chroms["n"]
+    keep_bins = np.sort(np.random.default_rng(nkeep).choice(np.arange(20, 280), size=nkeep, replace=False))
+    ok = np.isin(px.bin1, keep_bins) & np.isin(px.bin2, keep_bins)
+    # make sure every kept bin has a pixel (its diagonal), so exactly nkeep columns are non-empty
+    b1 = np.concatenate([px.bin1[ok], keep_bins.astype(np.int32)])
+    b2 = np.concatenate([px.bin2[ok], keep_bins.astype(np.int32)])
+    ct = np.concatenate([px.count[ok], np.full(nkeep, 3, np.int32)])
+    o = np.lexsort((b2, b1))
+    first = np.ones(len(o), bool)
+    first[1:] = (b1[o][1:] != b1[o][:-1]) | (b2[o][1:] != b2[o][:-1])
+    o = o[first]
+    base.chroms["n"] = type(px)("n", px.size_bp, px.nbins, b1[o].astype(np.int32), b2[o].astype(np.int32),
+                                ct[o].astype(np.int32))
+    mat = OracleMatrix(base, False)
+    lib = gs.DeviceMatrix(base, False, dev)
+    cid = lib.ensure("n")
+    M = 4.0
+    fr = pl.load_frame(mat, "n", 0)
+    assert fr["S"] == nkeep
+    w = cn.gaussian_weights(sigma)
+    G = im.saturate(fr["D"], M)
+    for b in (0, 5):
+        d = dev.debug_stages(cid, M, sigma, 3, 0, b)
+        gray = im.gray_image(G, im.BRIGHTNESS[b], 3)
+        st = cn.canny(gray, sigma, w, None, return_stages=True)
+        assert d["S"] == nkeep
+        assert np.array_equal(d["smoothed"], st["smoothed"]), (nkeep, sigma, b)
+        assert np.array_equal(d["mag"], st["mag"])
+
+
 def test_load_errors(dev):
     with pytest.raises(_lib.StripennB200Error) as e:
         dev.load_chrom(0, 100, 5000, 500000, [5, 3], [6, 4], [1, 1])       # not sorted
