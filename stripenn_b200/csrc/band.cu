@@ -200,7 +200,7 @@ extern "C" int snn_heatmap(snn_ctx* ctx, int chrom_id, int64_t i0, int64_t i1, d
 // ex[d] = sum_i nan0(band[i][d]) / (N - d), d < 400.  Two deterministic stages: per row-chunk
 // partial column sums (coalesced along d), then one fixed-order reduction over chunks.
 // Algorithmic bytes: nbins * min(400, bw) * 8.
-#define EXP_ROWS 256
+#define EXP_ROWS 64    // rows per partial sum: 4x the CTAs of the first version (latency-bound at 2 CTAs per SM)
 
 __global__ void k_expected_partial(const double* __restrict__ band, int64_t nbins, int bw, int nd,
                                    double* __restrict__ partial) {

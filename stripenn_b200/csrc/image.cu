@@ -188,6 +188,27 @@ __global__ void __launch_bounds__(256) k_gray(const double* __restrict__ Dc_all,
 }
 
 // ---- Gaussian ----------------------------------------------------------------------------------
+// One pixel of gaussian(ones, mode='constant') + eps: scipy's two correlate1d passes over a mask of
+// ones (float32 between the passes, float64 accumulation, farthest pair first).
+__device__ __forceinline__ float bleed_at(const GaussParams& G, int i, int j, int S) {
+    const int r = G.radius;
+    double t = 1.0 * G.w[r];
+    for (int k = r; k >= 1; --k) {
+        double lo = (i - k >= 0) ? 1.0 : 0.0, hi = (i + k < S) ? 1.0 : 0.0;
+        t = t + (lo + hi) * G.w[r - k];
+    }
+    const double bv = (double)(float)t;
+    double u = bv * G.w[r];
+    for (int k = r; k >= 1; --k) {
+        double lo = (j - k >= 0) ? bv : 0.0, hi = (j + k < S) ? bv : 0.0;
+        u = u + (lo + hi) * G.w[r - k];
+    }
+    return (float)u + 1.1920928955078125e-07f;
+}
+
+// Pixels at least `radius` away from every border see all taps: the same operations on the same
+// operands for each of them (92 % of a 400 x 400 window), so a thread evaluates that value once
+// and the loops only run for border pixels.
 __global__ void __launch_bounds__(256) k_bleed(const FrameInfo* __restrict__ info, GaussParams G,
                                                float* __restrict__ bleed_all) {
     const int f = blockIdx.z;
@@ -195,19 +216,11 @@ __global__ void __launch_bounds__(256) k_bleed(const FrameInfo* __restrict__ inf
     const int j = blockIdx.x * 32 + threadIdx.x;
     if (j >= S) return;
     const int r = G.radius;
+    const float interior = bleed_at(G, r, r, 2 * r + 1);
+    const bool jin = j >= r && j < S - r;
     for (int i = blockIdx.y * 32 + threadIdx.y; i < blockIdx.y * 32 + 32 && i < S; i += 8) {
-        double t = 1.0 * G.w[r];
-        for (int k = r; k >= 1; --k) {
-            double lo = (i - k >= 0) ? 1.0 : 0.0, hi = (i + k < S) ? 1.0 : 0.0;
-            t = t + (lo + hi) * G.w[r - k];
-        }
-        const double bv = (double)(float)t;
-        double u = bv * G.w[r];
-        for (int k = r; k >= 1; --k) {
-            double lo = (j - k >= 0) ? bv : 0.0, hi = (j + k < S) ? bv : 0.0;
-            u = u + (lo + hi) * G.w[r - k];
-        }
-        bleed_all[(int64_t)f * SNN_SMAX * SNN_SMAX + i * SNN_SMAX + j] = (float)u + 1.1920928955078125e-07f;
+        const bool in = jin && i >= r && i < S - r;
+        bleed_all[(int64_t)f * SNN_SMAX * SNN_SMAX + i * SNN_SMAX + j] = in ? interior : bleed_at(G, i, j, S);
     }
 }
 
