@@ -113,7 +113,9 @@ int snn_heatmap(snn_ctx* ctx, int chrom_id, int64_t i0, int64_t i1, double maxpi
 
 /* ---- a2: getStripe.getQuantile_original (getStripe.py:160-176):
  * np.quantile(mat[mat > 0], q) over the full symmetric matrix (off-diagonal pixels count
- * twice), numpy 'linear' interpolation reproduced bit-exactly. */
+ * twice), numpy 'linear' interpolation reproduced bit-exactly.  Raw counts (no weights) are
+ * selected from a one-pass histogram of the integer values, balanced values by an 8-bit radix
+ * select over the float64 bit patterns (also the fallback for counts >= 4096); same results. */
 int snn_quantiles(snn_ctx* ctx, int chrom_id, int nq, const double* q, double* out);
 /* The same for several resident chromosomes in one call (getStripe.py:166 loops over ChrList):
  * out = nchrom x nq, row k = chrom_ids[k]. */
