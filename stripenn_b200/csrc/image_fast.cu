@@ -460,6 +460,130 @@ __global__ void __launch_bounds__(GH_WARPS * 32) k_gauss_hm(const float* __restr
     }
 }
 
+// ---- axis 1 + bleed-over division, direct-store version (SNN_GAUSS_HD=1; A/B candidate) -----------
+// k_gauss_hm spends more than half of its instructions outside the accumulation (profiles/r01s:
+// phase 3 = second shared-memory tile, bleed-over loads and division 35 %, staging 18 %): 548 M
+// warp instructions per launch against 253 M for the same arithmetic along axis 0.  Here the
+// thread that walks along a row keeps its outputs in registers, divides them by the bleed-over
+// values of its own row (five float4 loads per 20 outputs, issued before the arithmetic) and
+// stores float4s straight to global memory — no second tile, no third phase, one barrier.  The
+// window ring has HD_N = 20 slots (>= 2R+1, a multiple of 4) so that an unrolled group yields 20
+// outputs = 5 aligned float4s; input k of the thread's segment lives in slot k % 20.
+#define HD_ROWS 32
+#define HD_WARPS 5
+#define HD_N 20
+#define HD_SEG 40                      // outputs per thread: 2 groups; 5 warps x 40 = 200 columns per CTA
+#ifndef HD_MINB
+#define HD_MINB 4
+#endif
+template <int R>
+__device__ __forceinline__ double gauss_fused_ring(const double* x, const int u, const GaussParams& G) {
+    // centre = input u + R of the group -> slot (u + R) % HD_N; pairs k away on both sides
+    double t = x[(u + R) % HD_N] * G.w[R];
+#pragma unroll
+    for (int k = R; k >= 1; --k)
+        t = __fma_rn(x[(u + R - k + HD_N) % HD_N] + x[(u + R + k) % HD_N], G.w[R - k], t);
+    return t;
+}
+
+template <int R>
+__global__ void __launch_bounds__(HD_WARPS * 32, HD_MINB) k_gauss_hd(const float* __restrict__ in_all,
+                                                            const FrameInfo* __restrict__ info, int passes_per_frame,
+                                                            GaussParams G, unsigned tieK,
+                                                            const float* __restrict__ bleed_all,
+                                                            float* __restrict__ out_all) {
+    static_assert(2 * R + 1 <= HD_N, "ring too small");
+    constexpr int TC = HD_SEG * HD_WARPS;         // tile columns
+    constexpr int NCOL = TC + 2 * R;
+    constexpr int PIN = NCOL | 1;                 // odd pitch: lane = row hits 32 banks
+    __shared__ float tin[HD_ROWS * PIN];
+    const int pass = blockIdx.z;
+    const int f = pass / passes_per_frame;
+    const int S = info[f].S;
+    const int r0 = blockIdx.y * HD_ROWS, ct0 = blockIdx.x * TC;
+    if (r0 >= S || ct0 >= S) return;
+    const int nr = min(HD_ROWS, S - r0);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* in = in_all + (int64_t)pass * SNN_SMAX * SNN_SMAX + (int64_t)r0 * SNN_SMAX;
+    {   // staging: warp = row, lanes along the columns; zero fill outside the image
+        constexpr int NIT = (NCOL + 31) / 32;
+        const unsigned tin_s = (unsigned)__cvta_generic_to_shared(tin);
+#pragma unroll 2
+        for (int rr = warp; rr < HD_ROWS; rr += HD_WARPS) {
+            const bool rowok = rr < nr;
+            const float* grow = in + rr * SNN_SMAX + (ct0 - R);
+            const unsigned sdst = tin_s + (unsigned)(rr * PIN) * 4u;
+#pragma unroll
+            for (int it = 0; it < NIT; ++it) {
+                const int p = lane + 32 * it;
+                if (p < NCOL) {
+                    const int c = ct0 - R + p;
+                    const bool ok = rowok && c >= 0 && c < S;
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sdst + (unsigned)p * 4u),
+                                 "l"(ok ? grow + p : in), "r"(ok ? 4 : 0));
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;");
+        asm volatile("cp.async.wait_group 0;");
+    }
+    __syncthreads();
+    const int cs = ct0 + warp * HD_SEG;           // first output column of this thread (multiple of 4)
+    if (lane >= nr || cs >= S) return;
+    const float* pin = tin + lane * PIN + warp * HD_SEG;      // pin[k] = image column cs - R + k
+    const int64_t rowoff = (int64_t)(r0 + lane) * SNN_SMAX + cs;
+    const float* bleed = bleed_all + (int64_t)f * SNN_SMAX * SNN_SMAX + rowoff;
+    float* out = out_all + (int64_t)pass * SNN_SMAX * SNN_SMAX + rowoff;
+    double x[HD_N];
+    int sgn = 0;
+#pragma unroll
+    for (int k = 0; k < 2 * R; ++k) {
+        const float v = pin[k];
+        sgn |= __float_as_int(v);
+        x[k] = (double)v;
+    }
+#pragma unroll
+    for (int k = 2 * R; k < HD_N; ++k) x[k] = 0.0;
+#pragma unroll 1
+    for (int g = 0; g < HD_SEG / HD_N; ++g) {
+        if (cs + g * HD_N >= S) break;            // the rest of the segment lies right of the image
+        float4 bl[HD_N / 4];
+#pragma unroll
+        for (int m = 0; m < HD_N / 4; ++m) bl[m] = *reinterpret_cast<const float4*>(bleed + g * HD_N + 4 * m);
+        float cur[HD_N];
+#pragma unroll
+        for (int u = 0; u < HD_N; ++u) {
+            cur[u] = pin[g * HD_N + u + 2 * R];
+            sgn |= __float_as_int(cur[u]);
+        }
+        const unsigned kk = sgn < 0 ? GAUSS_TIE_ALWAYS : tieK;
+        unsigned redo = 0;
+        float o[HD_N];
+#pragma unroll
+        for (int u = 0; u < HD_N; ++u) {
+            x[(u + 2 * R) % HD_N] = (double)cur[u];
+            const double t = gauss_fused_ring<R>(x, u, G);
+            redo |= gauss_near_tie(t, kk) ? (1u << u) : 0u;
+            o[u] = (float)t;
+        }
+        if (__builtin_expect(redo != 0u, 0)) {    // next to a rounding tie: the literal form decides
+#pragma unroll
+            for (int u = 0; u < HD_N; ++u)
+                if ((redo >> u) & 1u) o[u] = gauss_literal(pin + g * HD_N + u + R, 1, -R, R, R, G);
+        }
+        // columns >= S of the last group hold don't-care values (never read; inside the row pitch)
+#pragma unroll
+        for (int m = 0; m < HD_N / 4; ++m) {
+            float4 q;
+            q.x = o[4 * m] / bl[m].x;
+            q.y = o[4 * m + 1] / bl[m].y;
+            q.z = o[4 * m + 2] / bl[m].z;
+            q.w = o[4 * m + 3] / bl[m].w;
+            *reinterpret_cast<float4*>(out + g * HD_N + 4 * m) = q;
+        }
+    }
+}
+
 // ---- Sobel + magnitude + NMS ------------------------------------------------------------------------
 __device__ __forceinline__ int f_symm(int i, int n) {
     if (i < 0) i = -i - 1;
@@ -862,8 +986,19 @@ static int launch_gauss_march(snn_ctx* ctx, const ExtractPlan& pl, int npass, in
     const unsigned tieK = tk ? (unsigned)strtoul(tk, nullptr, 0) : 64u;
     k_gauss_vm<R><<<dim3(13, (nseg + 3) / 4, npass), dim3(32, 4), 0, ctx->stream>>>(pl.bufA, pl.info, ppf, pl.gauss,
                                                                                    tieK, pl.bufB);
+    static_assert(SNN_SMAX % (HD_SEG * HD_WARPS) == 0, "k_gauss_hd tiles must cover the row pitch exactly");
+    const char* hd = getenv("SNN_GAUSS_HD");        // A/B switch: direct-store axis-1 kernel (default sigma only)
+    if constexpr (2 * R + 1 <= HD_N && 2 * R + 1 > HD_N - 4) {
+        if (hd && hd[0] == '1') {
+            k_gauss_hd<R><<<dim3(SNN_SMAX / (HD_SEG * HD_WARPS), (SNN_SMAX + HD_ROWS - 1) / HD_ROWS, npass),
+                            HD_WARPS * 32, 0, ctx->stream>>>(pl.bufB, pl.info, ppf, pl.gauss, tieK, pl.bleed, pl.bufC);
+            SNN_LAUNCH_CHECK("k_gauss_hd");
+            return SNN_OK;
+        }
+    }
+    (void)hd;
     k_gauss_hm<R><<<dim3((SNN_SMAX + TC - 1) / TC, (SNN_SMAX + GH_ROWS - 1) / GH_ROWS, npass), GH_WARPS * 32, 0,
-                    ctx->stream>>>(pl.bufB, pl.info, ppf, pl.gauss, tieK, pl.bleed, pl.bufC);
+                        ctx->stream>>>(pl.bufB, pl.info, ppf, pl.gauss, tieK, pl.bleed, pl.bufC);
     SNN_LAUNCH_CHECK("k_gauss_march");
     return SNN_OK;
 }

@@ -292,7 +292,7 @@ def test_small_and_empty_windows(dev):
 
 
 @pytest.mark.parametrize("nkeep,sigma", [(11, 2.0), (13, 2.0), (16, 2.0), (17, 2.0), (18, 2.5), (21, 2.5), (30, 2.0)])
-def test_narrow_windows_match_oracle(dev, nkeep, sigma):
+def test_narrow_windows_match_oracle(dev, nkeep, sigma, monkeypatch):
     """Windows with fewer non-empty columns than the Gaussian kernel is wide (S < 2 radius + 1):
     k_gauss_hm evaluates the bleed-over definition there instead of its border-distance table;
     at and above 2 radius + 1 the table is used.  Smoothed image and magnitude bit-exact."""
@@ -325,6 +325,10 @@ def test_narrow_windows_match_oracle(dev, nkeep, sigma):
         assert d["S"] == nkeep
         assert np.array_equal(d["smoothed"], st["smoothed"]), (nkeep, sigma, b)
         assert np.array_equal(d["mag"], st["mag"])
+        monkeypatch.setenv("SNN_GAUSS_HD", "1")            # the direct-store axis-1 kernel (radius 8 only)
+        d = dev.debug_stages(cid, M, sigma, 3, 0, b)
+        monkeypatch.delenv("SNN_GAUSS_HD")
+        assert np.array_equal(d["smoothed"], st["smoothed"]) and np.array_equal(d["mag"], st["mag"])
 
 
 def test_load_errors(dev):
@@ -392,6 +396,35 @@ def test_fused_gaussian_equals_literal_form(dev, tiny2_cm, monkeypatch):
     lit_c = dev.extract(cid, mp, 2.0, 10, 8, 3)
     monkeypatch.delenv("SNN_GAUSS_TIE_K")
     assert np.array_equal(dev.extract(cid, mp, 2.0, 10, 8, 3), lit_c)
+
+
+def test_direct_store_gaussian_kernel_equals_default(dev, tiny2_cm, monkeypatch):
+    """SNN_GAUSS_HD=1 selects k_gauss_hd (axis-1 pass that divides and stores from registers, no
+    second shared-memory tile) instead of k_gauss_hm: same bits for every window and brightness of
+    a chromosome, with the tie check on and with the literal form forced, and the same candidates."""
+    obj, mat, names, _, _ = _obj(tiny2_cm, "KR", dev)
+    cid = obj.unbalLib.ensure("chrB")
+    M = float(np.quantile(mat.positive_population("chrB"), 0.96))
+    nwin = pl.n_frames(mat.nbins("chrB"))
+    want = {(idx, b): dev.debug_stages(cid, M, 2.0, 3, idx, b) for idx in range(nwin) for b in (0, 2, 5)}
+    mp = np.quantile(mat.positive_population("chrB"), [0.95, 0.99])
+    cand = dev.extract(cid, mp, 2.0, 10, 8, 3)
+    monkeypatch.setenv("SNN_GAUSS_HD", "1")
+    for tie in (None, str(0x10000000)):
+        if tie:
+            monkeypatch.setenv("SNN_GAUSS_TIE_K", tie)
+        for (idx, b), w in want.items():
+            d = dev.debug_stages(cid, M, 2.0, 3, idx, b)
+            S = w["S"]
+            assert d["S"] == S
+            assert np.array_equal(d["smoothed"][:S, :S], w["smoothed"][:S, :S]), (idx, b, tie)
+            assert np.array_equal(d["edges"], w["edges"]) and np.array_equal(d["vert"], w["vert"])
+    monkeypatch.delenv("SNN_GAUSS_TIE_K")
+    assert len(cand) > 0 and np.array_equal(dev.extract(cid, mp, 2.0, 10, 8, 3), cand)
+    # other radii have no direct-store instance: the switch must be harmless there
+    a = dev.debug_stages(cid, M, 2.5, 3, 1, 1)["smoothed"]
+    monkeypatch.delenv("SNN_GAUSS_HD")
+    assert np.array_equal(a, dev.debug_stages(cid, M, 2.5, 3, 1, 1)["smoothed"])
 
 
 @pytest.mark.parametrize("cfg,norm", [("tiny2", "KR"), ("tiny1k", "None"), ("tiny10k", "weight")])

@@ -47,6 +47,12 @@ def test_cfg1_properties(device, cfg1):
         assert np.array_equal(device.extract(cid, mp, 2.0, 10, 8, 3), cand)
     finally:
         del os.environ["SNN_GAUSS_TIE_K"]
+    # the direct-store axis-1 Gaussian kernel (A/B candidate) finds the same candidates
+    os.environ["SNN_GAUSS_HD"] = "1"
+    try:
+        assert np.array_equal(device.extract(cid, mp, 2.0, 10, 8, 3), cand)
+    finally:
+        del os.environ["SNN_GAUSS_HD"]
     # oracle parity on a sample of windows (the full chromosome takes ~10 min on one core)
     for idx in (0, 17, 33, 98):
         fr = pl.load_frame(mat, "16", idx)
