@@ -852,6 +852,9 @@ __global__ void __launch_bounds__(SN_WARPS * 32, 2) k_sobel_nms3(const float* __
 // (few) lanes that keep a pixel.
 #define SN4_COLS 60
 #define SN4_WARPS 7
+#ifndef SN4_MINB
+#define SN4_MINB 4
+#endif
 
 // skimage _nonmaximum_suppression_bilinear for one pixel (see k_sobel_nms3 for the branch merge)
 __device__ __forceinline__ void nms_pixel(float is, float js, float m, float mAl, float mA, float mAr, float mBl,
@@ -878,7 +881,7 @@ __device__ __forceinline__ void nms_pixel(float is, float js, float m, float mAl
 }
 
 template <bool DBG>
-__global__ void __launch_bounds__(SN4_WARPS * 32, 4) k_sobel_nms4(const float* __restrict__ sm_all,
+__global__ void __launch_bounds__(SN4_WARPS * 32, SN4_MINB) k_sobel_nms4(const float* __restrict__ sm_all,
                                                                   const FrameInfo* __restrict__ info,
                                                                   int passes_per_frame, uint32_t* __restrict__ low_all,
                                                                   uint32_t* __restrict__ high_all,
