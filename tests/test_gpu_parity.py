@@ -293,9 +293,9 @@ def test_small_and_empty_windows(dev):
 
 @pytest.mark.parametrize("nkeep,sigma", [(11, 2.0), (13, 2.0), (16, 2.0), (17, 2.0), (18, 2.5), (21, 2.5), (30, 2.0)])
 def test_narrow_windows_match_oracle(dev, nkeep, sigma, monkeypatch):
-    """Windows with fewer non-empty columns than the Gaussian kernel is wide (S < 2 radius + 1):
-    k_gauss_hm evaluates the bleed-over definition there instead of its border-distance table;
-    at and above 2 radius + 1 the table is used.  Smoothed image and magnitude bit-exact."""
+    """Windows with fewer non-empty columns than the Gaussian kernel is wide (S < 2 radius + 1:
+    every pixel is a border pixel for both filter axes) and just above.  Smoothed image and
+    magnitude bit-exact, for both axis-1 kernels."""
     base = synth.make_map([("n", 300 * 5000)], 5000, seed=5)
     px = base.chroms["n"]
     keep_bins = np.sort(np.random.default_rng(nkeep).choice(np.arange(20, 280), size=nkeep, replace=False))
