@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Dict, Optional, Sequence
 
 import numpy as np
@@ -36,6 +37,33 @@ def gaussian_weights(sigma: float, truncate: float = 4.0):
     phi = np.exp(-0.5 / sigma2 * x ** 2)
     phi = phi / phi.sum()
     return np.ascontiguousarray(phi, dtype=np.float64), radius
+
+
+def unique_maxpixels(mp):
+    """Distinct maxpixel values in first-appearance order and, per input value, the index of its
+    representative (bitwise equality: NaN and -0.0 are not merged with anything else)."""
+    bits = np.ascontiguousarray(mp, dtype=np.float64).view(np.uint64)
+    first = {}
+    inverse = np.empty(len(bits), dtype=np.int64)
+    for i, b in enumerate(bits.tolist()):
+        inverse[i] = first.setdefault(b, len(first))
+    uniq = np.empty(len(first), dtype=np.float64)
+    for b, k in first.items():
+        uniq.view(np.uint64)[k] = b
+    return uniq, inverse
+
+
+def expand_duplicate_maxpixels(cand, inverse):
+    """Candidates of the distinct maxpixel values (sorted by q, then emission order) -> candidates
+    of every requested value: block of representative inverse[i] copied with q = i, blocks in q
+    order — the order snn_extract itself emits."""
+    blocks = []
+    q = cand["q"]
+    for i, u in enumerate(inverse.tolist()):
+        b = cand[q == u].copy()
+        b["q"] = i
+        blocks.append(b)
+    return np.concatenate(blocks) if blocks else cand
 
 
 class Device:
@@ -197,6 +225,19 @@ class Device:
     # ------------------------------------------------------------------ a5-a14
     def extract(self, chrom_id, maxpixel_values, sigma, minH, maxW, bfilter, gray_variant=0,
                 frame_lo=0, frame_hi=None, weights=None):
+        """snn_extract for several maxpixel values.  Equal values (common with raw counts: the 0.95
+        and 0.96 quantiles of small integers often coincide) give identical images, so the image
+        chain runs once per DISTINCT value and the candidates are replicated (same rows, same
+        order as separate passes would emit; STRIPENN_B200_NO_MP_DEDUP=1 disables it)."""
+        mp_all = np.ascontiguousarray(maxpixel_values, dtype=np.float64)
+        uniq, inverse = unique_maxpixels(mp_all)
+        if len(uniq) < len(mp_all) and not os.environ.get("STRIPENN_B200_NO_MP_DEDUP"):
+            out = self._extract(chrom_id, uniq, sigma, minH, maxW, bfilter, gray_variant, frame_lo, frame_hi, weights)
+            return expand_duplicate_maxpixels(out, inverse)
+        return self._extract(chrom_id, mp_all, sigma, minH, maxW, bfilter, gray_variant, frame_lo, frame_hi, weights)
+
+    def _extract(self, chrom_id, maxpixel_values, sigma, minH, maxW, bfilter, gray_variant=0,
+                 frame_lo=0, frame_hi=None, weights=None):
         mp = np.ascontiguousarray(maxpixel_values, dtype=np.float64)
         gw, radius = weights if weights is not None else gaussian_weights(sigma)
         nb = self.loaded[int(chrom_id)]["nbins"]

@@ -331,6 +331,21 @@ def test_narrow_windows_match_oracle(dev, nkeep, sigma, monkeypatch):
         assert np.array_equal(d["smoothed"], st["smoothed"]) and np.array_equal(d["mag"], st["mag"])
 
 
+def test_equal_maxpixel_values_share_one_search(dev, tiny_cm, monkeypatch):
+    """Raw-count quantiles that coincide: one image chain per distinct value, candidates replicated
+    — identical to searching every value separately (STRIPENN_B200_NO_MP_DEDUP=1)."""
+    obj, mat, names, _, _ = _obj(tiny_cm, "None", dev)
+    cid = obj.unbalLib.ensure("T1")
+    qs = [0.95, 0.9501, 0.97, 0.9701, 0.9702, 0.99]
+    mp = np.quantile(mat.positive_population("T1"), qs)
+    assert len(np.unique(mp)) < len(mp)                       # integers: neighbours coincide
+    a = dev.extract(cid, mp, 2.0, 10, 8, 3)
+    monkeypatch.setenv("STRIPENN_B200_NO_MP_DEDUP", "1")
+    b = dev.extract(cid, mp, 2.0, 10, 8, 3)
+    assert len(a) > 0 and np.array_equal(a, b)
+    assert set(np.unique(a["q"]).tolist()) == set(range(len(qs)))
+
+
 def test_load_errors(dev):
     with pytest.raises(_lib.StripennB200Error) as e:
         dev.load_chrom(0, 100, 5000, 500000, [5, 3], [6, 4], [1, 1])       # not sorted

@@ -173,3 +173,27 @@ def test_window_range_sharding_matches_reference(tiny_cm, golden_dir):
     for k in ("pos1", "pos2", "pos3", "pos4"):
         assert t[k].astype(np.int64).tolist() == g["q2_" + k].tolist(), k
     np.testing.assert_allclose(t["pvalue"].to_numpy(float), g["q2_pvalue"], rtol=1e-12)
+
+
+def test_duplicate_maxpixel_values_are_searched_once():
+    """engine.Device.extract runs the image chain once per DISTINCT maxpixel value (raw-count
+    quantiles often coincide) and replicates the candidates in snn_extract's own order."""
+    from stripenn_b200._lib import CANDIDATE_DTYPE
+    from stripenn_b200.engine import expand_duplicate_maxpixels, unique_maxpixels
+    u, inv = unique_maxpixels(np.array([2.0, 2.0, 3.0, 2.0, 5.0]))
+    assert u.tolist() == [2.0, 3.0, 5.0] and inv.tolist() == [0, 0, 1, 0, 2]
+    u, inv = unique_maxpixels(np.array([0.0, -0.0, np.nan, np.nan]))      # bitwise: +0 and -0 stay apart
+    assert len(u) == 3 and inv.tolist() == [0, 1, 2, 2]
+    u, inv = unique_maxpixels(np.array([7.5]))
+    assert u.tolist() == [7.5] and inv.tolist() == [0]
+    c = np.zeros(6, dtype=CANDIDATE_DTYPE)
+    c["q"] = [0, 0, 1, 2, 2, 2]
+    c["frame"] = [1, 4, 2, 0, 0, 3]
+    c["x"] = [10, 11, 12, 13, 14, 15]
+    e = expand_duplicate_maxpixels(c, np.array([0, 0, 1, 0, 2]))
+    assert e["q"].tolist() == [0, 0, 1, 1, 2, 3, 3, 4, 4, 4]
+    assert e["x"].tolist() == [10, 11, 10, 11, 12, 10, 11, 13, 14, 15]
+    assert e["frame"].tolist() == [1, 4, 1, 4, 2, 1, 4, 0, 0, 3]
+    # sorted like one call over all values: (q, then the per-value emission order kept)
+    assert np.all(np.diff(e["q"]) >= 0)
+    assert len(expand_duplicate_maxpixels(c[:0], np.array([0, 0]))) == 0
