@@ -293,6 +293,20 @@ class DeviceQueue:
         self._ex.shutdown(wait=True)
 
 
+def filtered_sorted(table, pvals, stripiness, pcut):
+    """``table[table.pvalue < pcut].sort_values(by=['Stripiness'], ascending=False)``
+    (stripenn.py:153-154) as ONE take instead of a boolean take plus a sorted take: pandas' nargsort
+    restated on the indices of the filtered rows (quicksort on the reversed non-NaN keys, result
+    reversed, NaN rows last) — same rows, same tie order, same index labels
+    (tests/test_host_logic.py compares with the pandas expression)."""
+    idx = np.flatnonzero(np.asarray(pvals, dtype=np.float64) < pcut)
+    key = np.asarray(stripiness, dtype=np.float64)[idx]
+    nan = np.isnan(key)
+    good = idx[~nan][::-1]
+    srt = good[key[~nan][::-1].argsort(kind="quicksort")][::-1]
+    return table.take(np.concatenate([srt, idx[nan]]))
+
+
 def run_pipeline(obj, cm, qs, chromnames, pvalue, mask, slow, comm=None, say=lambda *a, **k: None,
                  return_stages=False, group=5, ahead=2):
     """Stages 1-5 of compute (stripenn.py:120-152) for the units this rank owns (plan_units:
@@ -468,17 +482,19 @@ def run_pipeline(obj, cm, qs, chromnames, pvalue, mask, slow, comm=None, say=lam
         # (rows of one chromosome come from one rank, already in emission order)
         order = np.lexsort((np.arange(len(m["q"])), m["ck"], m["q"]))
         m = {k: v[order] for k, v in m.items()}
-        chrs = np.array(list(chromnames), dtype=object)[m["ck"]]
+        # string columns: take from a small typed array (pandas would convert an object array
+        # element by element); same dtype as a DataFrame built from Python strings
+        sdt = pd.Series(np.array(["x"], dtype=object)).dtype
+        chrs = pd.array([str(c) for c in chromnames], dtype=sdt).take(m["ck"])
         pos = m["pos"]
         with np.errstate(divide="ignore", invalid="ignore"):
             mean = m["total"] / m["h"] / m["w"]                     # getStripe.py:1097
         table = pd.DataFrame({
             'chr': chrs, 'pos1': pos[:, 0], 'pos2': pos[:, 1], 'chr2': chrs, 'pos3': pos[:, 2], 'pos4': pos[:, 3],
             'length': pos[:, 3] - pos[:, 2] + 1, 'width': pos[:, 1] - pos[:, 0] + 1, 'Mean': mean,
-            'maxpixel': np.array(labels, dtype=object)[m["q"]], 'pvalue': m["pvalue"], 'Stripiness': m["s"]},
-            copy=False)
-        filt = table[table['pvalue'] < pvalue].sort_values(by=['Stripiness'], ascending=False)
-        return table, filt
+            'maxpixel': pd.array(list(labels), dtype=sdt).take(m["q"]), 'pvalue': m["pvalue"],
+            'Stripiness': m["s"]}, copy=False)
+        return table, filtered_sorted(table, m["pvalue"], m["s"], pvalue)
     result_table, res_filter = comm.once(build) if hasattr(comm, "once") else build()
     clock.lap('tables')
     obj.last_host_ms = clock.ms

@@ -197,3 +197,22 @@ def test_duplicate_maxpixel_values_are_searched_once():
     # sorted like one call over all values: (q, then the per-value emission order kept)
     assert np.all(np.diff(e["q"]) >= 0)
     assert len(expand_duplicate_maxpixels(c[:0], np.array([0, 0]))) == 0
+
+
+def test_filtered_sorted_equals_the_pandas_expression():
+    """compute.filtered_sorted == table[table.pvalue < p].sort_values('Stripiness', ascending=False)
+    (stripenn.py:153-154), including ties, NaN scores, NaN p-values and empty results."""
+    import pandas as pd
+    rng = np.random.default_rng(5)
+    for n, cut in ((0, 0.1), (1, 0.1), (7, 0.5), (400, 0.1), (3000, 0.1), (3000, 0.0), (3000, 2.0)):
+        pv = rng.random(n) * 0.3
+        s = np.round(rng.normal(size=n), 1)            # one decimal: many ties
+        if n > 10:
+            s[::37] = np.nan
+            pv[5::91] = np.nan
+            s[3::50] = np.inf
+        t = pd.DataFrame({"chr": np.array(["c%d" % (i % 3) for i in range(n)], dtype=object),
+                          "pos1": np.arange(n), "pvalue": pv, "Stripiness": s})
+        want = t[t["pvalue"] < cut].sort_values(by=["Stripiness"], ascending=False)
+        got = cp.filtered_sorted(t, pv, s, cut)
+        pd.testing.assert_frame_equal(got, want)
