@@ -38,14 +38,44 @@ class _SeqParallel:
     def __init__(self, n_jobs=None, **_kw):
         self.n_jobs = n_jobs
 
+    # tasks that neither draw random numbers nor touch shared state: with SNN_REF_PROCS=N they run on
+    # N forked workers (same results as the sequential loop; used for the config-size goldens and
+    # by bench.py's reference arm, which is allowed all host cores)
+    PURE = ("search_frame", "iterate_idx", "calc", "available_cols")
+
     def __call__(self, tasks):
         import cloudpickle
+        tasks = list(tasks)
+        procs = int(os.environ.get("SNN_REF_PROCS", "1") or 1)
+        if procs > 1 and len(tasks) > 1 and all(getattr(t[0], "__name__", "") in self.PURE for t in tasks):
+            return _fork_map(tasks, procs)
         out = []
         for fn, args, kwargs in tasks:
             if getattr(fn, "__name__", "") == "main_null_calc":
                 fn = cloudpickle.loads(cloudpickle.dumps(fn))
             out.append(fn(*args, **kwargs))
         return out
+
+
+_FORK_TASKS = None
+
+
+def _fork_call(i):
+    fn, args, kwargs = _FORK_TASKS[i]
+    return fn(*args, **kwargs)
+
+
+def _fork_map(tasks, procs):
+    """Run closures on forked workers without pickling them: the task list is inherited through
+    fork, only indices go in and results come back."""
+    global _FORK_TASKS
+    import multiprocessing as mp
+    _FORK_TASKS = tasks
+    try:
+        with mp.get_context("fork").Pool(min(procs, len(tasks))) as pool:
+            return pool.map(_fork_call, range(len(tasks)), chunksize=1)
+    finally:
+        _FORK_TASKS = None
 
 
 _MODS = None

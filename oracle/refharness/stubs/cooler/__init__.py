@@ -10,7 +10,8 @@ behaviour):
   a bare ``"chr"`` is the whole chromosome; ``end < start`` or ``end > chromsize`` raise
   ``ValueError`` (that is why the reference clamps, getStripe.py:187-190,317-322,805-806);
 * ``balance=False`` -> raw int32 counts; ``True`` -> column ``weight``; a name -> that bins
-  column, inverted first when it is one of cooler's divisive names (KR, VC, VC_SQRT);
+  column, inverted first when it is one of cooler's divisive names
+  (`_4DN_DIVISIVE_WEIGHTS` = KR, VC, SQRT_VC);
 * dense balanced window = ``counts * np.outer(w_rows, w_cols)`` (outer product first), so a
   bin with NaN weight yields a whole NaN row and column — zeros included;
 * the matrix is symmetric: the stored upper triangle is mirrored.
@@ -25,7 +26,7 @@ import scipy.sparse as sp
 
 __version__ = "0.0-fake"
 
-_DIVISIVE = ("KR", "VC", "VC_SQRT", "SQRT_VC")
+_DIVISIVE = ("KR", "VC", "SQRT_VC")
 _CACHE = {}
 
 

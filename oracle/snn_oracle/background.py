@@ -76,6 +76,10 @@ def available_rows(mat, chrom):
     r = mat.binsize
     csize = mat.chromsize(chrom)
     itera = int(min(csize / r / 500, 25))
+    if itera == 0:
+        # fewer than 500 bins: the reference divides by np.uint64(0) (-> inf, silenced by errstate)
+        # and loops over range(0): poolsum = 0, the chromosome drops out of the sample budget
+        return 0
     unit = int(np.floor(csize / r / itera))
     tot = 0
     for it in range(itera):

@@ -4,7 +4,6 @@ output layout :149-159) on top of the B200 :class:`getStripe`.
 """
 from __future__ import annotations
 
-import errno
 import os
 import shutil
 import sys
@@ -19,39 +18,37 @@ from .contactmap import ContactMap, open_contact_map
 from .engine import Device
 
 
+def _empty_directory(path):
+    """Remove everything inside `path`, reporting (not raising) what cannot be removed."""
+    with os.scandir(path) as entries:
+        for entry in entries:
+            try:
+                if entry.is_dir(follow_symlinks=False):
+                    shutil.rmtree(entry.path)
+                else:
+                    os.unlink(entry.path)
+            except Exception as e:
+                print('Failed to delete %s with the reason: %s' % (entry.path, e))
+
+
 def makeOutDir(outdir, assume_yes=False):
-    """stripenn.py:12-42 (interactive overwrite prompt kept; ``assume_yes`` answers Y)."""
-    if outdir[-1] != '/':
-        outdir += '/'
-    if os.path.exists(outdir):
-        if assume_yes:
-            userinput = 'Y'
-        else:
-            print('\n%s exists. Do you want to remove all files and save new results in this folder? [Y/n]' % (outdir))
-            userinput = input()
-        if userinput in ('Y', 'y'):
-            print('All directories and files in %s will be deleted.' % (outdir))
-            for filename in os.listdir(outdir):
-                file_path = os.path.join(outdir, filename)
-                try:
-                    if os.path.isfile(file_path) or os.path.islink(file_path):
-                        os.unlink(file_path)
-                    elif os.path.isdir(file_path):
-                        shutil.rmtree(file_path)
-                except Exception as e:
-                    print('Failed to delete %s with the reason: %s' % (file_path, e))
-        elif userinput in ('n', 'N'):
-            print('Input another output directory. Exit.')
-            sys.exit()
-        else:
-            print('Type Y or n.\nExit.')
-            sys.exit()
-    else:
-        try:
-            os.makedirs(outdir)
-        except OSError as e:
-            if e.errno != errno.EEXIST:
-                raise
+    """Output directory handling of stripenn.py:12-42: a new directory is created; an existing one is
+    emptied after the user confirms with Y/y (``assume_yes`` answers for them), anything else ends
+    the run.  The prompt and messages are the reference's."""
+    outdir = outdir if outdir.endswith('/') else outdir + '/'
+    if not os.path.exists(outdir):
+        os.makedirs(outdir, exist_ok=True)
+        return
+    answer = 'Y'
+    if not assume_yes:
+        print('\n%s exists. Do you want to remove all files and save new results in this folder? [Y/n]' % (outdir))
+        answer = input()
+    if answer in ('Y', 'y'):
+        print('All directories and files in %s will be deleted.' % (outdir))
+        _empty_directory(outdir)
+        return
+    print('Input another output directory. Exit.' if answer in ('n', 'N') else 'Type Y or n.\nExit.')
+    sys.exit()
 
 
 def addlog(cool, out, norm, chrom, canny, minL, maxW, maxpixel, numcores, pvalue, mask, bfilter):

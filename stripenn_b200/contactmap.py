@@ -19,9 +19,12 @@ from typing import Dict, List, Optional
 
 import numpy as np
 
-# cooler interprets these weight columns as divisive unless told otherwise
-# (cooler/api.py `matrix(..., divisive_weights=None)`).
-DIVISIVE_WEIGHT_NAMES = ("KR", "VC", "VC_SQRT", "SQRT_VC")
+# cooler interprets these weight columns as divisive unless told otherwise: cooler/api.py
+# `matrix(..., divisive_weights=None)` switches on `balance in _4DN_DIVISIVE_WEIGHTS`, the set
+# {"KR", "VC", "SQRT_VC"} (4DN's hic2cool column names; restated from cooler's source from memory —
+# cooler is not installed here).  hic2cool's older "VC_SQRT" spelling, which the reference's CLI
+# help mentions, is NOT in that set: through cooler it is applied multiplicatively, so it is here.
+DIVISIVE_WEIGHT_NAMES = ("KR", "VC", "SQRT_VC")
 
 
 @dataclass

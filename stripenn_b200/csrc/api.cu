@@ -138,7 +138,6 @@ int snn_create(int device, snn_ctx** out) {
     ctx->stream = ctx->own_stream;
     if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) {
         cudaStreamDestroy(ctx->own_stream);
-    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
         delete ctx;
         return snn_cuda_fail(nullptr, e, "cudaStreamCreate");
     }
@@ -189,6 +188,7 @@ void snn_destroy(snn_ctx* ctx) {
     cudaFree(ctx->bg_sorted);
     cudaFree(ctx->bg_valid);
     cudaFree(ctx->scratch);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -235,42 +235,66 @@ static int load_common(snn_ctx* ctx, int chrom_id, int64_t nbins, int64_t binsiz
         c.count = const_cast<int32_t*>(cnt);
         c.weight = const_cast<double*>(w);
     } else {
+        // every failure below releases what was allocated so far (free_chrom takes null members)
+#define LOAD_CUDA(call)                                                  \
+    do {                                                                 \
+        cudaError_t e__ = (call);                                        \
+        if (e__ != cudaSuccess) {                                        \
+            if (alloc_done) cudaEventDestroy(alloc_done);                \
+            free_chrom(ctx, c);                                          \
+            return snn_cuda_fail(ctx, e__, #call);                       \
+        }                                                                \
+    } while (0)
+        cudaEvent_t alloc_done = nullptr;
         size_t nb = (size_t)(nnz > 0 ? nnz : 1) * sizeof(int32_t);
-        SNN_CUDA(cudaMallocAsync(&c.bin1, nb, ctx->stream));
-        SNN_CUDA(cudaMallocAsync(&c.bin2, nb, ctx->stream));
-        SNN_CUDA(cudaMallocAsync(&c.count, nb, ctx->stream));
-        if (w) SNN_CUDA(cudaMallocAsync(&c.weight, (size_t)nbins * sizeof(double), ctx->stream));
+        LOAD_CUDA(cudaMallocAsync(&c.bin1, nb, ctx->stream));
+        LOAD_CUDA(cudaMallocAsync(&c.bin2, nb, ctx->stream));
+        LOAD_CUDA(cudaMallocAsync(&c.count, nb, ctx->stream));
+        if (w) LOAD_CUDA(cudaMallocAsync(&c.weight, (size_t)nbins * sizeof(double), ctx->stream));
         cudaStream_t cs = ctx->stream;
         if (async) {
             // the allocations are ordered on the compute stream: the copy stream starts after them
-            cudaEvent_t alloc_done;
-            SNN_CUDA(cudaEventCreateWithFlags(&alloc_done, cudaEventDisableTiming));
-            SNN_CUDA(cudaEventRecord(alloc_done, ctx->stream));
-            SNN_CUDA(cudaStreamWaitEvent(ctx->copy_stream, alloc_done, 0));
+            LOAD_CUDA(cudaEventCreateWithFlags(&alloc_done, cudaEventDisableTiming));
+            LOAD_CUDA(cudaEventRecord(alloc_done, ctx->stream));
+            LOAD_CUDA(cudaStreamWaitEvent(ctx->copy_stream, alloc_done, 0));
             cudaEventDestroy(alloc_done);
+            alloc_done = nullptr;
             cs = ctx->copy_stream;
         }
         if (nnz > 0) {
-            SNN_CUDA(cudaMemcpyAsync(c.bin1, b1, nb, cudaMemcpyHostToDevice, cs));
-            SNN_CUDA(cudaMemcpyAsync(c.bin2, b2, nb, cudaMemcpyHostToDevice, cs));
-            SNN_CUDA(cudaMemcpyAsync(c.count, cnt, nb, cudaMemcpyHostToDevice, cs));
+            LOAD_CUDA(cudaMemcpyAsync(c.bin1, b1, nb, cudaMemcpyHostToDevice, cs));
+            LOAD_CUDA(cudaMemcpyAsync(c.bin2, b2, nb, cudaMemcpyHostToDevice, cs));
+            LOAD_CUDA(cudaMemcpyAsync(c.count, cnt, nb, cudaMemcpyHostToDevice, cs));
         }
-        if (w) SNN_CUDA(cudaMemcpyAsync(c.weight, w, (size_t)nbins * sizeof(double), cudaMemcpyHostToDevice, cs));
+        if (w) LOAD_CUDA(cudaMemcpyAsync(c.weight, w, (size_t)nbins * sizeof(double), cudaMemcpyHostToDevice, cs));
         if (async) {
-            SNN_CUDA(cudaEventCreateWithFlags(&c.ready, cudaEventDisableTiming));
-            SNN_CUDA(cudaEventRecord(c.ready, ctx->copy_stream));
+            LOAD_CUDA(cudaEventCreateWithFlags(&c.ready, cudaEventDisableTiming));
+            LOAD_CUDA(cudaEventRecord(c.ready, ctx->copy_stream));
             c.pending = true;
             ctx->chroms[chrom_id] = c;      // the band is built on first use (snn_materialize)
             return SNN_OK;
         }
+#undef LOAD_CUDA
     }
-    SNN_CUDA(cudaMallocAsync(&c.band, (size_t)nbins * c.bw * sizeof(double), ctx->stream));
+    {
+        cudaError_t e = cudaMallocAsync(&c.band, (size_t)nbins * c.bw * sizeof(double), ctx->stream);
+        if (e != cudaSuccess) {
+            free_chrom(ctx, c);
+            return snn_cuda_fail(ctx, e, "cudaMallocAsync(band)");
+        }
+    }
     int rc = snn_band_build(ctx, &c);
     if (rc != SNN_OK) {
         free_chrom(ctx, c);
         return rc;
     }
-    if (!device_ptrs) SNN_CUDA(cudaStreamSynchronize(ctx->stream));  // host buffers may go away
+    if (!device_ptrs) {  // host buffers may go away
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) {
+            free_chrom(ctx, c);
+            return snn_cuda_fail(ctx, e, "cudaStreamSynchronize");
+        }
+    }
     ctx->chroms[chrom_id] = c;
     return SNN_OK;
 }

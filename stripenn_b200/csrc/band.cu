@@ -51,6 +51,7 @@ __global__ void k_rowptr(const int32_t* __restrict__ b1, const int32_t* __restri
             if (t > 0 && (prev > cur || (prev == cur && b2[t - 1] >= c2))) *bad = 2;  // sorted, unique
         }
         if (cur > nbins) cur = nbins;
+        if (prev < -1) prev = -1;    // malformed input (negative bin, reported through `bad`): no write below row 0
         for (int64_t r = prev + 1; r <= cur && r <= nbins; ++r) rowptr[r] = t;
     }
 }

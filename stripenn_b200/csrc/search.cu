@@ -526,8 +526,10 @@ __global__ void k_finish(const RawCand* __restrict__ raw, const int* __restrict_
                          snn_candidate* __restrict__ out) {
     const int lane = threadIdx.x & 31;
     const int hi = min(counter[0], cap);
-    const int warp = counter[2] + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    if (warp >= hi) return;
+    // grid-stride over the batch's candidates [counter[2], counter[0]): one batch may append up to
+    // raw_cap of them, more than the launch has warps
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int warp = counter[2] + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); warp < hi; warp += nwarps) {
     const RawCand rc = raw[warp];
     const int f = rc.pass / (nq * SNN_NBRIGHT);
     const FrameInfo fi = info[f];
@@ -568,6 +570,7 @@ __global__ void k_finish(const RawCand* __restrict__ raw, const int* __restrict_
         c.pos4 = ea(rc.hi);
         c.total = s;
         out[warp] = c;
+    }
     }
 }
 

@@ -188,6 +188,11 @@ class getStripe:
         r = self.resol
         csize = self.chromnames2sizes[chrom]
         itera = int(min(csize / r / 500, 25))
+        if itera == 0:
+            # fewer than 500 bins: available_cols (getStripe.py:249-273) divides by np.uint64(0)
+            # (inf under errstate) and loops over range(0) -> poolsum 0, so the chromosome drops
+            # out of the sample budget and main_null_calc never sees it
+            return csize, 0, 0
         unit = int(np.floor(csize / r / itera))
         return csize, itera, unit
 
@@ -214,6 +219,9 @@ class getStripe:
         available_cols :249-273) and live (non-empty row of the unit's sampling window :328-331)."""
         r = self.resol
         csize, itera, unit = self._units(chrom)
+        if itera == 0:
+            nb = int(math.ceil(csize / r))
+            return [], np.zeros(nb, dtype=np.uint8), np.zeros(nb, dtype=np.uint8)
         geom = []
         for it in range(itera):
             a0, a1 = _bins_of(unit * r * it + 1, unit * r * (it + 1), csize, r)
@@ -252,6 +260,8 @@ class getStripe:
         chromosome — what every loky task of the reference sees with -n >= 2."""
         prng = random.Random(self.seed)
         csize, itera, unit = self._units(chrom)
+        if itera == 0:
+            return np.zeros((0, 6), dtype=np.int32)
         if not hasattr(self, "_flag_cache"):
             self._flag_cache = {}
         if chrom not in self._flag_cache:

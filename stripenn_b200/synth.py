@@ -152,6 +152,8 @@ def config_chroms(cfg: str) -> Tuple[List[Tuple[str, int]], int, bool]:
         return [("U1", 2600 * 1000 - 321)], 1000, False
     if cfg == "tiny10k":  # 10 kb bins: bs = 5, odd block split (bu = 2, bd = 3), balanced
         return [("V1", 2100 * 10000 - 4321), ("V2", 1300 * 10000 - 99)], 10000, True
+    if cfg == "mid":  # config-size parity fixture: a 12,050-bin KR chromosome + one shorter than 500 bins
+        return [("chrL", 12050 * 5000 - 777), ("chrS", 450 * 5000 - 13)], 5000, True
     if cfg == "tiny2":  # two small chromosomes, balanced
         return [("chrA", 2400 * 5000 - 1234), ("chrB", 1500 * 5000 - 77)], 5000, True
     raise ValueError("unknown config %r" % cfg)

@@ -45,7 +45,7 @@ def test_from_cooler_round_trip(cooler_module, tiny2_cm):
         assert np.array_equal(got.count, want.count)
         for col in tiny2_cm.weights:
             assert np.array_equal(cm.weights[col][name], tiny2_cm.weights[col][name], equal_nan=True)
-            # divisive columns (KR, VC, VC_SQRT) are inverted, `weight` is not (cooler's rule)
+            # divisive columns (KR, VC, SQRT_VC) are inverted, `weight` is not (cooler's rule)
             a, b = cm.weight_vector(name, col), tiny2_cm.weight_vector(name, col)
             assert np.array_equal(a, b, equal_nan=True)
 

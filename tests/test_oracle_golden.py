@@ -58,6 +58,30 @@ def test_tiny2_kr_compute_matches_reference(tiny2_cm, golden_dir):
         np.testing.assert_allclose(st["EV"][c], g["EV_" + c], rtol=1e-12)
 
 
+def test_mid_kr_compute_matches_reference(golden_dir):
+    """Config-size pin (tests/golden/make_golden_mid.py): a 12,050-bin KR chromosome, five maxpixel
+    quantiles, plus a chromosome shorter than 500 bins that nulldist must drop from the sample
+    budget (itera = 0, getStripe.py:249-283) — end tables and every stage product of the
+    UNMODIFIED reference."""
+    g = np.load(os.path.join(golden_dir, "mid_compute.npz"))
+    cm = synth.make_config("mid")
+    unf, fil, st = driver.compute(cm, norm="KR", maxpixel="0.95,0.96,0.97,0.98,0.99", return_stages=True)
+    _cmp_tables(unf, g, "unf_")
+    _cmp_tables(fil, g, "fil_")
+    for c in ("chrL", "chrS"):
+        np.testing.assert_allclose(st["MP"][c], g["MP_" + c], rtol=1e-15)
+        np.testing.assert_allclose(st["EV"][c], g["EV_" + c], rtol=1e-12)
+    for name, t in zip(BG, st["bg"]):
+        assert list(t.shape) == g["bg_%s_shape" % name].tolist()
+        # differences of block means: near-zero entries carry the summation-order noise of the means
+        np.testing.assert_allclose(t[:, ::25], g["bg_" + name], rtol=1e-12, atol=1e-12, equal_nan=True)
+        assert np.array_equal(np.isnan(t).sum(axis=1), g["bg_%s_nnan" % name])
+    for i, t in enumerate(st["per_q"]):
+        for k in ("pos1", "pos2", "pos3", "pos4", "num", "x", "y", "h", "w"):
+            assert list(t[k]) == g["q%d_%s" % (i, k)].tolist(), (i, k)
+        np.testing.assert_allclose(np.array(t["pvalue"], float), g["q%d_pvalue" % i], rtol=1e-12)
+
+
 def test_tiny2_score_matches_reference(tiny2_cm, golden_dir):
     g = np.load(os.path.join(golden_dir, "tiny2_score.npz"))
     table = {"chr": g["chr"].tolist(), "pos1": g["pos1"].tolist(), "pos2": g["pos2"].tolist(),
