@@ -7,17 +7,21 @@ scored — extract + score + pvalue — at 1/2/4/8 B200 next to the CPU path).
 
 A step = one pass of stages 1-5 of `compute` (maxpixel quantiles, expected values, background
 sampling, candidate search over every 400-bin window x 5 maxpixel values x 6 brightness passes,
-p-values, dedup, stripiness) over one synthetic genome.  Workload = BASELINE.json configs[1]:
-synthetic mouse whole genome at 10 kb (chr1-19+X, 263,389 bins, 1,329 windows), --norm None,
+p-values, dedup, stripiness) over one synthetic genome.  Default workload = BASELINE.json
+configs[2], the largest configuration that fits one GPU and the north star's target: synthetic
+human whole genome at 5 kb (hg38 chr1-22+X; chrY is dropped by the reference's chromosome
+filter), KR-balanced with NaN-weight bins, 606,219 bins searched, 3,044 windows,
 -m 0.95,0.96,0.97,0.98,0.99.  Mpixels = Q * sum over windows of (end-start+1)^2 / 1e6
- = 1,041 Mpixels per genome.
+ = 2,410 Mpixels per genome.  --config cfg2 / cfg1 / cfg4 select the others.
 
 `value`: pixels resident in HBM (COO arrays on the device) when the timed region starts;
 `e2e`: the same step through the public API with pinned HOST buffers, H2D copies of the pixel
 tables and D2H of candidates/results inside the timed region.
-Multi-GPU (`--scaling weak`, default): one genome per rank (independent samples, different
-seeds), no collective.  `--scaling strong`: ONE genome sharded by chromosome (LPT) with the two
-host-side exchanges of the background tables (stripenn_b200.compute.run_pipeline).
+Multi-GPU (`--scaling strong`, the default): ONE genome sharded over the GPUs by chromosome —
+stripenn_b200.compute.plan_units, longest first, over-sized chromosomes cut into window ranges —
+with `--streams` host threads per GPU; the exchanges are typed (comm.py): availability counts,
+ONE NCCL all-gather of the background columns between the GPUs, final rows.  `--scaling weak`:
+one genome per rank (independent samples, different seeds), no exchange.
 """
 from __future__ import annotations
 
@@ -46,8 +50,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--config", default="cfg2")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--config", default="cfg3")
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"])
     ap.add_argument("--streams", type=int, default=2, help="host threads (contexts/streams) feeding each GPU")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -335,13 +339,15 @@ def native_arm(args):
     chroms, binsize, balanced = synth.config_chroms(args.config)
     names = [c[0] for c in chroms]
     sizes = [c[1] for c in chroms]
+    nstreams = max(1, args.streams)                 # host threads (virtual ranks) per GPU
     if strong:
-        # the same plan run_pipeline derives: whole chromosomes longest-first, window ranges of an
-        # over-sized chromosome (single-chromosome configs) spread over several ranks
+        # the same plan run_pipeline derives: world x nstreams virtual ranks, whole chromosomes
+        # longest-first, window ranges of an over-sized chromosome spread over several of them;
+        # virtual rank v lives in process v // nstreams
         shell = synth.make_map(chroms, binsize, only=[])
         f_names, f_sizes, _, _ = cp.compute_chromosomes(shell, ["all"])
-        units = cp.plan_units(f_names, f_sizes, binsize, world)
-        mine = [c for c in names if any(u["chrom"] == c and u["rank"] == rank for u in units)]
+        units = cp.plan_units(f_names, f_sizes, binsize, world * nstreams, selected=f_names)
+        mine = [c for c in names if any(u["chrom"] == c and u["rank"] // nstreams == rank for u in units)]
         seed = synth.DEFAULT_SEED
     else:
         mine = names
@@ -352,14 +358,13 @@ def native_arm(args):
     norm = "KR" if balanced else "None"
     bal = cp.resolve_norm(cm, norm, "compute", False)
     all_names, all_sizes, chromnames, chromsizes = cp.compute_chromosomes(cm, ["all"])
-    if strong:   # pixels of the windows THIS rank searches (a cut chromosome is shared)
+    if strong:   # pixels of the windows THIS process searches (a cut chromosome is shared)
         mpix_rank = NQ * sum(synth.frame_pixels_range(cm.nbins(u["chrom"]), u["lo"], u["hi"]) for u in units
-                             if u["rank"] == rank and u["chrom"] in chromnames) / 1e6
+                             if u["search"] and u["rank"] // nstreams == rank and u["chrom"] in chromnames) / 1e6
     else:
         mpix_rank = genome_mpixels(cm, [c for c in chromnames if c in cm.chroms])
     nnz_rank = sum(cm.chroms[c].nnz for c in cm.chroms)
 
-    nstreams = 1 if strong else max(1, args.streams)
     stream = torch.cuda.current_stream()
     devs, tstreams = [], []
     for k in range(nstreams):
@@ -369,7 +374,17 @@ def native_arm(args):
         devs.append(d)
         tstreams.append(ts)
     dev = devs[0]
-    comm = cp.TorchComm() if strong else None
+    # communicators, one per host thread: threads of a process meet in shared memory; with several
+    # processes thread 0 of each talks to the others through torch.distributed (NCCL)
+    if strong:
+        comms = cp.HybridComm.group(nstreams, cp.TorchComm())
+        thread_of = lambda c: c.tc.rank
+    elif nstreams > 1:
+        comms = cp.ThreadComm.group(nstreams)
+        thread_of = lambda c: c.rank
+    else:
+        comms = [cp.LocalComm()]
+        thread_of = lambda c: 0
 
     # resident copies (HBM) and pinned host copies of the pixel tables
     resident, pinned = {}, {}
@@ -420,9 +435,9 @@ def native_arm(args):
 
     def step(matrix_cls):
         matrix_cls_now[0] = matrix_cls
-        if nstreams == 1:
-            return one_rank(dev, comm)
-        return cp.run_threads(lambda tc: one_rank(devs[tc.rank], tc), nstreams)[0]
+        if len(comms) == 1:
+            return one_rank(dev, comms[0])
+        return cp.run_threads(lambda c: one_rank(devs[thread_of(c)], c), comms)[0]
 
     def timed(matrix_cls, k, w):
         for _ in range(w):
@@ -479,6 +494,14 @@ def native_arm(args):
     value = mpix_total * steps / (ms_dev / 1000.0)
     e2e = mpix_total * steps / (ms_e2e / 1000.0)
 
+    shard_text = ""
+    if strong:
+        per = {}
+        for u in units:
+            if u["search"]:
+                per.setdefault(u["rank"] // nstreams, []).append(
+                    u["chrom"] if u["npieces"] == 1 else "%s[%d:%d]" % (u["chrom"], u["lo"], u["hi"]))
+        shard_text = "; ".join("gpu%d: %s" % (g, ",".join(v)) for g, v in sorted(per.items()))
     if rank == 0:
         peak, peak_src = measured_peaks()
         launches = int(sum(v["launches"] for v in stages.values()))
@@ -530,7 +553,9 @@ def native_arm(args):
                                         mpix_rank if not strong else mpix_total, norm, QS),
                            "host_threads_per_gpu": nstreams,
                            "parallelism": ("1 genome per GPU (independent samples)" if not strong else
-                                           "1 genome sharded by chromosome (LPT) over %d GPUs" % world),
+                                           "1 genome sharded over %d GPUs x %d host threads: plan_units (chromosomes "
+                                           "longest-first, over-sized ones cut into window ranges): %s" %
+                                           (world, nstreams, shard_text)),
                            "l2": "inputs larger than L2 (pixel tables %.0f MB per genome)" % (nnz_rank * 12 / 1e6),
                            "stripes_found": int(len(unf)), "stripes_filtered": int(len(fil)),
                            "generate_s": round(gen_s, 1)},

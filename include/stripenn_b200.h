@@ -154,6 +154,26 @@ int snn_background(snn_ctx* ctx, int chrom_id, int64_t nsamp, const int32_t* spe
  * used by snn_score's p-values; they are sorted per distance on the device. */
 int snn_set_background(snn_ctx* ctx, int64_t ncol, const double* tables);
 
+/* Device-resident form of the two calls above, for the sharded pipeline (each GPU
+ * computes the background columns of its own chromosomes, all GPUs need all columns before any
+ * p-value): the columns never visit the host.
+ * snn_background_dev writes sample k of the call to SAMPLE-MAJOR slot (slot0 + k) of a device
+ * buffer: d_buf[(slot0 + k) * 4 * SNN_NDIST + table * SNN_NDIST + distance].  The buffer may be any
+ * device allocation of this process (snn_device_alloc, or memory a collective library gathers
+ * into: one ncclAllGather of the slot ranges completes it on every GPU).  The call returns after
+ * the kernel has finished (the buffer can be handed to another stream).
+ * snn_set_background_dev installs the tables from such a buffer: column t of every table is slot
+ * slots[t] (host array of ncol int32; NULL = slots 0..ncol-1).  The p-values depend on the multiset
+ * of each row only, so the order of the slots is free. */
+int snn_background_dev(snn_ctx* ctx, int chrom_id, int64_t nsamp, const int32_t* spec, double* d_buf,
+                       int64_t slot0);
+int snn_set_background_dev(snn_ctx* ctx, int64_t ncol, const int32_t* slots, const double* d_buf);
+/* Plain device memory for such buffers (and tests): allocate / release / copy to the host
+ * (synchronises the context's stream first). */
+int snn_device_alloc(snn_ctx* ctx, int64_t bytes, void** d_out);
+int snn_device_free(snn_ctx* ctx, void* d_ptr);
+int snn_device_read(snn_ctx* ctx, void* dst_host, const void* d_src, int64_t bytes);
+
 /* ---- a5-a14: getStripe.extract/search_frame/StripeSearch (getStripe.py:790-1114) for the
  * windows [frame_lo, frame_hi) of one chromosome and ALL maxpixel values at once.
  * gauss_w = the 2*radius+1 weights of scipy's _gaussian_kernel1d(sigma) (computed by the

@@ -67,6 +67,11 @@ SIGNATURES = {
     "snn_row_flags": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P]),
     "snn_background": (C.c_int, [_P, C.c_int, C.c_int64, _P, _P]),
     "snn_set_background": (C.c_int, [_P, C.c_int64, _P]),
+    "snn_background_dev": (C.c_int, [_P, C.c_int, C.c_int64, _P, _P, C.c_int64]),
+    "snn_set_background_dev": (C.c_int, [_P, C.c_int64, _P, _P]),
+    "snn_device_alloc": (C.c_int, [_P, C.c_int64, C.POINTER(_P)]),
+    "snn_device_free": (C.c_int, [_P, _P]),
+    "snn_device_read": (C.c_int, [_P, _P, _P, C.c_int64]),
     "snn_extract": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int,
                               C.c_int, C.c_int, C.c_int, _P, C.c_int64, _i64p]),
     "snn_debug_stages": (C.c_int, [_P, C.c_int, C.c_double, _P, C.c_int, C.c_int, C.c_int, C.c_int,

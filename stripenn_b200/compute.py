@@ -129,99 +129,9 @@ class StageClock:
         self.t = now
 
 
-class LocalComm:
-    """Single-process stand-in for the two host-side exchanges of the sharded pipeline."""
-    rank = 0
-    world = 1
-
-    def all_gather(self, obj):
-        return [obj]
-
-
-class TorchComm:
-    """torch.distributed (nccl or gloo) as the exchange: the payloads are the per-chromosome
-    availability counts, the background columns (12.8 MB in total) and the candidate tables —
-    host objects, gathered with all_gather_object.  No data-path collective exists (SURVEY.md
-    §8e): every (chromosome, window) unit is independent."""
-
-    def __init__(self):
-        import torch.distributed as dist
-        self.dist = dist
-        self.rank = dist.get_rank()
-        self.world = dist.get_world_size()
-
-    def all_gather(self, obj):
-        out = [None] * self.world
-        self.dist.all_gather_object(out, obj)
-        return out
-
-
-class ThreadComm:
-    """Several host threads feeding ONE GPU through separate contexts/streams ("virtual ranks"):
-    while one thread post-processes its chromosome on the host (table assembly, dedup), the
-    kernels of the others keep the GPU busy.  Same exchange points as the multi-GPU pipeline,
-    implemented with a barrier.  Create with ThreadComm.group(k)."""
-
-    def __init__(self, rank, world, shared):
-        self.rank, self.world, self._sh = rank, world, shared
-
-    @classmethod
-    def group(cls, world):
-        import threading
-        shared = {"slots": [None] * world, "barrier": threading.Barrier(world)}
-        return [cls(r, world, shared) for r in range(world)]
-
-    def all_gather(self, obj):
-        sh = self._sh
-        sh["slots"][self.rank] = obj
-        sh["barrier"].wait()
-        out = list(sh["slots"])
-        sh["barrier"].wait()
-        return out
-
-    def once(self, fn):
-        """fn() evaluated by rank 0 only; every rank gets the same object (threads share memory,
-        and the GIL would serialise identical copies of the work anyway)."""
-        sh = self._sh
-        if self.rank == 0:
-            try:
-                sh["once"] = (fn(), None)
-            except BaseException as e:  # noqa: BLE001 - re-raised on every rank
-                sh["once"] = (None, e)
-        sh["barrier"].wait()
-        val, err = sh["once"]
-        sh["barrier"].wait()
-        if err is not None:
-            raise err
-        return val
-
-
-def run_threads(fn, world):
-    """Run fn(comm) on `world` host threads (one ThreadComm each); returns the per-rank results
-    and re-raises the first exception."""
-    import threading
-    comms = ThreadComm.group(world)
-    res, err = [None] * world, [None] * world
-
-    def work(i):
-        try:
-            res[i] = fn(comms[i])
-        except BaseException as e:  # noqa: BLE001 - re-raised below
-            err[i] = e
-            comms[i]._sh["barrier"].abort()
-
-    ts = [threading.Thread(target=work, args=(i,)) for i in range(world)]
-    for t in ts:
-        t.start()
-    for t in ts:
-        t.join()
-    for e in err:
-        if e is not None and not isinstance(e, threading.BrokenBarrierError):
-            raise e
-    for e in err:
-        if e is not None:
-            raise e
-    return res
+# communicators of the sharded pipeline (re-exported: tests and bench.py use them from here)
+from .comm import (HybridComm, LocalComm, ThreadComm, TorchComm, background_layout,  # noqa: E402,F401
+                   run_threads)
 
 
 def lpt_partition(names, sizes, world):
@@ -237,32 +147,54 @@ def lpt_partition(names, sizes, world):
     return owner
 
 
-def plan_units(names, sizes_bp, binsize, world, split=True):
+def plan_units(names, sizes_bp, binsize, world, split=True, selected=None):
     """Work units of the sharded pipeline: whole chromosomes, except that a chromosome holding
-    more than 1.25 x its fair share of the bins (total / world) is cut into window ranges
+    more than 1.25 x its fair share of the SEARCHED bins (total / world) is cut into window ranges
     (getStripe.py:841-842: windows of one chromosome are independent tasks) — a single-chromosome
-    run (BASELINE configs 1 and 4) then still uses every GPU.  Units are assigned longest first
-    (work ~ windows).  Returns a list of dicts {chrom, piece, npieces, lo, hi, rank}; piece 0's
-    rank is the chromosome's PRIMARY (it runs the chromosome-wide stages and the host steps)."""
+    run (BASELINE configs 1 and 4, or `-k chr1` on a whole-genome file) then still uses every GPU.
+    Units are assigned longest first (work ~ windows).  `selected` = the -k chromosomes (default:
+    all): only they are searched and only they count for the fair share; the other chromosomes of
+    the file still need an owner for the background stage (getStripe.py:242,276 samples every
+    chromosome) and are dealt out afterwards as units without windows (search = False).
+    Returns a list of dicts {chrom, piece, npieces, lo, hi, rank, search}; piece 0's rank is the
+    chromosome's PRIMARY (it runs the chromosome-wide stages and the host steps)."""
     import math
+    sel = set(names if selected is None else selected)
     nb = [int(math.ceil(int(s) / binsize)) for s in sizes_bp]
-    total = max(sum(nb), 1)
+    total = max(sum(nb[i] for i, c in enumerate(names) if c in sel), 1)
     fair = total / max(world, 1)
-    units = []
+    units, rest = [], []
     for i, c in enumerate(names):
+        if c not in sel:
+            rest.append(dict(chrom=c, piece=0, npieces=1, lo=0, hi=0, order=i, rank=0, search=False))
+            continue
         nfr = max(1, int(math.ceil(nb[i] / 200)))
         k = 1
         if split and world > 1 and nb[i] > 1.25 * fair:
             k = max(1, min(world, nfr, int(round(nb[i] / fair))))
         for p in range(k):
             lo, hi = (nfr * p) // k, (nfr * (p + 1)) // k
-            units.append(dict(chrom=c, piece=p, npieces=k, lo=lo, hi=hi, order=i, rank=0))
+            units.append(dict(chrom=c, piece=p, npieces=k, lo=lo, hi=hi, order=i, rank=0, search=True))
     load = [0] * world
     for u in sorted(units, key=lambda u: (-(u["hi"] - u["lo"]), u["order"], u["piece"])):
         r = min(range(world), key=lambda k: (load[k], k))
         u["rank"] = r
         load[r] += u["hi"] - u["lo"]
-    return units
+    # background-only chromosomes: their cost (row flags + a share of 1000 samples) is small next to
+    # a search; spread them by size on counters of their own
+    bload = [0] * world
+    for u in sorted(rest, key=lambda u: (-nb[u["order"]], u["order"])):
+        r = min(range(world), key=lambda k: (bload[k], load[k], k))
+        u["rank"] = r
+        bload[r] += nb[u["order"]]
+    return sorted(units + rest, key=lambda u: (u["order"], u["piece"]))
+
+
+# fixed-dtype records the ranks exchange (never pickled objects)
+FINAL_DTYPE = np.dtype([("q", "<i8"), ("ck", "<i8"), ("pos1", "<i8"), ("pos2", "<i8"), ("pos3", "<i8"),
+                        ("pos4", "<i8"), ("total", "<f8"), ("h", "<i8"), ("w", "<i8"), ("pvalue", "<f8"),
+                        ("s", "<f8")])
+PIECE_DTYPE = np.dtype([("ck", "<i4"), ("piece", "<i4"), ("rec", gs.CANDIDATE_DTYPE)])
 
 
 def make_object(cm, bal, dev, all_names, all_sizes, chromnames, chromsizes, minL, maxW, canny, numcores,
@@ -306,10 +238,18 @@ def filtered_sorted(table, pvals, stripiness, pcut):
 
 def run_pipeline(obj, cm, qs, chromnames, pvalue, mask, slow, comm=None, say=lambda *a, **k: None,
                  return_stages=False, group=5, ahead=2):
-    """Stages 1-5 of compute (stripenn.py:120-152) for the units this rank owns (plan_units:
-    whole chromosomes, window ranges of over-sized ones), with the two host-side exchanges the
-    background needs (+ one for the window ranges of cut chromosomes).  `obj` is a
-    getStripe-shaped object.
+    """Stages 1-5 of compute (stripenn.py:120-152) for the units this (virtual) rank owns
+    (plan_units: whole chromosomes, window ranges of over-sized ones).  `obj` is a getStripe-shaped
+    object, `comm` a communicator of stripenn_b200.comm.
+
+    Exchanges between ranks (typed arrays, see comm.py): the availability counts (one int64 per
+    background chromosome); the background columns — device to device: every GPU's k_background
+    writes into its slot range of one buffer, one in-place all-gather completes it everywhere,
+    k_bg_sort reads it (with a Device that lacks the device-resident calls, e.g. the oracle-backed
+    test double, the columns travel as float64 arrays instead); the raw candidates of a chromosome
+    that was cut into window ranges; the final rows.  The searches of every rank start before the
+    first exchange and keep the GPU busy through all of them — only the p-values wait for the
+    background.
 
     Every device call goes through one DeviceQueue in an order that keeps the GPU busy while this
     thread does the host steps: maxpixel values, expected values and row flags of all
@@ -322,17 +262,20 @@ def run_pipeline(obj, cm, qs, chromnames, pvalue, mask, slow, comm=None, say=lam
     comm = comm or LocalComm()
     clock = StageClock()
     all_names = list(obj.all_chromnames)
-    units = plan_units(all_names, obj.all_chromsizes, obj.resol, comm.world)
+    chromnames = list(chromnames)
+    units = plan_units(all_names, obj.all_chromsizes, obj.resol, comm.world, selected=chromnames)
     primary = {u["chrom"]: u["rank"] for u in units if u["piece"] == 0}
     mine = lambda c: primary.get(c, 0) == comm.rank
     my_sel = [c for c in chromnames if mine(c)]
     # search units of this rank, in -k order; a split chromosome's windows are searched by several
     # ranks (each holds the chromosome and derives the same maxpixel values) and merged by its primary
-    my_units = sorted((u for u in units if u["rank"] == comm.rank and u["chrom"] in chromnames),
-                      key=lambda u: (list(chromnames).index(u["chrom"]), u["piece"]))
+    my_units = sorted((u for u in units if u["search"] and u["rank"] == comm.rank),
+                      key=lambda u: (chromnames.index(u["chrom"]), u["piece"]))
     split_chroms = [c for c in chromnames if any(u["chrom"] == c and u["npieces"] > 1 for u in units)]
     quant_sel = list(dict.fromkeys(my_sel + [u["chrom"] for u in my_units]))
     labels = [str(q * 100) + '%' for q in qs]
+    cidx = {c: i for i, c in enumerate(chromnames)}
+    dev_bg = hasattr(obj.dev, "background_dev")       # device-resident background columns
     dq = DeviceQueue()
     try:
         say('1. Maximum pixel value calculation ...')
@@ -367,21 +310,46 @@ def run_pipeline(obj, cm, qs, chromnames, pvalue, mask, slow, comm=None, say=lam
         f_avail = dq.submit(obj.available_counts, [c for c in names2 if mine(c)])
         for _ in range(ahead - 1):
             submit_search()
-        avail = {}
-        for part in comm.all_gather(f_avail.result()):
-            avail.update(part)
+        # exchange 1: availability counts, one int64 per background chromosome (-1 = not mine)
+        got = f_avail.result()
+        counts = np.array([got.get(c, -1) for c in names2], dtype=np.int64)
+        merged = np.max(np.stack(comm.all_gather_arrays(counts)), axis=0) if names2 else counts
+        avail = {c: int(merged[i]) for i, c in enumerate(names2)}
         clock.lap('quantiles+expected+flags')
         names2b, budget = obj.sample_budget(names2, avail)
+        n_of = {c: int(budget[names2b.index(c)]) for c in names2b}
+        ncol = sum(n_of.values())
         # sampling plan on the host while the first searches run; its device part goes in next
-        f_cols = {c: dq.submit(obj.background_columns, c, obj.plan_chromosome(c, int(budget[names2b.index(c)])))
-                  for c in names2b if mine(c)}
-        submit_search()
-        allcols = {}
-        for part in comm.all_gather({c: f.result() for c, f in f_cols.items()}):
-            allcols.update(part)
-        full = np.concatenate([allcols[c] for c in names2b], axis=2) if names2b else np.zeros((4, 400, 0))
-        bg = (full[0], full[1], full[2], full[3])
-        f_bg = dq.submit(obj._install_background, bg)
+        bg_host = None
+        if dev_bg:
+            slot0, per_proc, slots = background_layout(names2b, n_of, primary, comm.tpp, comm.nproc)
+            d_buf = comm.bg_buffer(obj.dev, per_proc * comm.nproc)
+            f_cols = [dq.submit(obj.background_columns_dev, c, obj.plan_chromosome(c, n_of[c]), d_buf, slot0[c],
+                                n_of[c]) for c in names2b if mine(c)]
+            submit_search()
+            for f in f_cols:
+                f.result()
+            comm.bg_exchange(per_proc)                  # exchange 2: one all-gather between the GPUs
+            f_bg = dq.submit(obj.install_background_dev, d_buf, ncol, slots)
+            if return_stages:
+                raw_bg = dq.submit(obj.dev.device_read, d_buf, (per_proc * comm.nproc, 4, 400)).result()
+                full = (np.concatenate([raw_bg[slot0[c]:slot0[c] + n_of[c]] for c in names2b]).transpose(1, 2, 0)
+                        if names2b else np.zeros((4, 400, 0)))
+                bg_host = tuple(np.ascontiguousarray(full[t]) for t in range(4))
+        else:
+            f_cols = {c: dq.submit(obj.background_columns, c, obj.plan_chromosome(c, n_of[c]))
+                      for c in names2b if mine(c)}
+            submit_search()
+            # exchange 2 (host form): sample-major float64 rows, chromosome index in front
+            rows = [np.concatenate([np.full((f.result().shape[2], 1), names2b.index(c), dtype=np.float64),
+                                    f.result().transpose(2, 0, 1).reshape(-1, 1600)], axis=1)
+                    for c, f in f_cols.items()]
+            mine_rows = np.concatenate(rows) if rows else np.zeros((0, 1601))
+            allrows = np.concatenate(comm.all_gather_arrays(mine_rows))
+            allrows = allrows[np.argsort(allrows[:, 0], kind="stable")]        # names2b order, draws in order
+            full = allrows[:, 1:].reshape(-1, 4, 400).transpose(1, 2, 0) if len(allrows) else np.zeros((4, 400, 0))
+            bg_host = tuple(np.ascontiguousarray(full[t]) for t in range(4))
+            f_bg = dq.submit(obj._install_background, bg_host)
         clock.lap('background')
         MP = {c: f_mp[c].result()[c] for c in quant_sel}
         EV = {c: f_ev[c].result() for c in my_sel}
@@ -392,7 +360,7 @@ def run_pipeline(obj, cm, qs, chromnames, pvalue, mask, slow, comm=None, say=lam
             if pend:
                 grp = list(pend)
                 del pend[:]
-                f_pv.append((grp, dq.submit(obj.candidate_pvalues, grp, bg)))
+                f_pv.append((grp, dq.submit(obj.candidate_pvalues, grp)))
         def take(c, raw):
             cand, pos = obj.prune_candidates(raw)
             if len(cand):
@@ -401,7 +369,7 @@ def run_pipeline(obj, cm, qs, chromnames, pvalue, mask, slow, comm=None, say=lam
             if len(pend) >= group:
                 flush_group()
         i = 0
-        pieces = {}
+        pieces = []
         while i < len(f_cand):
             u, f = f_cand[i]
             i += 1
@@ -410,18 +378,19 @@ def run_pipeline(obj, cm, qs, chromnames, pvalue, mask, slow, comm=None, say=lam
             if u["npieces"] == 1:
                 take(u["chrom"], raw)
             else:
-                pieces[(u["chrom"], u["piece"])] = raw
+                rec = np.empty(len(raw), dtype=PIECE_DTYPE)
+                rec["ck"], rec["piece"], rec["rec"] = cidx[u["chrom"]], u["piece"], raw
+                pieces.append(rec)
         if split_chroms:
-            # third host-side exchange (only when a chromosome was cut): the window ranges of a
-            # chromosome meet at its primary, in window order, before the cross-window pruning
-            gathered = {}
-            for part in comm.all_gather(pieces):
-                gathered.update(part)
+            # exchange 3 (only when a chromosome was cut): the window ranges of a chromosome meet
+            # at its primary, in window order, before the cross-window pruning
+            sent = np.concatenate(pieces) if pieces else np.zeros(0, dtype=PIECE_DTYPE)
+            gathered = np.concatenate(comm.all_gather_arrays(sent))
             for c in split_chroms:
                 if not mine(c):
                     continue
-                k = max(u["npieces"] for u in units if u["chrom"] == c)
-                raw = np.concatenate([gathered[(c, p)] for p in range(k)])
+                g = gathered[gathered["ck"] == cidx[c]]
+                raw = g["rec"][np.argsort(g["piece"], kind="stable")]
                 take(c, raw[np.argsort(raw["q"], kind="stable")])   # (q, window, ...) order of one call
         flush_group()
         f_bg.result()
@@ -451,53 +420,51 @@ def run_pipeline(obj, cm, qs, chromnames, pvalue, mask, slow, comm=None, say=lam
         clock.lap('stripiness')
     finally:
         dq.close()
-    # ---- result tables.  Ranks exchange plain arrays (maxpixel index, chromosome index, bp
-    # coordinates, window sum, size, p-value, Stripiness); the DataFrames are built ONCE from the
-    # merged arrays (by one thread when the ranks are host threads of one process).
+    # ---- result tables.  Exchange 4: fixed-dtype rows (maxpixel index, chromosome index, bp
+    # coordinates, window sum, size, p-value, Stripiness); the DataFrames are built ONCE per process
+    # from the merged rows.
     final = [r for r in final if len(r[1])]
-    cidx = {c: i for i, c in enumerate(chromnames)}
-    if final:
-        allc = np.concatenate([r[1] for r in final])
-        part = dict(q=allc["q"].astype(np.int64),
-                    ck=np.concatenate([np.full(len(r[1]), cidx[r[0]], dtype=np.int64) for r in final]),
-                    pos=np.stack([allc["pos1"], allc["pos2"], allc["pos3"], allc["pos4"]], axis=1),
-                    total=allc["total"].astype(np.float64), h=allc["h"].astype(np.int64),
-                    w=allc["w"].astype(np.int64), pvalue=np.concatenate([r[2] for r in final]),
-                    s=np.concatenate([r[3] for r in final]))
-    else:
-        part = None
-    parts = [p for p in (comm.all_gather(part) if comm.world > 1 else [part]) if p is not None]
+    part = np.zeros(sum(len(r[1]) for r in final), dtype=FINAL_DTYPE)
+    off = 0
+    for c, cand, p, st in final:
+        v = part[off:off + len(cand)]
+        v["q"], v["ck"] = cand["q"], cidx[c]
+        for k in ("pos1", "pos2", "pos3", "pos4", "total", "h", "w"):
+            v[k] = cand[k]
+        v["pvalue"], v["s"] = p, st
+        off += len(cand)
+    parts = comm.all_gather_arrays(part)
 
     def build():
-        if not parts:
+        m = np.concatenate(parts)
+        if not len(m):
             empty = pd.DataFrame(columns=[k for k in gs.RESULT_COLUMNS if k not in
                                           ('total', 'num', 'start', 'end', 'x', 'y', 'h', 'w', 'medpixel')] +
                                  ['pvalue', 'Stripiness'])
             return empty, empty[empty['pvalue'] < pvalue]
-        m = {k: np.concatenate([p[k] for p in parts]) for k in parts[0]}
         # reference row order: maxpixel-major, then chromosomes in -k order, then emission order
         # (rows of one chromosome come from one rank, already in emission order)
-        order = np.lexsort((np.arange(len(m["q"])), m["ck"], m["q"]))
-        m = {k: v[order] for k, v in m.items()}
+        m = m[np.lexsort((np.arange(len(m)), m["ck"], m["q"]))]
         # string columns: take from a small typed array (pandas would convert an object array
         # element by element); same dtype as a DataFrame built from Python strings
         sdt = pd.Series(np.array(["x"], dtype=object)).dtype
         chrs = pd.array([str(c) for c in chromnames], dtype=sdt).take(m["ck"])
-        pos = m["pos"]
         with np.errstate(divide="ignore", invalid="ignore"):
             mean = m["total"] / m["h"] / m["w"]                     # getStripe.py:1097
+        pv, st = np.ascontiguousarray(m["pvalue"]), np.ascontiguousarray(m["s"])
         table = pd.DataFrame({
-            'chr': chrs, 'pos1': pos[:, 0], 'pos2': pos[:, 1], 'chr2': chrs, 'pos3': pos[:, 2], 'pos4': pos[:, 3],
-            'length': pos[:, 3] - pos[:, 2] + 1, 'width': pos[:, 1] - pos[:, 0] + 1, 'Mean': mean,
-            'maxpixel': pd.array(list(labels), dtype=sdt).take(m["q"]), 'pvalue': m["pvalue"],
-            'Stripiness': m["s"]}, copy=False)
-        return table, filtered_sorted(table, m["pvalue"], m["s"], pvalue)
-    result_table, res_filter = comm.once(build) if hasattr(comm, "once") else build()
+            'chr': chrs, 'pos1': np.ascontiguousarray(m["pos1"]), 'pos2': np.ascontiguousarray(m["pos2"]),
+            'chr2': chrs, 'pos3': np.ascontiguousarray(m["pos3"]), 'pos4': np.ascontiguousarray(m["pos4"]),
+            'length': m["pos4"] - m["pos3"] + 1, 'width': m["pos2"] - m["pos1"] + 1, 'Mean': mean,
+            'maxpixel': pd.array(list(labels), dtype=sdt).take(m["q"]), 'pvalue': pv,
+            'Stripiness': st}, copy=False)
+        return table, filtered_sorted(table, pv, st, pvalue)
+    result_table, res_filter = comm.once(build)
     clock.lap('tables')
     obj.last_host_ms = clock.ms
     if return_stages:
         per_q = obj.candidate_tables(kept, np.concatenate(all_pv) if all_pv else np.zeros(0), qs)
-        return result_table, res_filter, dict(MP=MP, EV=EV, bg=bg, per_q=per_q)
+        return result_table, res_filter, dict(MP=MP, EV=EV, bg=bg_host, per_q=per_q)
     return result_table, res_filter
 
 

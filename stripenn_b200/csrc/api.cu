@@ -423,6 +423,52 @@ int snn_set_background(snn_ctx* ctx, int64_t ncol, const double* tables) {
     return snn_set_background_impl(ctx, ncol, tables);
 }
 
+int snn_background_dev(snn_ctx* ctx, int chrom_id, int64_t nsamp, const int32_t* spec, double* d_buf,
+                       int64_t slot0) {
+    GET_CHROM(c);
+    if (nsamp < 0 || slot0 < 0 || (nsamp > 0 && (!spec || !d_buf)))
+        return snn_fail(ctx, SNN_EINVAL, "snn_background_dev: bad arguments");
+    if (nsamp == 0) return SNN_OK;
+    return snn_background_dev_impl(ctx, c, nsamp, spec, d_buf, slot0);
+}
+
+int snn_set_background_dev(snn_ctx* ctx, int64_t ncol, const int32_t* slots, const double* d_buf) {
+    if (!ctx) return snn_fail(nullptr, SNN_EINVAL, "ctx is NULL");
+    if (ncol < 0 || (ncol > 0 && !d_buf))
+        return snn_fail(ctx, SNN_EINVAL, "snn_set_background_dev: bad arguments");
+    for (int64_t t = 0; slots && t < ncol; ++t)
+        if (slots[t] < 0) return snn_fail(ctx, SNN_EINVAL, "snn_set_background_dev: negative slot %lld", (long long)t);
+    SNN_CUDA(cudaSetDevice(ctx->device));
+    return snn_set_background_dev_impl(ctx, ncol, slots, d_buf);
+}
+
+int snn_device_alloc(snn_ctx* ctx, int64_t bytes, void** d_out) {
+    if (!ctx) return snn_fail(nullptr, SNN_EINVAL, "ctx is NULL");
+    if (!d_out || bytes < 0) return snn_fail(ctx, SNN_EINVAL, "snn_device_alloc: bad arguments");
+    *d_out = nullptr;
+    SNN_CUDA(cudaSetDevice(ctx->device));
+    SNN_CUDA(cudaMalloc(d_out, (size_t)(bytes > 0 ? bytes : 1)));
+    return SNN_OK;
+}
+
+int snn_device_free(snn_ctx* ctx, void* d_ptr) {
+    if (!ctx) return snn_fail(nullptr, SNN_EINVAL, "ctx is NULL");
+    SNN_CUDA(cudaSetDevice(ctx->device));
+    SNN_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (d_ptr) SNN_CUDA(cudaFree(d_ptr));
+    return SNN_OK;
+}
+
+int snn_device_read(snn_ctx* ctx, void* dst_host, const void* d_src, int64_t bytes) {
+    if (!ctx) return snn_fail(nullptr, SNN_EINVAL, "ctx is NULL");
+    if (bytes < 0 || (bytes > 0 && (!dst_host || !d_src)))
+        return snn_fail(ctx, SNN_EINVAL, "snn_device_read: bad arguments");
+    SNN_CUDA(cudaSetDevice(ctx->device));
+    SNN_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (bytes) SNN_CUDA(cudaMemcpy(dst_host, d_src, (size_t)bytes, cudaMemcpyDeviceToHost));
+    return SNN_OK;
+}
+
 int snn_extract(snn_ctx* ctx, int chrom_id, int nq, const double* mp, const double* gw, int radius,
                 int minH, int maxW, int bfilter, int gray_variant, int frame_lo, int frame_hi,
                 snn_candidate* out, int64_t cap, int64_t* n_out) {

@@ -24,8 +24,12 @@ __device__ __forceinline__ double block_mean(const MatView& m, int64_t i0, int64
     return s / (double)(nr * nc);
 }
 
+// sample_major = 0: out[table][distance][sample] (snn_background, what the host API returns);
+// sample_major = 1: out[slot0 + sample][table][distance] (snn_background_dev: the columns of one
+// chromosome are a contiguous slot range, the unit the GPUs exchange)
 __global__ void __launch_bounds__(256) k_background(MatView m, const int32_t* __restrict__ spec, int64_t nsamp,
-                                                    int bs, int bu, int bd, double* __restrict__ out) {
+                                                    int bs, int bu, int bd, double* __restrict__ out,
+                                                    int sample_major, int64_t slot0) {
     const int64_t k = blockIdx.x;
     const int32_t* sp = spec + k * 6;
     const int64_t i0 = sp[0], i1 = sp[1], j0 = sp[2], j1 = sp[3], x = sp[4], shift = sp[5];
@@ -44,45 +48,71 @@ __global__ void __launch_bounds__(256) k_background(MatView m, const int32_t* __
         const double mid = block_mean(m, i0, j0, ra[1], rb[1], ca, cb);
         const double bot = block_mean(m, i0, j0, ra[2], rb[2], ca, cb);
         // tables: 0 bgleft_up, 1 bgright_up, 2 bgleft_down, 3 bgright_down
-        out[((int64_t)(down ? 2 : 0) * SNN_NDIST + j) * nsamp + k] = mid - top;
-        out[((int64_t)(down ? 3 : 1) * SNN_NDIST + j) * nsamp + k] = mid - bot;
+        if (sample_major) {
+            double* o = out + (slot0 + k) * (4 * SNN_NDIST);
+            o[(down ? 2 : 0) * SNN_NDIST + j] = mid - top;
+            o[(down ? 3 : 1) * SNN_NDIST + j] = mid - bot;
+        } else {
+            out[((int64_t)(down ? 2 : 0) * SNN_NDIST + j) * nsamp + k] = mid - top;
+            out[((int64_t)(down ? 3 : 1) * SNN_NDIST + j) * nsamp + k] = mid - bot;
+        }
     }
 }
 
-int snn_background_impl(snn_ctx* ctx, SnnChrom* c, int64_t nsamp, const int32_t* spec, double* out) {
+static int check_specs(snn_ctx* ctx, SnnChrom* c, int64_t nsamp, const int32_t* spec) {
     for (int64_t k = 0; k < nsamp; ++k) {
         const int32_t* sp = spec + k * 6;
         if (sp[0] < 0 || sp[1] > c->nbins || sp[2] < 0 || sp[3] > c->nbins || sp[1] < sp[0] || sp[3] < sp[2])
             return snn_fail(ctx, SNN_EINVAL, "snn_background: sample %lld has a window outside the chromosome",
                             (long long)k);
     }
+    return SNN_OK;
+}
+
+// d_ext = null: table-major result copied to the host array `out`; else sample-major into d_ext
+static int background_run(snn_ctx* ctx, SnnChrom* c, int64_t nsamp, const int32_t* spec, double* out,
+                          double* d_ext, int64_t slot0) {
+    int rc = check_specs(ctx, c, nsamp, spec);
+    if (rc) return rc;
     const double bsf = 50000.0 / (double)c->binsize;  // getStripe.py:287-290
     const int bs = (int)bsf;
     const int bu = (int)floor(bsf / 2.0);
     const int bd = (int)(bsf - floor(bsf / 2.0));
     void* scratch = nullptr;
     size_t sbytes = ((size_t)nsamp * 6 * sizeof(int32_t) + 255) & ~(size_t)255;
-    size_t obytes = (size_t)4 * SNN_NDIST * nsamp * sizeof(double);
-    int rc = snn_scratch(ctx, sbytes + obytes, &scratch);
+    size_t obytes = d_ext ? 0 : (size_t)4 * SNN_NDIST * nsamp * sizeof(double);
+    rc = snn_scratch(ctx, sbytes + obytes, &scratch);
     if (rc) return rc;
     int32_t* dspec = (int32_t*)scratch;
-    double* dout = (double*)((char*)scratch + sbytes);
+    double* dout = d_ext ? d_ext : (double*)((char*)scratch + sbytes);
     SNN_CUDA(cudaMemcpyAsync(dspec, spec, (size_t)nsamp * 6 * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     {
         SnnScope scope(ctx, ST_BACKGROUND, 1);
-        k_background<<<(unsigned)nsamp, 256, 0, ctx->stream>>>(snn_view(c), dspec, nsamp, bs, bu, bd, dout);
+        k_background<<<(unsigned)nsamp, 256, 0, ctx->stream>>>(snn_view(c), dspec, nsamp, bs, bu, bd, dout,
+                                                                d_ext ? 1 : 0, slot0);
         SNN_LAUNCH_CHECK("k_background");
     }
-    SNN_CUDA(cudaMemcpyAsync(out, dout, obytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (!d_ext) SNN_CUDA(cudaMemcpyAsync(out, dout, obytes, cudaMemcpyDeviceToHost, ctx->stream));
     SNN_CUDA(cudaStreamSynchronize(ctx->stream));
     return SNN_OK;
+}
+
+int snn_background_impl(snn_ctx* ctx, SnnChrom* c, int64_t nsamp, const int32_t* spec, double* out) {
+    return background_run(ctx, c, nsamp, spec, out, nullptr, 0);
+}
+
+int snn_background_dev_impl(snn_ctx* ctx, SnnChrom* c, int64_t nsamp, const int32_t* spec, double* d_buf,
+                            int64_t slot0) {
+    return background_run(ctx, c, nsamp, spec, nullptr, d_buf, slot0);
 }
 
 // ---- sorted copy of the genome-wide tables for the p-value kernel ---------------------------------
 // One CTA per (table, distance) row: bitonic sort in shared memory with NaNs sent to the end;
 // #(bg >= v) then becomes n_valid - lower_bound(v).
+// slots = null: in[row][col] (the host tables); else sample-major in[slots[col]][row]
 __global__ void __launch_bounds__(512) k_bg_sort(const double* __restrict__ in, int64_t ncol, int npow2,
-                                                 double* __restrict__ out, int32_t* __restrict__ nvalid) {
+                                                 double* __restrict__ out, int32_t* __restrict__ nvalid,
+                                                 const int32_t* __restrict__ slots, int use_slots) {
     extern __shared__ double s[];
     const int64_t row = blockIdx.x;
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
@@ -91,7 +121,7 @@ __global__ void __launch_bounds__(512) k_bg_sort(const double* __restrict__ in, 
         double v = inf;
         bool pad = true;
         if (t < ncol) {
-            v = in[row * ncol + t];
+            v = use_slots ? in[(int64_t)(slots ? slots[t] : t) * (4 * SNN_NDIST) + row] : in[row * ncol + t];
             if (v == v) { ++local; pad = false; }
         }
         // NaNs and padding sort last: keep real +inf values ahead of them with a flag trick —
@@ -120,7 +150,10 @@ __global__ void __launch_bounds__(512) k_bg_sort(const double* __restrict__ in, 
     if (threadIdx.x == 0) nvalid[row] = total;
 }
 
-int snn_set_background_impl(snn_ctx* ctx, int64_t ncol, const double* tables) {
+// tables != null: host tables [4][400][ncol]; else sample-major device buffer d_buf with the host
+// slot list `slots` (null = identity)
+static int set_background_run(snn_ctx* ctx, int64_t ncol, const double* tables, const int32_t* slots,
+                              const double* d_buf) {
     if (ncol != ctx->bg_ncol) {   // keep the buffers when the shape repeats (every compute step)
         cudaFree(ctx->bg_sorted);
         cudaFree(ctx->bg_valid);
@@ -137,23 +170,39 @@ int snn_set_background_impl(snn_ctx* ctx, int64_t ncol, const double* tables) {
     const int64_t rows = 4 * SNN_NDIST;
     size_t bytes = (size_t)rows * ncol * sizeof(double);
     void* scratch = nullptr;
-    int rc = snn_scratch(ctx, bytes, &scratch);
+    int rc = snn_scratch(ctx, tables ? bytes : (size_t)ncol * sizeof(int32_t) + 256, &scratch);
     if (rc) return rc;
     if (!ctx->bg_sorted) {
         SNN_CUDA(cudaMalloc(&ctx->bg_sorted, bytes));
         SNN_CUDA(cudaMalloc(&ctx->bg_valid, rows * sizeof(int32_t)));
     }
-    SNN_CUDA(cudaMemcpyAsync(scratch, tables, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    const double* src = d_buf;
+    const int32_t* dslots = nullptr;
+    if (tables) {
+        SNN_CUDA(cudaMemcpyAsync(scratch, tables, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        src = (const double*)scratch;
+    } else if (slots) {
+        SNN_CUDA(cudaMemcpyAsync(scratch, slots, (size_t)ncol * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+        dslots = (const int32_t*)scratch;
+    }
     size_t smem = (size_t)npow2 * sizeof(double);
     // constant across calls (host threads may race on the attribute otherwise)
     SNN_CUDA(cudaFuncSetAttribute(k_bg_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     {
         SnnScope scope(ctx, ST_BGSORT, 1);
-        k_bg_sort<<<(unsigned)rows, 512, smem, ctx->stream>>>((const double*)scratch, ncol, npow2, ctx->bg_sorted,
-                                                              ctx->bg_valid);
+        k_bg_sort<<<(unsigned)rows, 512, smem, ctx->stream>>>(src, ncol, npow2, ctx->bg_sorted, ctx->bg_valid, dslots,
+                                                              tables ? 0 : 1);
         SNN_LAUNCH_CHECK("k_bg_sort");
     }
     SNN_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->bg_ncol = ncol;
     return SNN_OK;
+}
+
+int snn_set_background_impl(snn_ctx* ctx, int64_t ncol, const double* tables) {
+    return set_background_run(ctx, ncol, tables, nullptr, nullptr);
+}
+
+int snn_set_background_dev_impl(snn_ctx* ctx, int64_t ncol, const int32_t* slots, const double* d_buf) {
+    return set_background_run(ctx, ncol, nullptr, slots, d_buf);
 }

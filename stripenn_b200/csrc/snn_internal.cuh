@@ -199,6 +199,9 @@ int snn_row_flags_impl(snn_ctx* ctx, SnnChrom* c, int nunits, const int64_t* geo
                        uint8_t* live);
 int snn_background_impl(snn_ctx* ctx, SnnChrom* c, int64_t nsamp, const int32_t* spec, double* out);
 int snn_set_background_impl(snn_ctx* ctx, int64_t ncol, const double* tables);
+int snn_background_dev_impl(snn_ctx* ctx, SnnChrom* c, int64_t nsamp, const int32_t* spec, double* d_buf,
+                            int64_t slot0);
+int snn_set_background_dev_impl(snn_ctx* ctx, int64_t ncol, const int32_t* slots, const double* d_buf);
 int snn_extract_impl(snn_ctx* ctx, SnnChrom* c, int nq, const double* mp, const double* gw, int radius,
                      int minH, int maxW, int bfilter, int gray_variant, int frame_lo, int frame_hi,
                      snn_candidate* out, int64_t cap, int64_t* n_out);

@@ -222,6 +222,41 @@ class Device:
         check(self.lib.snn_set_background(self.h, int(t.shape[2]), ptr(t)), self.h)
         self.h2d_bytes += t.nbytes
 
+    # device-resident background (sharded pipeline: the columns never visit the host)
+    BG_SLOT = 4 * NDIST          # doubles per sample slot
+
+    def device_alloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        check(self.lib.snn_device_alloc(self.h, int(nbytes), C.byref(p)), self.h)
+        return int(p.value or 0)
+
+    def device_free(self, d_ptr: int):
+        check(self.lib.snn_device_free(self.h, C.c_void_p(int(d_ptr))), self.h)
+
+    def device_read(self, d_ptr: int, shape, dtype=np.float64):
+        out = np.empty(shape, dtype=dtype)
+        check(self.lib.snn_device_read(self.h, ptr(out), C.c_void_p(int(d_ptr)), out.nbytes), self.h)
+        self.d2h_bytes += out.nbytes
+        return out
+
+    def background_dev(self, chrom_id, spec, d_buf: int, slot0: int) -> int:
+        """snn_background_dev: the samples go to slots slot0.. of the device buffer (sample-major);
+        returns the number of samples written."""
+        s = np.ascontiguousarray(spec, dtype=np.int32).reshape(-1, 6)
+        n = int(s.shape[0])
+        if n:
+            check(self.lib.snn_background_dev(self.h, int(chrom_id), n, ptr(s), C.c_void_p(int(d_buf)), int(slot0)),
+                  self.h)
+            self.h2d_bytes += s.nbytes
+        return n
+
+    def set_background_dev(self, d_buf: int, ncol: int, slots=None):
+        sl = None if slots is None else np.ascontiguousarray(slots, dtype=np.int32)
+        if sl is not None and sl.shape[0] != int(ncol):
+            raise ValueError("set_background_dev: %d slots for %d columns" % (sl.shape[0], ncol))
+        check(self.lib.snn_set_background_dev(self.h, int(ncol), ptr(sl), C.c_void_p(int(d_buf))), self.h)
+        self.h2d_bytes += 0 if sl is None else sl.nbytes
+
     # ------------------------------------------------------------------ a5-a14
     def extract(self, chrom_id, maxpixel_values, sigma, minH, maxW, bfilter, gray_variant=0,
                 frame_lo=0, frame_hi=None, weights=None):

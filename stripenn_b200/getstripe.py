@@ -18,6 +18,7 @@ import numpy as np
 import pandas as pd
 
 from .contactmap import ContactMap
+from ._lib import CANDIDATE_DTYPE  # noqa: F401 (re-exported)
 from .engine import Device, gaussian_weights, remove_redundant_mask  # noqa: F401 (re-exported)
 
 NDIST = 400
@@ -311,6 +312,21 @@ class getStripe:
         cid = self.unbalLib.ensure(chrom)
         return self.dev.background(cid, spec)
 
+    def background_columns_dev(self, chrom, spec, d_buf, slot0, expect):
+        """The same tables written to slots slot0.. of a device buffer (snn_background_dev): the
+        form the sharded pipeline exchanges between GPUs.  `expect` = the sample budget the slot
+        layout was derived from."""
+        if len(spec) != expect:
+            raise RuntimeError("chromosome %s: sampling plan has %d samples, budget %d" % (chrom, len(spec), expect))
+        cid = self.unbalLib.ensure(chrom)
+        return self.dev.background_dev(cid, spec, d_buf, slot0)
+
+    def install_background_dev(self, d_buf, ncol, slots):
+        """Genome-wide tables from a device buffer (snn_set_background_dev)."""
+        self.dev.set_background_dev(d_buf, ncol, slots)
+        self._bg_installed = ("dev", int(d_buf), int(ncol))
+        self._bg_keepalive = None
+
     def nulldist(self):
         """getStripe.py:238-499 -> bgleft_up, bgright_up, bgleft_down, bgright_down."""
         names2, plans = self.plan_samples()
@@ -369,12 +385,14 @@ class getStripe:
         keep = remove_redundant_mask(cand["q"], frame, pos, hh, ww, None, "size")   # one group per q
         return cand[keep], pos[keep]
 
-    def candidate_pvalues(self, kept, bg):
+    def candidate_pvalues(self, kept, bg=None):
         """p-values of every chromosome's candidates in ONE device call (all chromosomes are
-        resident).  kept = [(chrom, records, positions)] with non-empty records."""
+        resident).  kept = [(chrom, records, positions)] with non-empty records; bg = the four host
+        tables, or None when the background is already installed."""
         if not kept:
             return np.zeros(0)
-        self._install_background(bg)
+        if bg is not None:
+            self._install_background(bg)
         ids = np.array([self.unbalLib.ensure(k[0]) for k in kept], dtype=np.int32)
         index = np.concatenate([np.full(len(k[1]), i, dtype=np.int32) for i, k in enumerate(kept)])
         allpos = np.concatenate([k[2] for k in kept])
