@@ -48,6 +48,8 @@ int snn_scratch(snn_ctx* ctx, size_t bytes, void** out) {
         ctx->scratch = nullptr;
         ctx->scratch_bytes = 0;
         SNN_CUDA(cudaMalloc(&ctx->scratch, bytes));
+        // image buffers are read a little beyond what was written (discarded results): never NaN bits
+        SNN_CUDA(cudaMemsetAsync(ctx->scratch, 0, bytes, ctx->stream));
         ctx->scratch_bytes = bytes;
     }
     *out = ctx->scratch;

@@ -123,17 +123,6 @@ __device__ __forceinline__ int reflect101(int i, int n) {
     return i;
 }
 
-__device__ __forceinline__ double adjust_pixel(double D, double M, double b, double k) {
-    double blue = (255.0 * (M - D)) / M;          // getStripe.py:889  255*(M - submat)/M
-    if (blue < 0.0) blue = 0.0;                   // :890
-    double g = blue / 255.0;                      // :894  blue / 255
-    g = fmin(fmax(g, 0.0), 1.0);                  // :895  np.clip (NaN passes through)
-    if (g != g) return 0.0;                       // imBrightness3D leaves NaN cells at 0
-    if (g <= 0.0) return 0.0;                     // ImageProcessing.py:17-23
-    if (g > b) return 1.0;
-    return k * g;
-}
-
 __global__ void __launch_bounds__(256) k_gray(const double* __restrict__ Dc_all, const FrameInfo* __restrict__ info,
                                               GrayParams P, float* __restrict__ gray_all) {
     extern __shared__ double adj[];
@@ -157,7 +146,7 @@ __global__ void __launch_bounds__(256) k_gray(const double* __restrict__ Dc_all,
         if (r < S + bf && c < S + bf) {
             r = reflect101(r, S);
             c = reflect101(c, S);
-            if (r >= 0 && r < S && c >= 0 && c < S) v = adjust_pixel(Dc[r * SNN_SMAX + c], M, b, k);
+            if (r >= 0 && r < S && c >= 0 && c < S) v = snn_adjust_pixel(Dc[r * SNN_SMAX + c], M, b, k);
         }
         adj[t] = v;
     }
@@ -416,7 +405,7 @@ int snn_image_chain(snn_ctx* ctx, SnnChrom* c, const ExtractPlan& pl, int frame0
     const int npass = nf * pl.nq * SNN_NBRIGHT;
     const int ppf = pl.nq * SNN_NBRIGHT;
     {
-        SnnScope scope(ctx, ST_FRAME, 4);
+        SnnScope scope(ctx, ST_FRAME, 3);
         SNN_CUDA(cudaMemsetAsync(pl.flags, 0, (size_t)nf * SNN_SMAX * sizeof(int), ctx->stream));
         k_frame_flags<<<dim3(nf, (SNN_SMAX + FF_SLAB - 1) / FF_SLAB), 256, 0, ctx->stream>>>(c->band, c->nbins, c->bw,
                                                                                            frame0, pl.flags);
@@ -426,10 +415,15 @@ int snn_image_chain(snn_ctx* ctx, SnnChrom* c, const ExtractPlan& pl, int frame0
         k_frame_gather<<<dim3(nf, (SNN_SMAX + FG_ROWS - 1) / FG_ROWS), FG_ROWS * 32, 0, ctx->stream>>>(
             c->band, c->bw, pl.info, pl.nz, pl.Dc);
         SNN_LAUNCH_CHECK("k_frame_gather");
+    }
+    const bool generic = ctx->force_generic;
+    if (!generic && snn_fused_supported(pl))          // two fused kernels, no bleed-over image (image_fused.cu)
+        return snn_launch_fused(ctx, pl, npass, ppf, mag_dbg != nullptr, pl.bufA, pl.bufC, mag_dbg);
+    {
+        SnnScope scope(ctx, ST_FRAME, 1);
         k_bleed<<<dim3(13, 13, nf), dim3(32, 8), 0, ctx->stream>>>(pl.info, pl.gauss, pl.bleed);
         SNN_LAUNCH_CHECK("k_bleed");
     }
-    const bool generic = ctx->force_generic;
     {
         SnnScope scope(ctx, ST_GRAY, 1);
         if (!generic && pl.gray.bf == 3) {

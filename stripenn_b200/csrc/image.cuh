@@ -53,6 +53,9 @@ struct ExtractPlan {
     int raw_cap;      // capacity of raw / cand (candidates of one snn_extract call)
     int batch_cap;    // upper bound of the candidates one batch can add
     snn_candidate* cand;  // finished candidates (device)
+    // fused path (image_fused.cu): TMA tensor map of bufB (a CUtensorMap, kept opaque here)
+    alignas(64) unsigned char tmap[128];
+    bool tmap_ok;
 };
 
 int snn_launch_gray6(snn_ctx* ctx, const ExtractPlan& pl, int nf);
@@ -60,3 +63,24 @@ bool snn_gauss_fast_supported(int radius);
 int snn_launch_gauss_fast(snn_ctx* ctx, const ExtractPlan& pl, int npass, int ppf);
 int snn_launch_sobel_nms2(snn_ctx* ctx, const ExtractPlan& pl, int npass, int ppf, float* mag_dbg);
 int snn_image_chain(snn_ctx* ctx, SnnChrom* c, const ExtractPlan& pl, int frame0, int nf, float* mag_dbg);
+
+// ---- fused image chain (image_fused.cu)
+bool snn_fused_supported(const ExtractPlan& pl);
+int snn_fused_make_tmap(snn_ctx* ctx, ExtractPlan* pl, size_t npass);
+int snn_launch_fused(snn_ctx* ctx, const ExtractPlan& pl, int npass, int ppf, bool dbg, float* gray_dbg, float* sm_dbg,
+                     float* mag_dbg);
+
+#ifdef __CUDACC__
+// One pixel of the saturated, brightness-adjusted image, the reference's literal operation order
+// (getStripe.py:889-895, ImageProcessing.py:17-23)
+__device__ __forceinline__ double snn_adjust_pixel(double D, double M, double b, double k) {
+    double blue = (255.0 * (M - D)) / M;          // getStripe.py:889  255*(M - submat)/M
+    if (blue < 0.0) blue = 0.0;                   // :890
+    double g = blue / 255.0;                      // :894  blue / 255
+    g = fmin(fmax(g, 0.0), 1.0);                  // :895  np.clip (NaN passes through)
+    if (g != g) return 0.0;                       // imBrightness3D leaves NaN cells at 0
+    if (g <= 0.0) return 0.0;                     // ImageProcessing.py:17-23
+    if (g > b) return 1.0;
+    return k * g;
+}
+#endif

@@ -657,6 +657,8 @@ static int make_plan(snn_ctx* ctx, ExtractPlan* pl, int nq, const double* mp, co
     pl->counter = (int*)(b + o_cnt);
     pl->raw = (RawCand*)(b + o_raw);
     pl->cand = (snn_candidate*)(b + o_cand);
+    rc = snn_fused_make_tmap(ctx, pl, npass);
+    if (rc) pl->tmap_ok = false;      // the unfused kernels take over (snn_fused_supported)
     if (dbg) {
         *dbgE = (uint32_t*)(b + o_dE);
         *dbgV = (uint32_t*)(b + o_dV);

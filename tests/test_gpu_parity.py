@@ -600,3 +600,31 @@ def test_stripes_at_chromosome_ends_match_oracle(dev, cfg, norm):
     assert np.isfinite(want["pvalue"]).sum() > len(pos) // 2
     for k in got:
         np.testing.assert_allclose(got[k], want[k], rtol=RTOL, atol=0, equal_nan=True, err_msg=k)
+
+
+def test_fused_chain_equals_unfused_kernels(dev, tiny2_cm, monkeypatch):
+    """The default image chain is two fused kernels (image_fused.cu: k_gray_gv, k_gh_nms with TMA
+    tiles); SNN_FUSED=0 selects the five unfused kernels of image_fast.cu.  Every per-pass product
+    (gray, smoothed, magnitude, masks) of every window and brightness of a chromosome, and the
+    candidates of the whole chromosome, must be the same bits — with the tie check on and with the
+    literal form forced for every output."""
+    obj, mat, names, _, _ = _obj(tiny2_cm, "KR", dev)
+    cid = obj.unbalLib.ensure("chrA")
+    mp = np.quantile(mat.positive_population("chrA"), [0.95, 0.97, 0.99])
+    nwin = pl.n_frames(mat.nbins("chrA"))
+    monkeypatch.setenv("SNN_FUSED", "1")
+    fused = {(idx, b): dev.debug_stages(cid, mp[1], 2.0, 3, idx, b) for idx in range(nwin) for b in range(6)}
+    cand = dev.extract(cid, mp, 2.0, 10, 8, 3)
+    monkeypatch.setenv("SNN_GAUSS_TIE_K", str(0x10000000))
+    for (idx, b) in ((0, 0), (3, 2), (nwin - 1, 5)):
+        lit = dev.debug_stages(cid, mp[1], 2.0, 3, idx, b)
+        for k in ("gray", "smoothed", "mag", "low", "edges", "vert"):
+            assert np.array_equal(fused[idx, b][k], lit[k]), (idx, b, k, "literal")
+    monkeypatch.delenv("SNN_GAUSS_TIE_K")
+    monkeypatch.setenv("SNN_FUSED", "0")
+    for (idx, b), x in fused.items():
+        y = dev.debug_stages(cid, mp[1], 2.0, 3, idx, b)
+        assert x["S"] == y["S"]
+        for k in ("gray", "smoothed", "mag", "low", "edges", "vert"):
+            assert np.array_equal(x[k], y[k]), (idx, b, k)
+    assert len(cand) > 0 and np.array_equal(dev.extract(cid, mp, 2.0, 10, 8, 3), cand)
