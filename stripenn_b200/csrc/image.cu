@@ -417,12 +417,24 @@ int snn_image_chain(snn_ctx* ctx, SnnChrom* c, const ExtractPlan& pl, int frame0
         SNN_LAUNCH_CHECK("k_frame_gather");
     }
     const bool generic = ctx->force_generic;
-    if (!generic && snn_fused_supported(pl))          // two fused kernels, no bleed-over image (image_fused.cu)
-        return snn_launch_fused(ctx, pl, npass, ppf, mag_dbg != nullptr, pl.bufA, pl.bufC, mag_dbg);
+    const int fused = generic ? 0 : snn_fused_mode(pl);
+    if (fused == 2)          // two fused kernels, no bleed-over image (image_fused.cu)
+        return snn_launch_fused(ctx, pl, npass, ppf, mag_dbg != nullptr, pl.bufA, pl.bufC, mag_dbg, true, true);
     {
         SnnScope scope(ctx, ST_FRAME, 1);
         k_bleed<<<dim3(13, 13, nf), dim3(32, 8), 0, ctx->stream>>>(pl.info, pl.gauss, pl.bleed);
         SNN_LAUNCH_CHECK("k_bleed");
+    }
+    if (fused == 1) {        // gray + axis-0 Gaussian fused; axis 1 and Sobel/NMS as separate kernels
+        int rc = snn_launch_fused(ctx, pl, npass, ppf, mag_dbg != nullptr, pl.bufA, nullptr, nullptr, true, false);
+        if (rc) return rc;
+        {
+            SnnScope scope(ctx, ST_GAUSS, 1);
+            rc = snn_launch_gauss_fast(ctx, pl, npass, ppf, true);
+            if (rc) return rc;
+        }
+        SnnScope scope(ctx, ST_NMS, 1);
+        return snn_launch_sobel_nms2(ctx, pl, npass, ppf, mag_dbg);
     }
     {
         SnnScope scope(ctx, ST_GRAY, 1);

@@ -60,15 +60,15 @@ struct ExtractPlan {
 
 int snn_launch_gray6(snn_ctx* ctx, const ExtractPlan& pl, int nf);
 bool snn_gauss_fast_supported(int radius);
-int snn_launch_gauss_fast(snn_ctx* ctx, const ExtractPlan& pl, int npass, int ppf);
+int snn_launch_gauss_fast(snn_ctx* ctx, const ExtractPlan& pl, int npass, int ppf, bool axis1_only = false);
 int snn_launch_sobel_nms2(snn_ctx* ctx, const ExtractPlan& pl, int npass, int ppf, float* mag_dbg);
 int snn_image_chain(snn_ctx* ctx, SnnChrom* c, const ExtractPlan& pl, int frame0, int nf, float* mag_dbg);
 
 // ---- fused image chain (image_fused.cu)
-bool snn_fused_supported(const ExtractPlan& pl);
+int snn_fused_mode(const ExtractPlan& pl);
 int snn_fused_make_tmap(snn_ctx* ctx, ExtractPlan* pl, size_t npass);
 int snn_launch_fused(snn_ctx* ctx, const ExtractPlan& pl, int npass, int ppf, bool dbg, float* gray_dbg, float* sm_dbg,
-                     float* mag_dbg);
+                     float* mag_dbg, bool part_a, bool part_b);
 
 #ifdef __CUDACC__
 // One pixel of the saturated, brightness-adjusted image, the reference's literal operation order

@@ -982,13 +982,14 @@ int snn_launch_gray6(snn_ctx* ctx, const ExtractPlan& pl, int nf) {
 bool snn_gauss_fast_supported(int radius) { return radius == 8 || radius == 10 || radius == 6; }
 
 template <int R>
-static int launch_gauss_march(snn_ctx* ctx, const ExtractPlan& pl, int npass, int ppf) {
+static int launch_gauss_march(snn_ctx* ctx, const ExtractPlan& pl, int npass, int ppf, bool axis1_only) {
     constexpr int TC = 2 * (2 * R + 1) * GH_WARPS;
     const int nseg = (SNN_SMAX + GV_SEG - 1) / GV_SEG;
     const char* tk = getenv("SNN_GAUSS_TIE_K");     // read per launch: the tests switch it
     const unsigned tieK = tk ? (unsigned)strtoul(tk, nullptr, 0) : 64u;
-    k_gauss_vm<R><<<dim3(13, (nseg + 3) / 4, npass), dim3(32, 4), 0, ctx->stream>>>(pl.bufA, pl.info, ppf, pl.gauss,
-                                                                                   tieK, pl.bufB);
+    if (!axis1_only)
+        k_gauss_vm<R><<<dim3(13, (nseg + 3) / 4, npass), dim3(32, 4), 0, ctx->stream>>>(pl.bufA, pl.info, ppf, pl.gauss,
+                                                                                       tieK, pl.bufB);
     static_assert(SNN_SMAX % (HD_SEG * HD_WARPS) == 0, "k_gauss_hd tiles must cover the row pitch exactly");
     const char* hd = getenv("SNN_GAUSS_HD");        // A/B switch: direct-store axis-1 kernel (default sigma only)
     if constexpr (2 * R + 1 <= HD_N && 2 * R + 1 > HD_N - 4) {
@@ -1006,13 +1007,13 @@ static int launch_gauss_march(snn_ctx* ctx, const ExtractPlan& pl, int npass, in
     return SNN_OK;
 }
 
-int snn_launch_gauss_fast(snn_ctx* ctx, const ExtractPlan& pl, int npass, int ppf) {
+int snn_launch_gauss_fast(snn_ctx* ctx, const ExtractPlan& pl, int npass, int ppf, bool axis1_only) {
     static const bool old8 = getenv("SNN_GAUSS8") != nullptr;   // A/B switch for the 8-outputs-per-thread kernels
-    if (!old8) {
+    if (!old8 || axis1_only) {
         switch (pl.gauss.radius) {
-            case 8: return launch_gauss_march<8>(ctx, pl, npass, ppf);
-            case 10: return launch_gauss_march<10>(ctx, pl, npass, ppf);
-            default: return launch_gauss_march<6>(ctx, pl, npass, ppf);
+            case 8: return launch_gauss_march<8>(ctx, pl, npass, ppf, axis1_only);
+            case 10: return launch_gauss_march<10>(ctx, pl, npass, ppf, axis1_only);
+            default: return launch_gauss_march<6>(ctx, pl, npass, ppf, axis1_only);
         }
     }
     const dim3 gv(13, (SNN_SMAX + 8 * NOUT - 1) / (8 * NOUT), npass), bv(32, 8);

@@ -602,17 +602,19 @@ def test_stripes_at_chromosome_ends_match_oracle(dev, cfg, norm):
         np.testing.assert_allclose(got[k], want[k], rtol=RTOL, atol=0, equal_nan=True, err_msg=k)
 
 
-def test_fused_chain_equals_unfused_kernels(dev, tiny2_cm, monkeypatch):
-    """The default image chain is two fused kernels (image_fused.cu: k_gray_gv, k_gh_nms with TMA
-    tiles); SNN_FUSED=0 selects the five unfused kernels of image_fast.cu.  Every per-pass product
-    (gray, smoothed, magnitude, masks) of every window and brightness of a chromosome, and the
-    candidates of the whole chromosome, must be the same bits — with the tie check on and with the
-    literal form forced for every output."""
+@pytest.mark.parametrize("mode", ["a", "1"])
+def test_fused_chain_equals_unfused_kernels(dev, tiny2_cm, monkeypatch, mode):
+    """Image chain variants (image_fused.cu): SNN_FUSED=a runs k_gray_gv (gray + axis-0 Gaussian in one
+    kernel) in front of the unfused axis-1 and Sobel kernels, SNN_FUSED=1 adds k_gh_nms (axis 1 +
+    Sobel + NMS from TMA tiles), SNN_FUSED=0 is the five unfused kernels of image_fast.cu.  Every
+    per-pass product (gray, smoothed, magnitude, masks) of every window and brightness of a
+    chromosome, and the candidates of the whole chromosome, must be the same bits — with the tie
+    check on and with the literal form forced for every output."""
     obj, mat, names, _, _ = _obj(tiny2_cm, "KR", dev)
     cid = obj.unbalLib.ensure("chrA")
     mp = np.quantile(mat.positive_population("chrA"), [0.95, 0.97, 0.99])
     nwin = pl.n_frames(mat.nbins("chrA"))
-    monkeypatch.setenv("SNN_FUSED", "1")
+    monkeypatch.setenv("SNN_FUSED", mode)
     fused = {(idx, b): dev.debug_stages(cid, mp[1], 2.0, 3, idx, b) for idx in range(nwin) for b in range(6)}
     cand = dev.extract(cid, mp, 2.0, 10, 8, 3)
     monkeypatch.setenv("SNN_GAUSS_TIE_K", str(0x10000000))
