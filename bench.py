@@ -53,7 +53,9 @@ def parse():
     ap.add_argument("--config", default="cfg3")
     ap.add_argument("--scaling", default="strong", choices=["weak", "strong"])
     ap.add_argument("--streams", type=int, default=2, help="host threads (contexts/streams) feeding each GPU")
-    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--cpu-seconds", type=float, default=None,
+                    help="time budget of one CPU-arm step (default: 20 s for cpu_baseline, 300 s / (steps + warmup) "
+                         "clamped to 8..30 s for --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-score-mode", action="store_true", help="skip the config-5 side measurement")
     return ap.parse_args()
@@ -125,12 +127,42 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def fp64_peak():
+    """FP64 FMA rate of this GPU from the micro-benchmark tools/fp64_peak.cu (MEASURED_PEAKS.json has no
+    FP64 figure): run now if the binary was built (__graft_entry__.build()), else the committed
+    measurement of this pool (profiles/r02a_fp64_peak.json)."""
+    exe = os.path.join(ROOT, "tools", "bin", "fp64_peak")
+    if os.path.exists(exe):
+        try:
+            out = subprocess.run([exe], capture_output=True, text=True, timeout=120).stdout.strip().splitlines()[-1]
+            d = json.loads(out)
+            return d["rows"], "measured now (tools/fp64_peak.cu, %s, %d SMs, attr clock %d MHz)" % (
+                d["gpu"], d["sms"], d["clock_khz_attr"] // 1000)
+        except Exception:
+            pass
+    f = os.path.join(ROOT, "profiles", "r02a_fp64_peak.json")
+    if os.path.exists(f):
+        try:
+            return json.load(open(f))["rows"], "measured earlier on this pool (profiles/r02a_fp64_peak.json)"
+        except Exception:
+            pass
+    return None, "unavailable"
+
+
 CONFIG_TEXT = {"cfg1": "synthetic chr16-sized map at 5 kb", "cfg2": "synthetic mouse whole genome at 10 kb (chr1-19+X)",
                "cfg3": "synthetic human whole genome at 5 kb, KR-balanced (chrY dropped by the chromosome filter)",
                "cfg4": "synthetic human chr1 at 1 kb"}
 NCU_FAMILY = {"gaussian": ("k_gauss_vm", "k_gauss_hm"), "sobel_nms": ("k_sobel_nms",), "gray": ("k_gray6",),
               "search": ("k_search",), "score": ("k_score_warp",), "background": ("k_background",),
-              "quantile_select": ("k_radix_hist",)}
+              "quantile_select": ("k_radix_hist",), "k_gray_gv": ("k_gray_gv",), "k_gh_nms": ("k_gh_nms",)}
+# FP64 operations of the REFERENCE per pass pixel (one pixel of one (window, maxpixel, brightness) image),
+# counted from its literal operation sequence (DESIGN.md §3): what `roofline.achieved` credits.
+#   k_gray_gv: saturate 4 (255*(M-D)/M/255) + brightness 1 + cv.filter2D 3x3 (9 mul + 9 add) = 23,
+#              + scipy correlate1d along axis 0, 17 taps (8 pair adds + 9 mul + 8 adds) = 25
+#   k_gh_nms:  correlate1d along axis 1 = 25, + ndi.sobel: two derivative passes (sub, mul) = 4,
+#              two [1 2 1] passes (2 mul + 2 add) = 8 (float32 work — division, magnitude, NMS — not counted)
+FP64_FLOPS_PER_PASS_PIXEL = {"k_gray_gv": 48.0, "k_gh_nms": 37.0, "gray": 23.0, "gaussian": 50.0, "sobel_nms": 12.0}
+FULL_BATCH_WINDOWS = 51      # windows of one full image-chain launch (1536 // (5 * 6)); ncu captures use this shape
 
 
 def ncu_traffic(family):
@@ -153,6 +185,128 @@ def ncu_traffic(family):
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
+# The CPU arm times the reference's own implementation of the path on the box's host cores.
+#   kind "reference": the UNMODIFIED reference (ysora/stripenn 1.1.65.22) imported from baseline/_ref
+#       (installed there with `pip install --no-index --no-deps --target baseline/_ref /root/reference`,
+#       git-ignored, travels to the GPU box) or $STRIPENN_REFERENCE_SRC, through oracle/refharness
+#       (stub packages for cooler / matplotlib / scikit-image, which the image lacks);
+#   kind "port": the numpy restatement oracle/snn_oracle when no reference tree is present.
+# A step = the stages the B200 arm times — maxpixel quantiles, expected values, candidate search over
+# every window x 5 maxpixel values x 6 brightness passes, p-values, dedup, stripiness — on a bounded
+# SAMPLE of the workload: one synthetic chromosome of the same generator and resolution (5 kb, KR
+# weights with NaN bins for cfg3), F windows long, F sized to the per-step time budget with the
+# windows spread over all host cores (one task per window like the reference's joblib loop).  The
+# background tables (nulldist: 1000 samples, one serial task per chromosome, ~1 % of a genome's CPU
+# time) are computed ONCE before the steps; their measured time is charged to every step in
+# proportion: t_nulldist x (tasks per genome = chromosomes) x (sample pixels / genome pixels) / cores.
+GENOME = {"cfg3": (23, 2410.4), "cfg2": (20, 1041.0), "cfg1": (1, 78.0), "cfg4": (1, 995.0)}   # chromosomes, Mpixels
+
+
+def reference_src():
+    for p in (os.environ.get("STRIPENN_REFERENCE_SRC"), os.path.join(ROOT, "baseline", "_ref")):
+        if p and os.path.isfile(os.path.join(p, "stripenn", "getStripe.py")):
+            return p
+    return None
+
+
+def sample_mpixels(nbins, frames):
+    return NQ * sum((min((i + 1) * 200 + 99, nbins - 1) - (0 if i == 0 else i * 200 - 100) + 1) ** 2
+                    for i in frames) / 1e6
+
+
+class CpuArm:
+    def __init__(self, config, cores=None):
+        from stripenn_b200 import synth
+        self.cores = cores or os.cpu_count() or 1
+        self.config = config if config in GENOME else "cfg3"
+        chroms, self.binsize, self.balanced = synth.config_chroms(self.config)
+        self.norm = "KR" if self.balanced else "None"
+        self.qs = list(map(float, QS.split(",")))
+        self.src = reference_src()
+        self.kind = "reference" if self.src else "port"
+        self.F = None
+        self.t_null = None
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+    # ---- sample construction
+    def build(self, F):
+        """Sample chromosome of F windows (F * 200 bins), stage objects, background tables."""
+        from stripenn_b200 import synth
+        self.F = int(F)
+        nbins = self.F * 200
+        self.cm = synth.make_map([("chr1", nbins * self.binsize - 17)], self.binsize, balanced=self.balanced)
+        self.nbins = self.cm.nbins("chr1")
+        self.frames = list(range(int(math.ceil(self.nbins / 200))))
+        self.mpx = sample_mpixels(self.nbins, self.frames)
+        t0 = time.time()
+        if self.kind == "reference":
+            import tempfile
+            os.environ["STRIPENN_REFERENCE_SRC"] = self.src
+            os.environ["SNN_REF_PROCS"] = str(self.cores)
+            from refharness import run_reference as rr
+            self.rr = rr
+            tmp = tempfile.mkdtemp(prefix="snn_cpuarm_")
+            path = os.path.join(tmp, "sample.npz")
+            self.cm.save_npz(path)
+            self.obj, self.lib = rr.make_object(path, norm=self.norm, numcores=self.cores)
+            self.bg = self.obj.nulldist()
+        else:
+            from snn_oracle import background as bgm
+            from snn_oracle.matrix import OracleMatrix
+            from stripenn_b200.compute import resolve_norm
+            self.mat = OracleMatrix(self.cm, resolve_norm(self.cm, self.norm, "compute", False))
+            self.bg = bgm.null_distribution(self.mat, ["chr1"], np.array([self.cm.chromsizes[0]]), 123456789)
+        self.t_null = time.time() - t0
+
+    # ---- one step
+    def step(self):
+        t0 = time.time()
+        if self.kind == "reference":
+            import pandas as pd
+            obj = self.obj
+            MP = obj.getQuantile_original(self.lib, obj.chromnames, self.qs)      # stripenn.py:126
+            EV = obj.mpmean()                                                      # :128
+            res = pd.DataFrame()
+            for i, q in enumerate(self.qs):                                        # :134-138 (p-values inside)
+                res = pd.concat([res, obj.extract(MP, i, q, *self.bg)])
+            res = obj.RemoveRedundant(res, "pvalue")                               # :144
+            obj.scoringstripes(res, EV, "0")                                       # :147
+            nrow = len(res)
+        else:
+            import multiprocessing as mp
+            from snn_oracle import background as bgm, pipeline as pl, scoring as sc
+            MP = pl.quantiles(self.mat, ["chr1"], self.qs)["chr1"]
+            EV = bgm.expected_by_distance(self.mat, ["chr1"])
+            _CPU_STATE.update(mat=self.mat, chrom="chr1", qs=self.qs, MP=MP)
+            if self.cores > 1:
+                with mp.get_context("fork").Pool(self.cores) as pool:
+                    got = dict(pool.map(_cpu_window, [(i,) for i in self.frames], chunksize=1))
+            else:
+                got = dict(_cpu_window((i,)) for i in self.frames)
+            per_q = []
+            for qi in range(len(self.qs)):
+                t = pl.remove_redundant(pl.concat_tables([got[i][qi] for i in self.frames]), "size")
+                t["pvalue"] = sc.pvalues(self.mat, self.bg, t)
+                per_q.append(t)
+            final = pl.remove_redundant(pl.concat_tables(per_q), "pvalue")
+            sc.stripiness(self.mat, final, EV)
+            nrow = len(final["pos1"])
+        dt = time.time() - t0
+        nchrom, genome_mpx = GENOME[self.config]
+        share = self.t_null * nchrom * (self.mpx / genome_mpx) / self.cores
+        return dt + share, dt, share, nrow
+
+    def describe(self, dt, share, nrow):
+        what = ("UNMODIFIED reference (stripenn 1.1.65.22 from %s through oracle/refharness)" % os.path.relpath(self.src, ROOT)
+                if self.kind == "reference" else "oracle port (numpy restatement, oracle/snn_oracle; no reference tree here)")
+        return ("%s on a %d-window synthetic chromosome (%d bins at %d bp, --norm %s, same generator as %s), 5 maxpixel "
+                "values, %d host processes = %.1f windows per core: quantiles + expected values + search + p-values + "
+                "dedup + stripiness %.1f s per step, + %.2f s = share of the background stage (nulldist %.1f s per "
+                "chromosome task, measured once) ; %d stripes" %
+                (what, len(self.frames), self.nbins, self.binsize, self.norm, self.config, self.cores,
+                 len(self.frames) / self.cores, dt, share, self.t_null, nrow))
+
+
 def _cpu_window(args):
     """One search window x all maxpixel values with the oracle port (worker process)."""
     idx, = args
@@ -171,56 +325,30 @@ def _cpu_window(args):
 _CPU_STATE = {}
 
 
-def cpu_sample(budget_s, cores=None, chrom_size=61431566, binsize=10000, seed=20240501):
-    """The CPU implementation of the path (numpy oracle port of the reference, oracle/snn_oracle)
-    on a bounded sample of the workload: the first F windows of a chr19-sized synthetic chromosome
-    of the same generator, 5 maxpixel values: search (all cores, one task per window like the
-    reference's joblib loop) + serial p-values + dedup + stripiness.  Quantiles, expected values
-    and the background tables are prepared OUTSIDE the timed region (favours the CPU)."""
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import multiprocessing as mp
-    from snn_oracle import background as bgm, pipeline as pl, scoring as sc
-    from snn_oracle.matrix import OracleMatrix
-    from stripenn_b200 import synth
-    cores = cores or os.cpu_count() or 1
-    cm = synth.make_map([("19", chrom_size)], binsize, seed=seed)
-    mat = OracleMatrix(cm, False)
-    qs = list(map(float, QS.split(",")))
-    MP = pl.quantiles(mat, ["19"], qs)["19"]
-    EV = bgm.expected_by_distance(mat, ["19"])
-    bg = bgm.null_distribution(mat, ["19"], np.array([chrom_size]), 123456789)
-    _CPU_STATE.update(mat=mat, chrom="19", qs=qs, MP=MP)
-    # calibrate: one window on one core
-    t0 = time.time()
-    _cpu_window((3,))
-    per_window = time.time() - t0
-    nfr = pl.n_frames(mat.nbins("19"))
-    F = int(max(cores, min(nfr, budget_s * 0.7 * cores / max(per_window, 1e-3))))
-    F = min(F, nfr)
-    frames = list(range(F))
-    t0 = time.time()
-    if cores > 1:
-        ctx = mp.get_context("fork")
-        with ctx.Pool(cores) as pool:
-            res = dict(pool.map(_cpu_window, [(i,) for i in frames], chunksize=1))
-    else:
-        res = dict(_cpu_window((i,)) for i in frames)
-    per_q = []
-    for qi in range(len(qs)):
-        t = pl.remove_redundant(pl.concat_tables([res[i][qi] for i in frames]), "size")
-        t["pvalue"] = sc.pvalues(mat, bg, t)
-        per_q.append(t)
-    final = pl.remove_redundant(pl.concat_tables(per_q), "pvalue")
-    sc.stripiness(mat, final, EV)
-    dt = time.time() - t0
-    px = NQ * sum((min((i + 1) * 200 + 99, mat.nbins("19") - 1) - (0 if i == 0 else i * 200 - 100) + 1) ** 2
-                  for i in frames) / 1e6
-    return {"value": px / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "oracle port (numpy restatement of the reference), first %d of %d windows of a chr19-sized "
-                      "synthetic chromosome at 10 kb x 5 maxpixel values: search on %d processes + serial pvalue + "
-                      "dedup + stripiness in %.1f s; quantiles/expected/background prepared outside the timed region"
-                      % (F, nfr, cores, dt),
-            "seconds": dt, "mpixels": px, "stripes": len(final["pos1"])}
+def run_cpu_arm(config, steps, warm, budget_s, cores=None):
+    """Returns (per-step records of the timed steps, arm).  The sample is sized from one calibration
+    step on `cores` windows so that a step fits `budget_s`."""
+    arm = CpuArm(config, cores)
+    arm.build(arm.cores)                      # calibration: one window per core
+    tot, dt, share, nrow = arm.step()
+    per_window_core_s = dt * arm.cores / max(len(arm.frames), 1)
+    F = int(min(max(arm.cores, budget_s * arm.cores / max(per_window_core_s, 1e-3)), 8 * arm.cores))
+    if F > len(arm.frames):
+        arm.build(F)
+    recs = []
+    for i in range(warm + steps):
+        r = arm.step()
+        if i >= warm:
+            recs.append(r)
+    return recs, arm
+
+
+def cpu_sample(config, budget_s, cores=None):
+    """cpu_baseline of the B200 arm's line: one timed step of the CPU arm on a bounded sample."""
+    recs, arm = run_cpu_arm(config, 1, 0, budget_s, cores)
+    tot, dt, share, nrow = recs[0]
+    return {"value": arm.mpx / tot, "unit": UNIT, "cores": arm.cores, "kind": arm.kind,
+            "sample": arm.describe(dt, share, nrow)}
 
 
 def reference_arm(args):
@@ -228,26 +356,22 @@ def reference_arm(args):
     if rank != 0:
         return
     steps, warm = max(1, args.steps), max(0, args.warmup)
-    per = max(4.0, min(args.cpu_seconds, 150.0 / (steps + warm)))
-    vals = []
-    last = None
-    for i in range(warm + steps):
-        last = cpu_sample(per)
-        if i >= warm:
-            vals.append(last)
-    tot_px = sum(v["mpixels"] for v in vals)
-    tot_s = sum(v["seconds"] for v in vals)
-    value = tot_px / tot_s
+    # the whole run must end within a few minutes: ~300 s over all steps, 8-30 s per step
+    per = args.cpu_seconds if args.cpu_seconds else max(8.0, min(30.0, 300.0 / (steps + warm)))
+    recs, arm = run_cpu_arm(args.config, steps, warm, per)
+    tot_s = sum(r[0] for r in recs)
+    value = arm.mpx * len(recs) / tot_s
+    sample = arm.describe(recs[-1][1], recs[-1][2], recs[-1][3])
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": 1000.0 * tot_s / steps, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "cfg2 (synthetic mouse genome, 10 kb, norm None, 5 maxpixel values); each step "
-                                   "= a bounded sample of it", "sample": last["sample"]},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": last["cores"], "kind": "port",
-                             "sample": last["sample"]},
+            "config": {"workload": "%s: %s, --norm %s, -m %s, stages 1-5 of compute; each step = a bounded sample of it"
+                                   % (arm.config, CONFIG_TEXT.get(arm.config, ""), arm.norm, QS),
+                       "sample": sample, "sample_mpixels": arm.mpx},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": arm.kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------ score mode
@@ -462,6 +586,7 @@ def native_arm(args):
         return ms, res
 
     steps, warm = max(1, args.steps), max(0, args.warmup)   # the default (3) satisfies W >= 3
+    fp64_rows = fp64_peak() if rank == 0 else (None, "")
     sampler = ClockSampler(local)
     sampler.start()
     ms_dev, (unf, fil) = timed(ResidentMatrix, steps, warm)
@@ -521,26 +646,60 @@ def native_arm(args):
             "sobel_nms": fpx * NQ * 6 * 4,
             "search": fpx * NQ * 6 * 2 / 8,
         }
-        top = max(kern_ms, key=lambda k: kern_ms[k])
+        alg.update({"k_gray_gv": fpx * 8, "k_gh_nms": 0.0})
         per_stage = {k: {"ms_per_step": round(kern_ms[k], 4),
-                         "achieved_gbs": (alg[k] / 1e9) / (kern_ms[k] / 1e3) if k in alg and kern_ms[k] > 0 else None}
+                         "achieved_gbs": (alg[k] / 1e9) / (kern_ms[k] / 1e3) if alg.get(k) and kern_ms[k] > 0 else None}
                      for k in kern_ms}
-        ach = per_stage[top]["achieved_gbs"]
+        # the dominant KERNEL (a stage that is one kernel), by device time inside the timed region
+        single = [k for k in kern_ms if k in ("k_gray_gv", "k_gh_nms", "gray", "sobel_nms", "search", "score",
+                                              "background", "expected", "row_flags")]
+        top = max(single or list(kern_ms), key=lambda k: kern_ms[k])
         nl = max(stages[top]["launches"] / steps, 1)
         tr = ncu_traffic(top)
-        roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                    "frac": (ach / peak) if ach else None, "traffic": tr[0] if tr else None,
-                    "traffic_source": ("%s: dram read+write per launch, mean over %s" % (tr[1], "+".join(NCU_FAMILY[top])))
-                    if tr else None,
-                    "launches_per_step": nl, "algorithmic_bytes_per_launch": alg.get(top, 0) / nl,
-                    "avg_launch_ms": kern_ms[top] / nl, "peak_source": peak_src,
-                    "share_of_step": kern_ms[top] / (ms_dev / steps), "stages": per_stage,
-                    "gpu_ms_per_step": sum(kern_ms.values())}
+        rows, fsrc = fp64_rows
+        fpeak = rows["dfma"]["tflops"] if rows else None
+        pass_px = fpx * NQ * 6                                     # pass pixels per step on this rank
+        batch_px = FULL_BATCH_WINDOWS * 400 * 400                  # window pixels of one full launch
+        chain = [k for k in ("k_gray_gv", "k_gh_nms", "gray", "gaussian", "sobel_nms") if kern_ms.get(k, 0) > 0]
+        chain_ms = sum(kern_ms[k] for k in chain)
+        if top in FP64_FLOPS_PER_PASS_PIXEL and fpeak:
+            flops = FP64_FLOPS_PER_PASS_PIXEL[top]
+            ach = flops * pass_px / (kern_ms[top] / 1e3) / 1e12
+            roofline = {"kernel": top, "bound": "fp64", "achieved": ach, "peak": fpeak, "unit": "TFLOP/s",
+                        "frac": ach / fpeak,
+                        "algorithmic": "%.0f FP64 operations of the reference per pass pixel (DESIGN.md §3) x %.4g pass "
+                                       "pixels per step / kernel time per step" % (flops, pass_px),
+                        "algorithmic_flops_per_launch": flops * batch_px * NQ * 6}
+        else:
+            ach = per_stage[top]["achieved_gbs"]
+            roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                        "frac": (ach / peak) if ach else None}
+        roofline.update({
+            "fp64_peak_tflops": fpeak, "fp64_peak_source": fsrc,
+            "fp64_pipe_rates_per_clk_per_sm": ({k: rows[k]["ops_per_clk_per_sm_at_attr_clock"] for k in
+                                                ("dfma", "dadd", "dmul", "cvt_widen", "cvt_narrow", "sqrtf_rn", "divf_rn")}
+                                               if rows else None),
+            # HBM view, for information (the image chain is not HBM-bound): the chain's
+            # algorithmic bytes are the compacted window read once, 8 B per window pixel
+            "hbm": {"peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                    "image_chain_kernels": chain,
+                    "algorithmic_bytes_per_step": fpx * 8,
+                    "achieved": (fpx * 8 / 1e9) / (chain_ms / 1e3) if chain_ms > 0 else None,
+                    "frac": ((fpx * 8 / 1e9) / (chain_ms / 1e3) / peak) if chain_ms > 0 else None,
+                    "algorithmic_bytes_per_launch": batch_px * 8},
+            "traffic": tr[0] if tr else None,
+            "traffic_source": ("%s: dram__bytes_read.sum + dram__bytes_write.sum of one %d-window launch of %s (ncu --set "
+                               "full)" % (tr[1], FULL_BATCH_WINDOWS, "+".join(NCU_FAMILY[top]))) if tr else None,
+            "traffic_over_algorithmic": (tr[0] / (batch_px * 8)) if tr else None,
+            "launch_shape": "%d windows x %d maxpixel values x 6 brightness passes of 400 x 400 pixels (full batch)"
+                            % (FULL_BATCH_WINDOWS, NQ),
+            "launches_per_step": nl, "avg_launch_ms": kern_ms[top] / nl,
+            "share_of_step": kern_ms[top] / (ms_dev / steps), "stages": per_stage,
+            "gpu_ms_per_step": sum(kern_ms.values())})
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             try:
-                cpu = cpu_sample(args.cpu_seconds)
-                cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+                cpu = cpu_sample(args.config, args.cpu_seconds or 20.0)
             except Exception as e:  # the checker must not break the measurement
                 cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % e}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
@@ -562,7 +721,7 @@ def native_arm(args):
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d_step),
                         "d2h_bytes_per_step": int(d2h_step), "ms_per_step": ms_e2e / steps},
                 "gpu_launches": launches, "host_phases_ms_last_step": host_phases, "score_mode": score_mode, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
-        print(json.dumps(line), flush=True)
+        emit(line)
     for d in devs:
         d.close()
     if world > 1:
@@ -570,16 +729,25 @@ def native_arm(args):
         dist.destroy_process_group()
 
 
+_OUT = [None]
+
+
+def emit(line):
+    """The ONE JSON line goes to the process's real stdout; everything else any library (or the
+    reference's own progress prints) writes to stdout is sent to stderr."""
+    out = _OUT[0] or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 if __name__ == "__main__":
     a = parse()
-    # stdout carries exactly ONE JSON line: anything else a library prints there (NCCL's version
-    # banner, warnings of child processes) is sent to stderr; the line goes to the real stdout
     sys.stdout.flush()
-    _real_stdout = os.fdopen(os.dup(1), "w")
-    os.dup2(2, 1)
-    sys.stdout = _real_stdout
+    _OUT[0] = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)                 # C-level writers (NCCL's version banner, child processes)
+    sys.stdout = sys.stderr       # Python-level prints
     if a.impl == "reference":
         reference_arm(a)
     else:
         native_arm(a)
-    _real_stdout.flush()
+    _OUT[0].flush()

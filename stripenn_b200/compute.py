@@ -211,12 +211,24 @@ class DeviceQueue:
     of earlier results at the same time.  A context is only ever touched by this thread while
     the queue is open — the C ABI's one-thread-at-a-time rule holds."""
 
-    def __init__(self):
+    def __init__(self, trace=False):
         from concurrent.futures import ThreadPoolExecutor
         self._ex = ThreadPoolExecutor(max_workers=1, thread_name_prefix="snn-device")
+        self.trace = [] if trace else None       # (call, submitted, started, finished) in seconds
 
     def submit(self, fn, *args, **kw):
-        return self._ex.submit(fn, *args, **kw)
+        if self.trace is None:
+            return self._ex.submit(fn, *args, **kw)
+        t_sub = time.perf_counter()
+        name = getattr(fn, "__name__", "call")
+
+        def timed():
+            t0 = time.perf_counter()
+            try:
+                return fn(*args, **kw)
+            finally:
+                self.trace.append((name, t_sub, t0, time.perf_counter()))
+        return self._ex.submit(timed)
 
     def close(self):
         self._ex.shutdown(wait=True)
@@ -276,7 +288,8 @@ def run_pipeline(obj, cm, qs, chromnames, pvalue, mask, slow, comm=None, say=lam
     labels = [str(q * 100) + '%' for q in qs]
     cidx = {c: i for i, c in enumerate(chromnames)}
     dev_bg = hasattr(obj.dev, "background_dev")       # device-resident background columns
-    dq = DeviceQueue()
+    dq = DeviceQueue(trace=bool(os.environ.get("SNN_TRACE")))
+    t_pipeline = time.perf_counter()
     try:
         say('1. Maximum pixel value calculation ...')
         quant = obj.getQuantile_slow if slow else obj.getQuantile_original
@@ -462,6 +475,10 @@ def run_pipeline(obj, cm, qs, chromnames, pvalue, mask, slow, comm=None, say=lam
     result_table, res_filter = comm.once(build)
     clock.lap('tables')
     obj.last_host_ms = clock.ms
+    if dq.trace is not None:
+        obj.last_trace = [(n, (a - t_pipeline) * 1e3, (b - t_pipeline) * 1e3, (c - t_pipeline) * 1e3)
+                          for n, a, b, c in dq.trace]
+        obj.last_trace_total_ms = (time.perf_counter() - t_pipeline) * 1e3
     if return_stages:
         per_q = obj.candidate_tables(kept, np.concatenate(all_pv) if all_pv else np.zeros(0), qs)
         return result_table, res_filter, dict(MP=MP, EV=EV, bg=bg_host, per_q=per_q)

@@ -101,7 +101,7 @@ static void drain_timers(snn_ctx* ctx) {
 static const char* kStageNames[ST_COUNT] = {"band_build", "quantile_select", "expected",   "row_flags",
                                             "background", "background_sort", "frame_prepare", "gray",
                                             "gaussian",   "sobel_nms",       "search",     "finish",
-                                            "score"};
+                                            "score",      "k_gray_gv",       "k_gh_nms"};
 
 extern "C" {
 

@@ -29,6 +29,8 @@ enum SnnStage {
     ST_SEARCH,
     ST_FINISH,
     ST_SCORE,
+    ST_GRAY_GV,   // k_gray_gv (fused gray + axis-0 Gaussian)
+    ST_GH_NMS,    // k_gh_nms (fused axis-1 Gaussian + Sobel + NMS)
     ST_COUNT
 };
 

@@ -13,7 +13,7 @@ def _run(env_extra):
     env = dict(os.environ)
     env.update(env_extra)
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
-                        "--warmup", "0"], capture_output=True, text=True, env=env, timeout=600, cwd=ROOT)
+                        "--warmup", "0", "--cpu-seconds", "3"], capture_output=True, text=True, env=env, timeout=600, cwd=ROOT)
     assert p.returncode == 0, p.stderr[-2000:]
     return p.stdout.strip()
 
