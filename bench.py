@@ -453,11 +453,21 @@ def native_arm(args):
     from stripenn_b200.engine import Device, default_band_width
 
     rank, local, world = env_rank()
+    # host threads that wait on the GPU: 2 per host thread per process.  When all ranks together have
+    # more of them than half the cores, the library waits on blocking events instead of spinning.
+    if world * max(1, args.streams) * 2 > (os.cpu_count() or 1) // 2:
+        os.environ.setdefault("SNN_BLOCKING_SYNC", "1")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the B200 arm has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # high-priority NCCL stream: the one device-side exchange (background columns) must not queue
+        # behind the search kernels that keep every GPU full
+        try:
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local), pg_options=opts)
+        except Exception:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     strong = args.scaling == "strong" and world > 1
 
     chroms, binsize, balanced = synth.config_chroms(args.config)
@@ -470,7 +480,7 @@ def native_arm(args):
         # virtual rank v lives in process v // nstreams
         shell = synth.make_map(chroms, binsize, only=[])
         f_names, f_sizes, _, _ = cp.compute_chromosomes(shell, ["all"])
-        units = cp.plan_units(f_names, f_sizes, binsize, world * nstreams, selected=f_names)
+        units = cp.plan_units(f_names, f_sizes, binsize, world * nstreams, selected=f_names, tpp=nstreams)
         mine = [c for c in names if any(u["chrom"] == c and u["rank"] // nstreams == rank for u in units)]
         seed = synth.DEFAULT_SEED
     else:
@@ -563,9 +573,19 @@ def native_arm(args):
             return one_rank(dev, comms[0])
         return cp.run_threads(lambda c: one_rank(devs[thread_of(c)], c), comms)[0]
 
+    step_walls = {}
+
     def timed(matrix_cls, k, w):
         for _ in range(w):
             step(matrix_cls)
+        # Full garbage collections walk every container object of the process — with torch, pandas and
+        # numpy imported that is 50-100 ms, and CPython runs them often while the process is young: two
+        # steps of 75-105 ms in every 8-GPU run of 36 ms steps (profiles/bench_r02s/t_n8.json).  Collect
+        # once now and move the survivors out of the collector's sight; the steps' own garbage is
+        # still collected.
+        import gc
+        gc.collect()
+        gc.freeze()
         for d in devs:
             d.reset_stage_times()
         if world > 1:
@@ -573,10 +593,14 @@ def native_arm(args):
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
+        walls = []
         for _ in range(k):
+            t_s = time.perf_counter()
             res = step(matrix_cls)
+            walls.append(round((time.perf_counter() - t_s) * 1e3, 2))
         e1.record(stream)
         torch.cuda.synchronize()
+        step_walls[matrix_cls.__name__] = walls
         ms = e0.elapsed_time(e1)
         if world > 1:
             t = torch.tensor([ms], device="cuda", dtype=torch.float64)
@@ -587,10 +611,17 @@ def native_arm(args):
 
     steps, warm = max(1, args.steps), max(0, args.warmup)   # the default (3) satisfies W >= 3
     fp64_rows = fp64_peak() if rank == 0 else (None, "")
+    # One clock sampler, on rank 0 (its own GPU), started a second before the work: nvidia-smi's start-up
+    # (NVML attaches to every GPU of the box) holds driver locks, and eight of them starting inside
+    # the timed region cost two steps of 75-105 ms in a run of 36 ms steps (profiles/bench_r02s_n8.json).
     sampler = ClockSampler(local)
-    sampler.start()
+    if rank == 0:
+        sampler.start()
+        time.sleep(1.5)
+    if world > 1:
+        dist.barrier()
     ms_dev, (unf, fil) = timed(ResidentMatrix, steps, warm)
-    clocks = sampler.stop()
+    clocks = sampler.stop() if rank == 0 else None
     stages = {}
     for d in devs:
         for k, v in d.stage_times().items():
@@ -720,7 +751,9 @@ def native_arm(args):
                            "generate_s": round(gen_s, 1)},
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d_step),
                         "d2h_bytes_per_step": int(d2h_step), "ms_per_step": ms_e2e / steps},
-                "gpu_launches": launches, "host_phases_ms_last_step": host_phases, "score_mode": score_mode, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+                "gpu_launches": launches, "host_phases_ms_last_step": host_phases,
+                "host_wall_ms_per_step_rank0": {"resident": step_walls.get("ResidentMatrix"),
+                                                "pinned_host": step_walls.get("PinnedMatrix")}, "score_mode": score_mode, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
         emit(line)
     for d in devs:
         d.close()

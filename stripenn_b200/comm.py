@@ -47,6 +47,8 @@ class LocalComm:
     def all_gather_arrays(self, a):
         return [np.asarray(a)]
 
+    all_gather_fixed = all_gather_arrays
+
     def once(self, fn):
         return fn()
 
@@ -95,6 +97,8 @@ class ThreadComm:
 
     def all_gather_arrays(self, a):
         return self.all_gather(np.asarray(a))
+
+    all_gather_fixed = all_gather_arrays
 
     def once(self, fn):
         """fn() evaluated by thread 0 only; every thread gets the same object."""
@@ -145,14 +149,28 @@ class TorchComm:
         self.cuda = dist.get_backend() == "nccl"
         self.dev = torch.device("cuda", torch.cuda.current_device()) if self.cuda else torch.device("cpu")
         self._bg = None
+        # The small host arrays (counts, candidate and result rows) travel over a gloo group even when
+        # the default backend is nccl: an NCCL collective is a kernel that has to find room on GPUs the
+        # searches keep full, on all ranks at once — measured at 8 GPUs as milliseconds per exchange
+        # (profiles/bench_r02p_n8.json: the first exchange completed 23 ms into a 49 ms step).  Only
+        # the background buffer, which lives on the device, goes through NCCL.
+        self.host_group = dist.new_group(backend="gloo") if self.cuda and self.nproc > 1 else None
 
     def _gather_equal(self, a):
         """a: 1-D array of the same length and dtype on every process -> (nproc, len)."""
         torch = self.torch
-        t = torch.from_numpy(np.ascontiguousarray(a).reshape(-1)).to(self.dev)
-        out = torch.empty(self.nproc * t.numel(), dtype=t.dtype, device=self.dev)   # flat: gloo insists
-        self.dist.all_gather_into_tensor(out, t)
+        t = torch.from_numpy(np.ascontiguousarray(a).reshape(-1))
+        if self.host_group is None and self.cuda:
+            t = t.to(self.dev)
+        out = torch.empty(self.nproc * t.numel(), dtype=t.dtype, device=t.device)   # flat: gloo insists
+        self.dist.all_gather_into_tensor(out, t, group=self.host_group)
         return out.cpu().numpy().reshape(self.nproc, -1)
+
+    def all_gather_fixed(self, a):
+        """Arrays of the SAME shape and dtype on every process: one collective."""
+        a = np.ascontiguousarray(a)
+        got = self._gather_equal(a.reshape(-1).view(np.uint8))
+        return [got[p].copy().view(a.dtype).reshape(a.shape) for p in range(self.nproc)]
 
     def all_gather_arrays(self, a):
         a = np.ascontiguousarray(a)
@@ -214,17 +232,35 @@ class HybridComm:
         local = self.tc.all_gather(a)
 
         def across():
+            # two collectives: the per-thread lengths, then the rows padded to the longest process
             lens = np.array([x.shape[0] for x in local], dtype=np.int64)
             all_lens = self.pc._gather_equal(lens)                       # (nproc, tpp)
-            parts = self.pc.all_gather_arrays(np.concatenate(local))     # one array per process
+            row = int(np.prod(a.shape[1:], dtype=np.int64)) * a.dtype.itemsize
+            cap = int(all_lens.sum(axis=1).max()) * row
+            if cap == 0:
+                return [np.zeros((0,) + a.shape[1:], dtype=a.dtype) for _ in range(self.world)]
+            buf = np.zeros(cap, dtype=np.uint8)
+            mine = np.concatenate(local).reshape(-1).view(np.uint8)
+            buf[:mine.shape[0]] = mine
+            got = self.pc._gather_equal(buf)
             out = []
             for p in range(self.nproc):
                 off = 0
                 for t in range(self.tpp):
-                    n = int(all_lens[p, t])
-                    out.append(parts[p][off:off + n])
+                    n = int(all_lens[p, t]) * row
+                    out.append(got[p, off:off + n].copy().view(a.dtype).reshape((-1,) + a.shape[1:]))
                     off += n
             return out
+        return self.tc.once(across)
+
+    def all_gather_fixed(self, a):
+        """Same shape on every virtual rank: threads meet in shared memory, one collective."""
+        a = np.ascontiguousarray(a)
+        local = self.tc.all_gather(a)
+
+        def across():
+            parts = self.pc.all_gather_fixed(np.stack(local))            # (tpp, ...) per process
+            return [parts[p][t] for p in range(self.nproc) for t in range(self.tpp)]
         return self.tc.once(across)
 
     def once(self, fn):

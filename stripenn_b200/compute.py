@@ -147,22 +147,30 @@ def lpt_partition(names, sizes, world):
     return owner
 
 
-def plan_units(names, sizes_bp, binsize, world, split=True, selected=None):
-    """Work units of the sharded pipeline: whole chromosomes, except that a chromosome holding
-    more than 1.25 x its fair share of the SEARCHED bins (total / world) is cut into window ranges
-    (getStripe.py:841-842: windows of one chromosome are independent tasks) — a single-chromosome
-    run (BASELINE configs 1 and 4, or `-k chr1` on a whole-genome file) then still uses every GPU.
-    Units are assigned longest first (work ~ windows).  `selected` = the -k chromosomes (default:
-    all): only they are searched and only they count for the fair share; the other chromosomes of
-    the file still need an owner for the background stage (getStripe.py:242,276 samples every
-    chromosome) and are dealt out afterwards as units without windows (search = False).
+def plan_units(names, sizes_bp, binsize, world, split=True, selected=None, tpp=1):
+    """Work units of the sharded pipeline and their owners.  `world` virtual ranks = `world // tpp`
+    processes (one per GPU) x `tpp` host threads; virtual rank = process * tpp + thread.
+
+    Units are whole chromosomes, except that a chromosome holding more than 1.25 x a virtual rank's
+    fair share of the SEARCHED bins is cut into window ranges (getStripe.py:841-842: windows of one chromosome
+    are independent tasks) — a single-chromosome run (BASELINE configs 1 and 4, or `-k chr1` on a
+    whole-genome file) then still uses every GPU.  Assignment is longest-processing-time-first
+    (work ~ windows) over the GPUs, then over the threads of each GPU: what has to balance is the
+    work per GPU — with 16 virtual ranks as bins, chr1 alone exceeded a bin's fair share and the
+    GPU holding chr1 + chr2 carried 1.3 x the mean (profiles/bench_r02n_n8*.json).
+    `selected` = the -k chromosomes (default: all): only they are searched and only they count for
+    the fair share; the other chromosomes of the file still need an owner for the background stage
+    (getStripe.py:242,276 samples every chromosome) and are dealt out afterwards as units without
+    windows (search = False).
     Returns a list of dicts {chrom, piece, npieces, lo, hi, rank, search}; piece 0's rank is the
     chromosome's PRIMARY (it runs the chromosome-wide stages and the host steps)."""
     import math
+    tpp = max(1, min(int(tpp), world))
+    nproc = max(1, world // tpp)
     sel = set(names if selected is None else selected)
     nb = [int(math.ceil(int(s) / binsize)) for s in sizes_bp]
     total = max(sum(nb[i] for i, c in enumerate(names) if c in sel), 1)
-    fair = total / max(world, 1)
+    fair = total / max(world, 1)          # per virtual rank: a lone chromosome also feeds every thread of a GPU
     units, rest = [], []
     for i, c in enumerate(names):
         if c not in sel:
@@ -175,18 +183,22 @@ def plan_units(names, sizes_bp, binsize, world, split=True, selected=None):
         for p in range(k):
             lo, hi = (nfr * p) // k, (nfr * (p + 1)) // k
             units.append(dict(chrom=c, piece=p, npieces=k, lo=lo, hi=hi, order=i, rank=0, search=True))
-    load = [0] * world
+    pload = [0] * nproc                                  # windows per GPU
+    tload = [[0] * tpp for _ in range(nproc)]            # windows per host thread of a GPU
     for u in sorted(units, key=lambda u: (-(u["hi"] - u["lo"]), u["order"], u["piece"])):
-        r = min(range(world), key=lambda k: (load[k], k))
-        u["rank"] = r
-        load[r] += u["hi"] - u["lo"]
+        p = min(range(nproc), key=lambda k: (pload[k], k))
+        t = min(range(tpp), key=lambda k: (tload[p][k], k))
+        u["rank"] = p * tpp + t
+        pload[p] += u["hi"] - u["lo"]
+        tload[p][t] += u["hi"] - u["lo"]
     # background-only chromosomes: their cost (row flags + a share of 1000 samples) is small next to
     # a search; spread them by size on counters of their own
-    bload = [0] * world
+    bload = [0] * nproc
     for u in sorted(rest, key=lambda u: (-nb[u["order"]], u["order"])):
-        r = min(range(world), key=lambda k: (bload[k], load[k], k))
-        u["rank"] = r
-        bload[r] += nb[u["order"]]
+        p = min(range(nproc), key=lambda k: (bload[k], pload[k], k))
+        t = min(range(tpp), key=lambda k: (tload[p][k], k))
+        u["rank"] = p * tpp + t
+        bload[p] += nb[u["order"]]
     return sorted(units + rest, key=lambda u: (u["order"], u["piece"]))
 
 
@@ -275,7 +287,7 @@ def run_pipeline(obj, cm, qs, chromnames, pvalue, mask, slow, comm=None, say=lam
     clock = StageClock()
     all_names = list(obj.all_chromnames)
     chromnames = list(chromnames)
-    units = plan_units(all_names, obj.all_chromsizes, obj.resol, comm.world, selected=chromnames)
+    units = plan_units(all_names, obj.all_chromsizes, obj.resol, comm.world, selected=chromnames, tpp=comm.tpp)
     primary = {u["chrom"]: u["rank"] for u in units if u["piece"] == 0}
     mine = lambda c: primary.get(c, 0) == comm.rank
     my_sel = [c for c in chromnames if mine(c)]
@@ -309,6 +321,17 @@ def run_pipeline(obj, cm, qs, chromnames, pvalue, mask, slow, comm=None, say=lam
         first = [my_units[0]["chrom"]] if my_units else quant_sel[:1]
         rest = [c for c in quant_sel if c not in first]
         dq.submit(obj.prefetch, list(dict.fromkeys(first + rest + [c for c in names2 if mine(c)])))
+        # With several processes every rank waits for every other rank's availability counts
+        # (exchange 1) and background columns (exchange 2): the cheap row-flag kernels go FIRST there,
+        # before the quantile passes and the first search — once a search of the other host thread
+        # fills the GPU, every small kernel of this thread waits about a millisecond for SM space
+        # (profiles/bench_r02o_n8.json: exchange 1 completed 24 ms into a 51 ms step).  Alone, the
+        # first search starts at once and hides the uploads of the other chromosomes.
+        early_flags = comm.nproc > 1
+        f_avail = None
+        if early_flags:
+            say('3. Background distribution estimation ...')
+            f_avail = dq.submit(obj.available_counts, [c for c in names2 if mine(c)])
         if first:
             f_mp[first[0]] = dq.submit(quant, cm, first, qs)
         say('4. Finding candidate stripes from each chromosome ...')
@@ -319,14 +342,16 @@ def run_pipeline(obj, cm, qs, chromnames, pvalue, mask, slow, comm=None, say=lam
                 f_mp[c] = f
         say('2. Expected value calculation ...')
         f_ev = {c: dq.submit(obj.expected_values, c) for c in my_sel}
-        say('3. Background distribution estimation ...')
-        f_avail = dq.submit(obj.available_counts, [c for c in names2 if mine(c)])
-        for _ in range(ahead - 1):
-            submit_search()
+        if not early_flags:
+            say('3. Background distribution estimation ...')
+            f_avail = dq.submit(obj.available_counts, [c for c in names2 if mine(c)])
+        if not early_flags:           # with several processes the background columns go in front of search #2
+            for _ in range(ahead - 1):
+                submit_search()
         # exchange 1: availability counts, one int64 per background chromosome (-1 = not mine)
         got = f_avail.result()
         counts = np.array([got.get(c, -1) for c in names2], dtype=np.int64)
-        merged = np.max(np.stack(comm.all_gather_arrays(counts)), axis=0) if names2 else counts
+        merged = np.max(np.stack(comm.all_gather_fixed(counts)), axis=0) if names2 else counts
         avail = {c: int(merged[i]) for i, c in enumerate(names2)}
         clock.lap('quantiles+expected+flags')
         names2b, budget = obj.sample_budget(names2, avail)
@@ -339,7 +364,8 @@ def run_pipeline(obj, cm, qs, chromnames, pvalue, mask, slow, comm=None, say=lam
             d_buf = comm.bg_buffer(obj.dev, per_proc * comm.nproc)
             f_cols = [dq.submit(obj.background_columns_dev, c, obj.plan_chromosome(c, n_of[c]), d_buf, slot0[c],
                                 n_of[c]) for c in names2b if mine(c)]
-            submit_search()
+            for _ in range(ahead - 1 if early_flags else 1):
+                submit_search()
             for f in f_cols:
                 f.result()
             comm.bg_exchange(per_proc)                  # exchange 2: one all-gather between the GPUs
@@ -352,7 +378,8 @@ def run_pipeline(obj, cm, qs, chromnames, pvalue, mask, slow, comm=None, say=lam
         else:
             f_cols = {c: dq.submit(obj.background_columns, c, obj.plan_chromosome(c, n_of[c]))
                       for c in names2b if mine(c)}
-            submit_search()
+            for _ in range(ahead - 1 if early_flags else 1):
+                submit_search()
             # exchange 2 (host form): sample-major float64 rows, chromosome index in front
             rows = [np.concatenate([np.full((f.result().shape[2], 1), names2b.index(c), dtype=np.float64),
                                     f.result().transpose(2, 0, 1).reshape(-1, 1600)], axis=1)

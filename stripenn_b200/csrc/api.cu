@@ -42,6 +42,17 @@ int snn_materialize(snn_ctx* ctx, SnnChrom* c) {
     return snn_band_build(ctx, c);
 }
 
+cudaError_t snn_stream_sync(snn_ctx* ctx) {
+    if (!ctx->blocking_sync) return cudaStreamSynchronize(ctx->stream);
+    if (!ctx->sync_event) {
+        cudaError_t e = cudaEventCreateWithFlags(&ctx->sync_event, cudaEventBlockingSync | cudaEventDisableTiming);
+        if (e != cudaSuccess) return e;
+    }
+    cudaError_t e = cudaEventRecord(ctx->sync_event, ctx->stream);
+    if (e != cudaSuccess) return e;
+    return cudaEventSynchronize(ctx->sync_event);
+}
+
 int snn_scratch(snn_ctx* ctx, size_t bytes, void** out) {
     if (bytes > ctx->scratch_bytes) {
         if (ctx->scratch) cudaFree(ctx->scratch);
@@ -153,6 +164,8 @@ int snn_create(int device, snn_ctx** out) {
     {
         const char* g = getenv("SNN_FORCE_GENERIC");
         ctx->force_generic = g && g[0] == '1';
+        const char* b = getenv("SNN_BLOCKING_SYNC");
+        ctx->blocking_sync = b && b[0] == '1';
     }
     *out = ctx;
     return SNN_OK;
@@ -181,15 +194,16 @@ static void free_chrom(snn_ctx* ctx, SnnChrom& c) {
 void snn_destroy(snn_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    snn_stream_sync(ctx);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     drain_timers(ctx);
     for (auto& kv : ctx->chroms) free_chrom(ctx, kv.second);
-    cudaStreamSynchronize(ctx->stream);
+    snn_stream_sync(ctx);
     for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
     cudaFree(ctx->bg_sorted);
     cudaFree(ctx->bg_valid);
     cudaFree(ctx->scratch);
+    if (ctx->sync_event) cudaEventDestroy(ctx->sync_event);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -197,7 +211,7 @@ void snn_destroy(snn_ctx* ctx) {
 
 int snn_set_stream(snn_ctx* ctx, void* s) {
     if (!ctx) return snn_fail(nullptr, SNN_EINVAL, "ctx is NULL");
-    cudaStreamSynchronize(ctx->stream);
+    snn_stream_sync(ctx);
     ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
     return SNN_OK;
 }
@@ -205,7 +219,7 @@ int snn_set_stream(snn_ctx* ctx, void* s) {
 int snn_synchronize(snn_ctx* ctx) {
     if (!ctx) return snn_fail(nullptr, SNN_EINVAL, "ctx is NULL");
     SNN_CUDA(cudaSetDevice(ctx->device));
-    SNN_CUDA(cudaStreamSynchronize(ctx->stream));
+    SNN_CUDA(snn_stream_sync(ctx));
     SNN_CUDA(cudaStreamSynchronize(ctx->copy_stream));
     return SNN_OK;
 }
@@ -291,7 +305,7 @@ static int load_common(snn_ctx* ctx, int chrom_id, int64_t nbins, int64_t binsiz
         return rc;
     }
     if (!device_ptrs) {  // host buffers may go away
-        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        cudaError_t e = snn_stream_sync(ctx);
         if (e != cudaSuccess) {
             free_chrom(ctx, c);
             return snn_cuda_fail(ctx, e, "cudaStreamSynchronize");
@@ -456,7 +470,7 @@ int snn_device_alloc(snn_ctx* ctx, int64_t bytes, void** d_out) {
 int snn_device_free(snn_ctx* ctx, void* d_ptr) {
     if (!ctx) return snn_fail(nullptr, SNN_EINVAL, "ctx is NULL");
     SNN_CUDA(cudaSetDevice(ctx->device));
-    SNN_CUDA(cudaStreamSynchronize(ctx->stream));
+    SNN_CUDA(snn_stream_sync(ctx));
     if (d_ptr) SNN_CUDA(cudaFree(d_ptr));
     return SNN_OK;
 }
@@ -466,7 +480,7 @@ int snn_device_read(snn_ctx* ctx, void* dst_host, const void* d_src, int64_t byt
     if (bytes < 0 || (bytes > 0 && (!dst_host || !d_src)))
         return snn_fail(ctx, SNN_EINVAL, "snn_device_read: bad arguments");
     SNN_CUDA(cudaSetDevice(ctx->device));
-    SNN_CUDA(cudaStreamSynchronize(ctx->stream));
+    SNN_CUDA(snn_stream_sync(ctx));
     if (bytes) SNN_CUDA(cudaMemcpy(dst_host, d_src, (size_t)bytes, cudaMemcpyDeviceToHost));
     return SNN_OK;
 }

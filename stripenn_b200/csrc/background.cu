@@ -93,7 +93,7 @@ static int background_run(snn_ctx* ctx, SnnChrom* c, int64_t nsamp, const int32_
         SNN_LAUNCH_CHECK("k_background");
     }
     if (!d_ext) SNN_CUDA(cudaMemcpyAsync(out, dout, obytes, cudaMemcpyDeviceToHost, ctx->stream));
-    SNN_CUDA(cudaStreamSynchronize(ctx->stream));
+    SNN_CUDA(snn_stream_sync(ctx));
     return SNN_OK;
 }
 
@@ -194,7 +194,7 @@ static int set_background_run(snn_ctx* ctx, int64_t ncol, const double* tables, 
                                                               tables ? 0 : 1);
         SNN_LAUNCH_CHECK("k_bg_sort");
     }
-    SNN_CUDA(cudaStreamSynchronize(ctx->stream));
+    SNN_CUDA(snn_stream_sync(ctx));
     ctx->bg_ncol = ncol;
     return SNN_OK;
 }

@@ -73,7 +73,7 @@ int snn_band_build(snn_ctx* ctx, SnnChrom* c) {
         }
         int bad = 0;
         SNN_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost, ctx->stream));
-        SNN_CUDA(cudaStreamSynchronize(ctx->stream));
+        SNN_CUDA(snn_stream_sync(ctx));
         if (bad == 1)
             return snn_fail(ctx, SNN_EINVAL, "snn_load_chrom: pixels must satisfy 0 <= bin1 <= bin2 < nbins");
         if (bad == 2)
@@ -131,7 +131,7 @@ extern "C" int snn_fetch(snn_ctx* ctx, int chrom_id, int64_t i0, int64_t i1, int
     if (blocks > 148 * 8) blocks = 148 * 8;
     k_fetch<<<blocks, 256, 0, ctx->stream>>>(c->band, c->nbins, c->bw, i0, i1, j0, j1, d);
     cudaError_t e = cudaMemcpyAsync(out, d, total * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = snn_stream_sync(ctx);
     cudaFree(d);
     if (e != cudaSuccess) return snn_cuda_fail(ctx, e, "snn_fetch");
     return SNN_OK;
@@ -190,7 +190,7 @@ extern "C" int snn_heatmap(snn_ctx* ctx, int chrom_id, int64_t i0, int64_t i1, d
     if (e == cudaSuccess && chan)
         e = cudaMemcpyAsync(chan, dch, total * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess && rgb) e = cudaMemcpyAsync(rgb, drgb, total * 3, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = snn_stream_sync(ctx);
     cudaFree(dch);
     cudaFree(drgb);
     if (e != cudaSuccess) return snn_cuda_fail(ctx, e, "snn_heatmap");
@@ -244,7 +244,7 @@ int snn_expected_impl(snn_ctx* ctx, SnnChrom* c, double* out) {
         SNN_LAUNCH_CHECK("k_expected_final");
     }
     SNN_CUDA(cudaMemcpyAsync(out, dout, SNN_NDIST * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    SNN_CUDA(cudaStreamSynchronize(ctx->stream));
+    SNN_CUDA(snn_stream_sync(ctx));
     return SNN_OK;
 }
 
@@ -300,6 +300,6 @@ int snn_row_flags_impl(snn_ctx* ctx, SnnChrom* c, int nunits, const int64_t* geo
     }
     SNN_CUDA(cudaMemcpyAsync(avail, davail, nb, cudaMemcpyDeviceToHost, ctx->stream));
     SNN_CUDA(cudaMemcpyAsync(live, dlive, nb, cudaMemcpyDeviceToHost, ctx->stream));
-    SNN_CUDA(cudaStreamSynchronize(ctx->stream));
+    SNN_CUDA(snn_stream_sync(ctx));
     return SNN_OK;
 }

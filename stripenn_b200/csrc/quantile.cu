@@ -294,7 +294,7 @@ int snn_quantiles_sources_impl(snn_ctx* ctx, const std::vector<QSource>& src, in
         std::vector<unsigned long long> hh((size_t)nc * (QI_NB + 1));
         SNN_CUDA(cudaMemcpy2DAsync(hh.data(), (QI_NB + 1) * 8, d_work, QW_WORDS * 8, (QI_NB + 1) * 8, nc,
                                    cudaMemcpyDeviceToHost, ctx->stream));
-        SNN_CUDA(cudaStreamSynchronize(ctx->stream));
+        SNN_CUDA(snn_stream_sync(ctx));
         bool overflow = false;
         for (int ci = 0; ci < nc && !overflow; ++ci) {
             const unsigned long long* h = hh.data() + (size_t)ci * (QI_NB + 1);
@@ -330,7 +330,7 @@ int snn_quantiles_sources_impl(snn_ctx* ctx, const std::vector<QSource>& src, in
     // only the heads of the work areas travel: total, state, group
     SNN_CUDA(cudaMemcpy2DAsync(hw.data(), QW_WORDS * 8, d_work, QW_WORDS * 8, QW_HIST * 8, nc, cudaMemcpyDeviceToHost,
                                ctx->stream));
-    SNN_CUDA(cudaStreamSynchronize(ctx->stream));
+    SNN_CUDA(snn_stream_sync(ctx));
     for (int base = 0; base < nq; base += QMAXK / 2) {
         const int m = nq - base < QMAXK / 2 ? nq - base : QMAXK / 2;
         const int K = 2 * m;
@@ -365,7 +365,7 @@ int snn_quantiles_sources_impl(snn_ctx* ctx, const std::vector<QSource>& src, in
         }
         SNN_CUDA(cudaMemcpy2DAsync(hw.data(), QW_WORDS * 8, d_work, QW_WORDS * 8, QW_HIST * 8, nc,
                                    cudaMemcpyDeviceToHost, ctx->stream));
-        SNN_CUDA(cudaStreamSynchronize(ctx->stream));
+        SNN_CUDA(snn_stream_sync(ctx));
         for (int ci = 0; ci < nc; ++ci) {
             const unsigned long long* wk = hw.data() + (size_t)ci * QW_WORDS;
             const unsigned long long* state = wk + QW_STATE;

@@ -587,7 +587,7 @@ int snn_score_multi_impl(snn_ctx* ctx, const std::vector<ScoreSlot>& slots, int6
     scope.n = launches;
     std::vector<double> host((size_t)n * 6);
     SNN_CUDA(cudaMemcpyAsync(host.data(), dout, obytes, cudaMemcpyDeviceToHost, ctx->stream));
-    SNN_CUDA(cudaStreamSynchronize(ctx->stream));
+    SNN_CUDA(snn_stream_sync(ctx));
     for (int64_t i = 0; i < n; ++i) {
         if (pvalue) pvalue[i] = host[i * 6 + 0];
         if (stripiness) stripiness[i] = host[i * 6 + 1];

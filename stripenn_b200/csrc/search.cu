@@ -704,7 +704,7 @@ static int run_batch(snn_ctx* ctx, SnnChrom* c, const ExtractPlan& pl, int frame
 static int fetch_count(snn_ctx* ctx, const ExtractPlan& pl, int* n_found) {
     int cnt[2] = {0, 0};
     SNN_CUDA(cudaMemcpyAsync(cnt, pl.counter, sizeof cnt, cudaMemcpyDeviceToHost, ctx->stream));
-    SNN_CUDA(cudaStreamSynchronize(ctx->stream));
+    SNN_CUDA(snn_stream_sync(ctx));
     if (cnt[1] || cnt[0] > pl.raw_cap)
         return snn_fail(ctx, SNN_ENOMEM, "snn_extract: more than %d raw candidates in one call", pl.raw_cap);
     *n_found = cnt[0];
@@ -745,7 +745,7 @@ int snn_extract_impl(snn_ctx* ctx, SnnChrom* c, int nq, const double* mp, const 
     if (found > 0) {
         SNN_CUDA(cudaMemcpyAsync(all.data(), pl.cand, (size_t)found * sizeof(snn_candidate), cudaMemcpyDeviceToHost,
                                  ctx->stream));
-        SNN_CUDA(cudaStreamSynchronize(ctx->stream));
+        SNN_CUDA(snn_stream_sync(ctx));
     }
     // the reference's emission order: maxpixel, window, brightness pass, up/down, pair index
     std::sort(all.begin(), all.end(), [](const snn_candidate& a, const snn_candidate& b) {
@@ -783,7 +783,7 @@ int snn_debug_stages_impl(snn_ctx* ctx, SnnChrom* c, double mp, const double* gw
     if (rc) return rc;
     FrameInfo fi;
     SNN_CUDA(cudaMemcpyAsync(&fi, pl.info, sizeof fi, cudaMemcpyDeviceToHost, ctx->stream));
-    SNN_CUDA(cudaStreamSynchronize(ctx->stream));
+    SNN_CUDA(snn_stream_sync(ctx));
     const int S = fi.S;
     *S_out = S;
     if (nz) SNN_CUDA(cudaMemcpy(nz, pl.nz, SNN_SMAX * sizeof(int32_t), cudaMemcpyDeviceToHost));

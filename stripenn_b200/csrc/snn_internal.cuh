@@ -105,6 +105,11 @@ struct snn_ctx {
     size_t scratch_bytes = 0;
     // SNN_FORCE_GENERIC=1: run the unspecialised kernels of image.cu (A/B parity tests)
     bool force_generic = false;
+    // SNN_BLOCKING_SYNC=1: wait for the stream on a blocking event instead of cudaStreamSynchronize's
+    // spin loop — for hosts where the waiting threads of all processes outnumber the cores (8 GPUs x 2
+    // device threads on a 16-core box: the spinners starved each other, sporadic +40..70 ms steps)
+    bool blocking_sync = false;
+    cudaEvent_t sync_event = nullptr;
     // timers
     bool timing = false;
     SnnTimer timers[ST_COUNT];
@@ -117,6 +122,8 @@ SnnChrom* snn_find_chrom(snn_ctx* ctx, int chrom_id);
 // Finish an asynchronous load: make the compute stream wait for the copy, build the band.
 int snn_materialize(snn_ctx* ctx, SnnChrom* c);
 int snn_scratch(snn_ctx* ctx, size_t bytes, void** out);
+// Wait until everything queued on the context's stream has finished (see snn_ctx::blocking_sync).
+cudaError_t snn_stream_sync(snn_ctx* ctx);
 
 #define SNN_CUDA(call)                                                   \
     do {                                                                 \
