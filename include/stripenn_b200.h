@@ -238,6 +238,9 @@ int snn_remove_redundant(int64_t n, const int32_t* group, const int64_t* num, co
 int snn_stage_times(snn_ctx* ctx, int cap, const char** names, double* ms, int64_t* launches);
 int snn_reset_stage_times(snn_ctx* ctx);
 int snn_enable_stage_timing(snn_ctx* ctx, int on);
+/* How the stripes of the context's scoring calls were routed since the last reset (reset = 1 clears):
+ * out[0] fast kernel (regular stripes, score_fast.cu), out[1] warp kernel, out[2] CTA kernel. */
+int snn_score_routing(snn_ctx* ctx, int64_t out[3], int reset);
 
 #ifdef __cplusplus
 }

@@ -83,6 +83,7 @@ SIGNATURES = {
     "snn_stage_times": (C.c_int, [_P, C.c_int, C.POINTER(C.c_char_p), _f64p, _i64p]),
     "snn_reset_stage_times": (C.c_int, [_P]),
     "snn_enable_stage_timing": (C.c_int, [_P, C.c_int]),
+    "snn_score_routing": (C.c_int, [_P, _i64p, C.c_int]),
 }
 
 _lib = None

@@ -188,6 +188,9 @@ static void free_chrom(snn_ctx* ctx, SnnChrom& c) {
         if (c.weight) cudaFreeAsync(c.weight, ctx->stream);
     }
     if (c.band) cudaFreeAsync(c.band, ctx->stream);
+    if (c.fband) cudaFreeAsync(c.fband, ctx->stream);
+    if (c.nanbin) cudaFreeAsync(c.nanbin, ctx->stream);
+    if (c.nanpre) cudaFreeAsync(c.nanpre, ctx->stream);
     if (c.rowptr) cudaFreeAsync(c.rowptr, ctx->stream);
 }
 
@@ -202,6 +205,7 @@ void snn_destroy(snn_ctx* ctx) {
     for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
     cudaFree(ctx->bg_sorted);
     cudaFree(ctx->bg_valid);
+    cudaFree(ctx->bg_rcp);
     cudaFree(ctx->scratch);
     if (ctx->sync_event) cudaEventDestroy(ctx->sync_event);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -585,6 +589,14 @@ int snn_reset_stage_times(snn_ctx* ctx) {
 int snn_enable_stage_timing(snn_ctx* ctx, int on) {
     if (!ctx) return snn_fail(nullptr, SNN_EINVAL, "ctx is NULL");
     ctx->timing = on != 0;
+    return SNN_OK;
+}
+
+int snn_score_routing(snn_ctx* ctx, int64_t out[3], int reset) {
+    if (!ctx || !out) return snn_fail(ctx, SNN_EINVAL, "snn_score_routing: NULL argument");
+    for (int k = 0; k < 3; ++k) out[k] = ctx->score_routed[k];
+    if (reset)
+        for (int k = 0; k < 3; ++k) ctx->score_routed[k] = 0;
     return SNN_OK;
 }
 

@@ -112,6 +112,7 @@ int snn_background_dev_impl(snn_ctx* ctx, SnnChrom* c, int64_t nsamp, const int3
 // slots = null: in[row][col] (the host tables); else sample-major in[slots[col]][row]
 __global__ void __launch_bounds__(512) k_bg_sort(const double* __restrict__ in, int64_t ncol, int npow2,
                                                  double* __restrict__ out, int32_t* __restrict__ nvalid,
+                                                 double* __restrict__ nrcp,
                                                  const int32_t* __restrict__ slots, int use_slots) {
     extern __shared__ double s[];
     const int64_t row = blockIdx.x;
@@ -147,7 +148,10 @@ __global__ void __launch_bounds__(512) k_bg_sort(const double* __restrict__ in, 
     }
     __syncthreads();
     for (int t = threadIdx.x; t < ncol; t += blockDim.x) out[row * ncol + t] = s[t];
-    if (threadIdx.x == 0) nvalid[row] = total;
+    if (threadIdx.x == 0) {
+        nvalid[row] = total;
+        nrcp[row] = 1.0 / (double)total;
+    }
 }
 
 // tables != null: host tables [4][400][ncol]; else sample-major device buffer d_buf with the host
@@ -157,8 +161,10 @@ static int set_background_run(snn_ctx* ctx, int64_t ncol, const double* tables, 
     if (ncol != ctx->bg_ncol) {   // keep the buffers when the shape repeats (every compute step)
         cudaFree(ctx->bg_sorted);
         cudaFree(ctx->bg_valid);
+        cudaFree(ctx->bg_rcp);
         ctx->bg_sorted = nullptr;
         ctx->bg_valid = nullptr;
+        ctx->bg_rcp = nullptr;
     }
     ctx->bg_ncol = 0;
     if (ncol == 0) return SNN_OK;
@@ -175,6 +181,7 @@ static int set_background_run(snn_ctx* ctx, int64_t ncol, const double* tables, 
     if (!ctx->bg_sorted) {
         SNN_CUDA(cudaMalloc(&ctx->bg_sorted, bytes));
         SNN_CUDA(cudaMalloc(&ctx->bg_valid, rows * sizeof(int32_t)));
+        SNN_CUDA(cudaMalloc(&ctx->bg_rcp, rows * sizeof(double)));
     }
     const double* src = d_buf;
     const int32_t* dslots = nullptr;
@@ -190,7 +197,7 @@ static int set_background_run(snn_ctx* ctx, int64_t ncol, const double* tables, 
     SNN_CUDA(cudaFuncSetAttribute(k_bg_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     {
         SnnScope scope(ctx, ST_BGSORT, 1);
-        k_bg_sort<<<(unsigned)rows, 512, smem, ctx->stream>>>(src, ncol, npow2, ctx->bg_sorted, ctx->bg_valid, dslots,
+        k_bg_sort<<<(unsigned)rows, 512, smem, ctx->stream>>>(src, ncol, npow2, ctx->bg_sorted, ctx->bg_valid, ctx->bg_rcp, dslots,
                                                               tables ? 0 : 1);
         SNN_LAUNCH_CHECK("k_bg_sort");
     }

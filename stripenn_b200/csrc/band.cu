@@ -98,6 +98,113 @@ int snn_band_build(snn_ctx* ctx, SnnChrom* c) {
     return SNN_OK;
 }
 
+// ---- column-major full band for the fast scoring kernel (score_fast.cu) -------------------------
+// fband[col * S + (row - col) + bw - 1] = nan0(pixel (row, col)), S = 2*bw - 1, |row - col| < bw: the
+// rows of one matrix column are contiguous on BOTH sides of the diagonal, so a warp whose lanes are
+// the rows of a stripe reads each window column as one coalesced run (the row-major band gives that
+// only below the diagonal).  NaN pixels are stored as 0 — every consumer sums nan0(pixel) — and the
+// NaN bookkeeping of scoringstripes (dead columns, finite counts) comes from the weight vector:
+// the chromosome is eligible only if every weight is NaN or |w| < 1e140, so that a pixel is NaN
+// exactly when one of its two bins has a NaN weight (products of moderate weights and int32 counts
+// stay finite).  nanbin[i] = weight i is NaN, nanpre[i] = #(NaN bins < i).
+// Algorithmic bytes: 12 B per stored pixel read + 8 B * nbins * (2*bw - 1) written.
+__global__ void k_fband_scatter(double* __restrict__ fb, const int32_t* __restrict__ b1,
+                                const int32_t* __restrict__ b2, const int32_t* __restrict__ cnt,
+                                const double* __restrict__ w, int64_t nnz, int64_t nbins, int bw) {
+    const int S = 2 * bw - 1;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < nnz; t += stride) {
+        int64_t i = b1[t], j = b2[t];
+        if (i > j) { int64_t s = i; i = j; j = s; }
+        const int64_t d = j - i;
+        if (i < 0 || j >= nbins || d >= bw) continue;
+        double v = (double)cnt[t];
+        if (w) v = v * (w[i] * w[j]);
+        v = snn_nan0(v);
+        fb[j * S + (bw - 1) - d] = v;      // (row i, col j): above the diagonal
+        fb[i * S + (bw - 1) + d] = v;      // (row j, col i): below
+    }
+}
+
+__global__ void k_nan_bins(const double* __restrict__ w, int64_t nbins, uint8_t* __restrict__ flag,
+                           int* __restrict__ ineligible) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < nbins; t += stride) {
+        const double x = w[t];
+        flag[t] = (x != x) ? 1 : 0;
+        if (x == x && !(fabs(x) < 1e140)) *ineligible = 1;
+    }
+}
+
+// exclusive prefix counts of the NaN flags, one CTA: per-thread segment sums, a block scan, a second walk
+__global__ void __launch_bounds__(1024) k_nan_prefix(const uint8_t* __restrict__ flag, int64_t nbins,
+                                                     int32_t* __restrict__ pre) {
+    __shared__ int part[1024];
+    const int64_t seg = (nbins + 1023) / 1024;
+    const int64_t a = (int64_t)threadIdx.x * seg;
+    const int64_t b = a + seg < nbins ? a + seg : nbins;
+    int s = 0;
+    for (int64_t i = a; i < b; ++i) s += flag[i];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const int v = threadIdx.x >= o ? part[threadIdx.x - o] : 0;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    int run = part[threadIdx.x] - s;
+    for (int64_t i = a; i < b; ++i) {
+        pre[i] = run;
+        run += flag[i];
+    }
+    if (threadIdx.x == 1023) pre[nbins] = part[1023];
+}
+
+// Builds the full band on first use.  c->fband_state: 0 not built, 1 ready, 2 not eligible (weights
+// outside the moderate range: the fast kernel is not used for this chromosome).
+int snn_fband_build(snn_ctx* ctx, SnnChrom* c) {
+    if (c->fband_state) return SNN_OK;
+    if (c->weight) {
+        void* scratch = nullptr;
+        if (int rc0 = snn_scratch(ctx, 64, &scratch)) return rc0;
+        int* d_flag = (int*)scratch;
+        SNN_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), ctx->stream));
+        SNN_CUDA(cudaMallocAsync(&c->nanbin, (size_t)c->nbins, ctx->stream));
+        SNN_CUDA(cudaMallocAsync(&c->nanpre, (size_t)(c->nbins + 1) * sizeof(int32_t), ctx->stream));
+        int blocks = (int)((c->nbins + 255) / 256);
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        {
+            SnnScope scope(ctx, ST_BAND, 2);
+            k_nan_bins<<<blocks, 256, 0, ctx->stream>>>(c->weight, c->nbins, c->nanbin, d_flag);
+            SNN_LAUNCH_CHECK("k_nan_bins");
+            k_nan_prefix<<<1, 1024, 0, ctx->stream>>>(c->nanbin, c->nbins, c->nanpre);
+            SNN_LAUNCH_CHECK("k_nan_prefix");
+        }
+        int inel = 0;
+        SNN_CUDA(cudaMemcpyAsync(&inel, d_flag, sizeof inel, cudaMemcpyDeviceToHost, ctx->stream));
+        SNN_CUDA(snn_stream_sync(ctx));
+        if (inel) {
+            c->fband_state = 2;
+            return SNN_OK;
+        }
+    }
+    const int64_t total = c->nbins * (2 * (int64_t)c->bw - 1);
+    SNN_CUDA(cudaMallocAsync(&c->fband, (size_t)total * sizeof(double), ctx->stream));
+    SnnScope scope(ctx, ST_BAND, 1);
+    const int threads = 256;
+    SNN_CUDA(cudaMemsetAsync(c->fband, 0, (size_t)total * sizeof(double), ctx->stream));
+    if (c->nnz > 0) {
+        int blocks = (int)((c->nnz + threads - 1) / threads);
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        k_fband_scatter<<<blocks, threads, 0, ctx->stream>>>(c->fband, c->bin1, c->bin2, c->count, c->weight, c->nnz,
+                                                             c->nbins, c->bw);
+        SNN_LAUNCH_CHECK("k_fband_scatter");
+    }
+    c->fband_state = 1;
+    return SNN_OK;
+}
+
 // ---- dense window (tests / debugging) -------------------------------------------------------
 __global__ void k_fetch(const double* __restrict__ band, int64_t nbins, int bw, int64_t i0, int64_t i1,
                         int64_t j0, int64_t j1, double* __restrict__ out) {

@@ -9,6 +9,7 @@
 //
 // Roofline: HBM.  Algorithmic bytes per stripe: 8 * h * (w + 2*bs) window bytes + 48 B out;
 // the 12.8 MB background tables are read once per launch (L2-resident afterwards).
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -429,11 +430,18 @@ __global__ void __launch_bounds__(SCORE_THREADS) k_score(MatView m, const int64_
     if (threadIdx.x == 0 && !mask_bad) o[1] = med * avgdiff;
 }
 
-// slot y: ex[y*1024 + t] -> ex[y*1024 + 512 + t] = 1 / (expected + 1e-8)   (getStripe.py:650)
+// slot y (SF_EXSTRIDE doubles): e[t] = expected -> e[512 + t] = 1 / (expected + 1e-8)   (getStripe.py:650)
+// and the mirrored table of the fast kernel, e[2048 + SF_RM + d] = 1 / (expected[min(|d|, 399)] + 1e-8)
 __global__ void k_recip_expected(double* __restrict__ ex) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    double* e = ex + (size_t)blockIdx.y * 1024;
+    double* e = ex + (size_t)blockIdx.y * SF_EXSTRIDE;
     if (t < SNN_NDIST) e[512 + t] = 1.0 / (e[t] + .00000001);
+    if (t < 2 * SF_RM) {
+        int d = t - SF_RM;
+        if (d < 0) d = -d;
+        if (d > SNN_NDIST - 1) d = SNN_NDIST - 1;
+        e[2048 + t] = 1.0 / (e[d] + .00000001);
+    }
 }
 
 // ---- host side ------------------------------------------------------------------------------------------
@@ -463,6 +471,24 @@ int snn_score_multi_impl(snn_ctx* ctx, const std::vector<ScoreSlot>& slots, int6
     static const Cls cls[3] = {{128, 4096}, {512, 12288}, {4800, 0}};
     std::vector<int32_t> worder[3];
     std::vector<std::vector<int32_t>> gorder((size_t)nslot * 3);
+    // fast kernel (score_fast.cu): regular stripes by height class; SNN_SCORE_FAST=0 switches it off
+    // (read per call: the tests compare the kernels)
+    static const int kFastH[4] = {32, 64, 128, 320};
+    std::vector<FastRec> frec[4];
+    const char* fenv = getenv("SNN_SCORE_FAST");
+    const bool fast_on = !(fenv && fenv[0] == '0') && !ctx->force_generic && bs >= 1 && bs <= 64 &&
+                         (!want_p || ctx->bg_ncol >= 1);
+    std::vector<char> slot_fast((size_t)nslot, 1), slot_used((size_t)nslot, 0);
+    for (int sl = 0; sl < nslot; ++sl) {
+        const SnnChrom* c = slots[sl].c;
+        bool ok = fast_on && c->nbins < (1ll << 30) && c->bw < SF_RM;
+        if (ok && want_s)      // the mirrored table must be finite (no nan0 around the O/E products)
+            for (int d = 0; d < SNN_NDIST && ok; ++d) {
+                const double x = 1.0 / (slots[sl].expected[d] + .00000001);
+                ok = x == x && x - x == 0.0;
+            }
+        slot_fast[sl] = ok;
+    }
     const int64_t wmaxbp = (int64_t)std::min(62, SW_MAXCOLS - 2 - 2 * bs) * r;
     for (int64_t i = 0; i < n; ++i) {
         const int sl = slot_of ? slot_of[i] : 0;
@@ -481,6 +507,43 @@ int snn_score_multi_impl(snn_ctx* ctx, const std::vector<ScoreSlot>& slots, int6
                     if ((p4 - p3) <= (int64_t)(kWarpH[k] - 2) * r) wk = k;
             }
         }
+        if (wk >= 0 && slot_fast[sl] && p2 % r == 0 && p4 % r == 0) {
+            if (!slots[sl].c->fband_state)          // the column-major full band, built on first use
+                if (int rcf = snn_fband_build(ctx, slots[sl].c)) return rcf;
+            if (slots[sl].c->fband_state != 1) slot_fast[sl] = 0;
+        }
+        if (wk >= 0 && slot_fast[sl] && p2 % r == 0 && p4 % r == 0) {
+            // regular: the p-value slices and the stripiness parts are the same three column ranges
+            // and every shape check of scoringstripes holds (the tests of k_score_warp, evaluated here)
+            const int64_t xsi = p1 / r, xei = p2 / r, R0 = p3 / r, R1 = p4 / r;
+            const int64_t h = R1 - R0, wcb = xei - xsi;
+            int64_t lmost = p1 - (int64_t)bs * r, rmost = p2 + (int64_t)bs * r;
+            if (lmost < 1) lmost = 1;
+            if (rmost > c->chromsize) rmost = c->chromsize;
+            const int64_t C0 = lmost / r, C1 = (rmost + r - 1) / r;
+            if (h >= 1 && h <= kFastH[3] && wcb >= 1 && wcb <= 62 && xsi - bs >= 1 && xei + bs <= c->nbins - 1 &&
+                C0 == xsi - bs && C1 == xei + bs) {
+                FastRec fr;
+                fr.xsi = (int32_t)xsi;
+                fr.wc = (int32_t)wcb;
+                fr.R0 = (int32_t)R0;
+                fr.h = (int32_t)h;
+                const int64_t x1 = (p1 - 1) / r, y1 = (p3 - 1) / r;
+                int mode = 3, aux = 0;
+                if (x1 == y1) mode = 0;
+                else if (xei == R1) { mode = 1; aux = (int)(R1 - y1); }
+                else if (stale && stale[i * 2] >= 0) { mode = 2 | ((stale[i * 2] ? 0 : 1) << 4); aux = stale[i * 2 + 1]; }
+                fr.mode = mode | ((p1 == p3) ? 0x100 : 0);
+                fr.aux = aux;
+                fr.slot = sl;
+                fr.idx = (int32_t)i;
+                int k = 0;
+                while (h > kFastH[k]) ++k;
+                frec[k].push_back(fr);
+                slot_used[sl] = 1;
+                continue;
+            }
+        }
         if (wk >= 0) { worder[wk].push_back((int32_t)i); continue; }
         int64_t h = 1, w = 1;
         if (p3 >= 1 && p4 >= p3 && p4 <= c->chromsize) h = (p4 + r - 1) / r - p3 / r;
@@ -491,16 +554,23 @@ int snn_score_multi_impl(snn_ctx* ctx, const std::vector<ScoreSlot>& slots, int6
         gorder[(size_t)sl * 3 + k].push_back((int32_t)i);
     }
 
+    for (int k = 0; k < 4; ++k) ctx->score_routed[0] += (int64_t)frec[k].size();
+    for (int k = 0; k < 3; ++k) ctx->score_routed[1] += (int64_t)worder[k].size();
+    for (const auto& g : gorder) ctx->score_routed[2] += (int64_t)g.size();
+
     // ---- device scratch
     const size_t pbytes = up256((size_t)n * 4 * sizeof(int64_t));
     const size_t sbytes = stale ? up256((size_t)n * 2 * sizeof(int32_t)) : 0;
-    const size_t ebytes = up256((size_t)nslot * 1024 * sizeof(double));   // expected | 1/(expected+1e-8), 512 each
+    const size_t ebytes = up256((size_t)nslot * SF_EXSTRIDE * sizeof(double));   // expected | 1/(expected+1e-8) | mirrored
     const size_t cbytes = up256((size_t)nslot * sizeof(ChromDev));
     const size_t orbytes = up256((size_t)n * sizeof(int32_t));
     const size_t slbytes = slot_of ? up256((size_t)n * sizeof(int32_t)) : 0;
-    const size_t obytes = (size_t)n * 6 * sizeof(double);
+    const size_t obytes = up256((size_t)n * 6 * sizeof(double));
+    size_t nfast = 0;
+    for (int k = 0; k < 4; ++k) nfast += frec[k].size();
+    const size_t fbytes = up256(nfast * sizeof(FastRec));
     void* scratch = nullptr;
-    int rc = snn_scratch(ctx, pbytes + sbytes + ebytes + cbytes + orbytes + slbytes + obytes, &scratch);
+    int rc = snn_scratch(ctx, pbytes + sbytes + ebytes + cbytes + orbytes + slbytes + obytes + fbytes, &scratch);
     if (rc) return rc;
     char* b = (char*)scratch;
     int64_t* dpos = (int64_t*)b;                      b += pbytes;
@@ -509,7 +579,14 @@ int snn_score_multi_impl(snn_ctx* ctx, const std::vector<ScoreSlot>& slots, int6
     ChromDev* dcd = (ChromDev*)b;                     b += cbytes;
     int32_t* dorder = (int32_t*)b;                    b += orbytes;
     int32_t* dslot = slot_of ? (int32_t*)b : nullptr; b += slbytes;
-    double* dout = (double*)b;
+    double* dout = (double*)b;                        b += obytes;
+    FastRec* dfrec = (FastRec*)b;
+    std::vector<FastRec> frec_all;           // lives until the final synchronisation below
+    if (nfast) {
+        frec_all.reserve(nfast);
+        for (int k = 0; k < 4; ++k) frec_all.insert(frec_all.end(), frec[k].begin(), frec[k].end());
+        SNN_CUDA(cudaMemcpyAsync(dfrec, frec_all.data(), nfast * sizeof(FastRec), cudaMemcpyHostToDevice, ctx->stream));
+    }
     SNN_CUDA(cudaMemcpyAsync(dpos, pos, (size_t)n * 4 * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
     if (stale)
         SNN_CUDA(cudaMemcpyAsync(dstale, stale, (size_t)n * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -521,24 +598,41 @@ int snn_score_multi_impl(snn_ctx* ctx, const std::vector<ScoreSlot>& slots, int6
     for (int k = 0; k < 3; ++k) { wstart[k] = flat.size(); flat.insert(flat.end(), worder[k].begin(), worder[k].end()); }
     std::vector<size_t> gstart(gorder.size());
     for (size_t g = 0; g < gorder.size(); ++g) { gstart[g] = flat.size(); flat.insert(flat.end(), gorder[g].begin(), gorder[g].end()); }
-    SNN_CUDA(cudaMemcpyAsync(dorder, flat.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    if (!flat.empty())
+        SNN_CUDA(cudaMemcpyAsync(dorder, flat.data(), flat.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     std::vector<ChromDev> hcd((size_t)nslot);
-    std::vector<double> hex((size_t)nslot * 1024, 0.0);
+    std::vector<double> hex((size_t)nslot * SF_EXSTRIDE, 0.0);
     for (int sl = 0; sl < nslot; ++sl) {
         hcd[sl].m = snn_view(slots[sl].c);
         hcd[sl].chromsize = slots[sl].c->chromsize;
         hcd[sl].nbins = slots[sl].c->nbins;
-        hcd[sl].rex = want_s ? dex + (size_t)sl * 1024 + 512 : nullptr;
-        if (want_s) memcpy(hex.data() + (size_t)sl * 1024, slots[sl].expected, SNN_NDIST * sizeof(double));
+        hcd[sl].rex = want_s ? dex + (size_t)sl * SF_EXSTRIDE + 512 : nullptr;
+        hcd[sl].rexm = want_s ? dex + (size_t)sl * SF_EXSTRIDE + 2048 + SF_RM : nullptr;
+        hcd[sl].fb = slots[sl].c->fband ? slots[sl].c->fband + (slots[sl].c->bw - 1) : nullptr;
+        hcd[sl].fbT = 2 * (int64_t)slots[sl].c->bw - 2;
+        hcd[sl].nanbin = slots[sl].c->nanbin;
+        hcd[sl].nanpre = slots[sl].c->nanpre;
+        if (want_s) memcpy(hex.data() + (size_t)sl * SF_EXSTRIDE, slots[sl].expected, SNN_NDIST * sizeof(double));
     }
     SNN_CUDA(cudaMemcpyAsync(dcd, hcd.data(), (size_t)nslot * sizeof(ChromDev), cudaMemcpyHostToDevice, ctx->stream));
     int launches = 0;
     SnnScope scope(ctx, ST_SCORE, 0);
     if (want_s) {
         SNN_CUDA(cudaMemcpyAsync(dex, hex.data(), hex.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-        k_recip_expected<<<dim3(2, nslot), 256, 0, ctx->stream>>>(dex);
+        k_recip_expected<<<dim3(2 * SF_RM / 256, nslot), 256, 0, ctx->stream>>>(dex);
         SNN_LAUNCH_CHECK("k_recip_expected");
         ++launches;
+    }
+    // ---- fast kernel: regular stripes, one launch per height class, all chromosomes together
+    {
+        size_t off = 0;
+        for (int k = 0; k < 4; ++k) {
+            if (frec[k].empty()) continue;
+            rc = snn_launch_score_fast(ctx, dcd, dfrec + off, (int)frec[k].size(), bs, kFastH[k], want_p, want_s, dout);
+            if (rc) return rc;
+            off += frec[k].size();
+            ++launches;
+        }
     }
     // ---- warp kernel: one launch per height class, all chromosomes together
     for (int k = 0; k < 3; ++k) {
@@ -586,7 +680,7 @@ int snn_score_multi_impl(snn_ctx* ctx, const std::vector<ScoreSlot>& slots, int6
     }
     scope.n = launches;
     std::vector<double> host((size_t)n * 6);
-    SNN_CUDA(cudaMemcpyAsync(host.data(), dout, obytes, cudaMemcpyDeviceToHost, ctx->stream));
+    SNN_CUDA(cudaMemcpyAsync(host.data(), dout, (size_t)n * 6 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     SNN_CUDA(snn_stream_sync(ctx));
     for (int64_t i = 0; i < n; ++i) {
         if (pvalue) pvalue[i] = host[i * 6 + 0];

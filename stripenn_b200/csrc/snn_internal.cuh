@@ -44,6 +44,13 @@ struct SnnChrom {
     int32_t* count = nullptr;  // device
     double* weight = nullptr;  // device or null
     double* band = nullptr;    // device, nbins * bw
+    // device, nbins * (2*bw - 1): the band stored by COLUMN with both sides of the diagonal,
+    // fband[col * (2*bw-1) + (row - col) + bw - 1] = pixel (row, col); built on the first fast-scoring
+    // call (snn_fband_build), so a stripe's column is one contiguous run of rows (score_fast.cu)
+    double* fband = nullptr;
+    uint8_t* nanbin = nullptr;  // device, nbins: weight is NaN (null without weights)
+    int32_t* nanpre = nullptr;  // device, nbins + 1: exclusive prefix counts of nanbin
+    int fband_state = 0;        // 0 not built, 1 ready, 2 not eligible (band.cu: snn_fband_build)
     int64_t* rowptr = nullptr; // device, nbins + 1: CSR row pointers into the (bin1, bin2)-sorted pixels
     // snn_load_chrom_async: the pixel arrays are still travelling on the copy stream; `ready` fires
     // when they have landed and the band is built on first use (snn_materialize)
@@ -96,6 +103,7 @@ struct snn_ctx {
     // NaNs moved to the end; bg_valid[row] = number of non-NaN entries.
     double* bg_sorted = nullptr;
     int32_t* bg_valid = nullptr;
+    double* bg_rcp = nullptr;      // 1 / bg_valid[row] (correctly rounded; inf for an empty row)
     int64_t bg_ncol = 0;
     // --mask of scoringstripes (snn_set_mask): chromosome id (< 0: none), start/end in bp
     int mask_chrom = -1;
@@ -110,6 +118,8 @@ struct snn_ctx {
     // device threads on a 16-core box: the spinners starved each other, sporadic +40..70 ms steps)
     bool blocking_sync = false;
     cudaEvent_t sync_event = nullptr;
+    // stripes routed to the fast / warp / CTA scoring kernel (snn_score_routing)
+    int64_t score_routed[3] = {0, 0, 0};
     // timers
     bool timing = false;
     SnnTimer timers[ST_COUNT];
@@ -191,6 +201,7 @@ __host__ __device__ __forceinline__ void snn_pyslice(int64_t a, int64_t b, int64
 
 // ---- per-TU entry points used by api.cu ---------------------------------------------------
 int snn_band_build(snn_ctx* ctx, SnnChrom* c);
+int snn_fband_build(snn_ctx* ctx, SnnChrom* c);
 int snn_quantiles_impl(snn_ctx* ctx, SnnChrom* c, int nq, const double* q, double* out);
 // One source of a quantile job: the positive pixels of chromosome c, whole (sel = false) or
 // restricted like getQuantile_slow's genome-wide slices (quantile.cu: QChrom).

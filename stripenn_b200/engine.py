@@ -380,6 +380,16 @@ class Device:
         return {names[i].decode(): dict(ms=ms[i], launches=int(launches[i])) for i in range(n)}
 
 
+def _score_routing(self, reset=True):
+    """(fast, warp, CTA) stripe counts of the scoring calls since the last reset."""
+    out = (C.c_int64 * 3)()
+    check(self.lib.snn_score_routing(self.h, out, 1 if reset else 0), self.h)
+    return tuple(int(v) for v in out)
+
+
+Device.score_routing = _score_routing
+
+
 def remove_redundant_mask(group, num, pos, h, w, key, by: str):
     """getStripe.RemoveRedundant keep-mask (host C++ in the same library)."""
     lib = _lib.load()
