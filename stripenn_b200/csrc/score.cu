@@ -473,8 +473,7 @@ int snn_score_multi_impl(snn_ctx* ctx, const std::vector<ScoreSlot>& slots, int6
     std::vector<std::vector<int32_t>> gorder((size_t)nslot * 3);
     // fast kernel (score_fast.cu): regular stripes by height class; SNN_SCORE_FAST=0 switches it off
     // (read per call: the tests compare the kernels)
-    static const int kFastH[4] = {32, 64, 128, 320};
-    std::vector<FastRec> frec[4];
+    std::vector<FastRec> frec;
     const char* fenv = getenv("SNN_SCORE_FAST");
     const bool fast_on = !(fenv && fenv[0] == '0') && !ctx->force_generic && bs >= 1 && bs <= 64 &&
                          (!want_p || ctx->bg_ncol >= 1);
@@ -521,7 +520,7 @@ int snn_score_multi_impl(snn_ctx* ctx, const std::vector<ScoreSlot>& slots, int6
             if (lmost < 1) lmost = 1;
             if (rmost > c->chromsize) rmost = c->chromsize;
             const int64_t C0 = lmost / r, C1 = (rmost + r - 1) / r;
-            if (h >= 1 && h <= kFastH[3] && wcb >= 1 && wcb <= 62 && xsi - bs >= 1 && xei + bs <= c->nbins - 1 &&
+            if (h >= 1 && h <= SF_HMAX && wcb >= 1 && wcb <= 62 && xsi - bs >= 1 && xei + bs <= c->nbins - 1 &&
                 C0 == xsi - bs && C1 == xei + bs) {
                 FastRec fr;
                 fr.xsi = (int32_t)xsi;
@@ -537,9 +536,7 @@ int snn_score_multi_impl(snn_ctx* ctx, const std::vector<ScoreSlot>& slots, int6
                 fr.aux = aux;
                 fr.slot = sl;
                 fr.idx = (int32_t)i;
-                int k = 0;
-                while (h > kFastH[k]) ++k;
-                frec[k].push_back(fr);
+                frec.push_back(fr);
                 slot_used[sl] = 1;
                 continue;
             }
@@ -554,7 +551,7 @@ int snn_score_multi_impl(snn_ctx* ctx, const std::vector<ScoreSlot>& slots, int6
         gorder[(size_t)sl * 3 + k].push_back((int32_t)i);
     }
 
-    for (int k = 0; k < 4; ++k) ctx->score_routed[0] += (int64_t)frec[k].size();
+    ctx->score_routed[0] += (int64_t)frec.size();
     for (int k = 0; k < 3; ++k) ctx->score_routed[1] += (int64_t)worder[k].size();
     for (const auto& g : gorder) ctx->score_routed[2] += (int64_t)g.size();
 
@@ -566,9 +563,20 @@ int snn_score_multi_impl(snn_ctx* ctx, const std::vector<ScoreSlot>& slots, int6
     const size_t orbytes = up256((size_t)n * sizeof(int32_t));
     const size_t slbytes = slot_of ? up256((size_t)n * sizeof(int32_t)) : 0;
     const size_t obytes = up256((size_t)n * 6 * sizeof(double));
-    size_t nfast = 0;
-    for (int k = 0; k < 4; ++k) nfast += frec[k].size();
-    const size_t fbytes = up256(nfast * sizeof(FastRec));
+    const size_t nfast = frec.size();
+    // tallest first: the warps of the fast kernel take the stripes from an atomic counter
+    if (nfast) {                                   // counting sort by height (stable; std::stable_sort took 5 ms per 100k)
+        std::vector<int32_t> start(SF_HMAX + 2, 0);
+        for (const FastRec& f : frec) ++start[SF_HMAX - f.h + 1];
+        for (int k = 1; k <= SF_HMAX + 1; ++k) start[k] += start[k - 1];
+        std::vector<FastRec> sorted(nfast);
+        for (const FastRec& f : frec) sorted[start[SF_HMAX - f.h]++] = f;
+        frec.swap(sorted);
+    }
+    const int fgrid = snn_score_fast_grid((int)nfast);
+    const bool any_tall = nfast && frec[0].h > SF_HSM;
+    const size_t fbytes = up256(nfast * sizeof(FastRec)) + 256 +
+                          (any_tall ? up256((size_t)fgrid * SF_WARPS * 4 * SF_HMAX * sizeof(double)) : 0);
     void* scratch = nullptr;
     int rc = snn_scratch(ctx, pbytes + sbytes + ebytes + cbytes + orbytes + slbytes + obytes + fbytes, &scratch);
     if (rc) return rc;
@@ -581,12 +589,10 @@ int snn_score_multi_impl(snn_ctx* ctx, const std::vector<ScoreSlot>& slots, int6
     int32_t* dslot = slot_of ? (int32_t*)b : nullptr; b += slbytes;
     double* dout = (double*)b;                        b += obytes;
     FastRec* dfrec = (FastRec*)b;
-    std::vector<FastRec> frec_all;           // lives until the final synchronisation below
-    if (nfast) {
-        frec_all.reserve(nfast);
-        for (int k = 0; k < 4; ++k) frec_all.insert(frec_all.end(), frec[k].begin(), frec[k].end());
-        SNN_CUDA(cudaMemcpyAsync(dfrec, frec_all.data(), nfast * sizeof(FastRec), cudaMemcpyHostToDevice, ctx->stream));
-    }
+    int* dnext = (int*)((char*)dfrec + up256(nfast * sizeof(FastRec)));
+    double* dtall = (double*)((char*)dnext + 256);
+    if (nfast)
+        SNN_CUDA(cudaMemcpyAsync(dfrec, frec.data(), nfast * sizeof(FastRec), cudaMemcpyHostToDevice, ctx->stream));
     SNN_CUDA(cudaMemcpyAsync(dpos, pos, (size_t)n * 4 * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
     if (stale)
         SNN_CUDA(cudaMemcpyAsync(dstale, stale, (size_t)n * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -623,16 +629,11 @@ int snn_score_multi_impl(snn_ctx* ctx, const std::vector<ScoreSlot>& slots, int6
         SNN_LAUNCH_CHECK("k_recip_expected");
         ++launches;
     }
-    // ---- fast kernel: regular stripes, one launch per height class, all chromosomes together
-    {
-        size_t off = 0;
-        for (int k = 0; k < 4; ++k) {
-            if (frec[k].empty()) continue;
-            rc = snn_launch_score_fast(ctx, dcd, dfrec + off, (int)frec[k].size(), bs, kFastH[k], want_p, want_s, dout);
-            if (rc) return rc;
-            off += frec[k].size();
-            ++launches;
-        }
+    // ---- fast kernel: every regular stripe of every chromosome in one launch
+    if (nfast) {
+        rc = snn_launch_score_fast(ctx, dcd, dfrec, (int)nfast, bs, want_p, want_s, dnext, dtall, fgrid, dout);
+        if (rc) return rc;
+        ++launches;
     }
     // ---- warp kernel: one launch per height class, all chromosomes together
     for (int k = 0; k < 3; ++k) {

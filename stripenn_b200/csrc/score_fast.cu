@@ -49,19 +49,99 @@ __device__ __forceinline__ double f_div(double a, double b, double y) {
     return fma(r, y, q);
 }
 
-// One column part of one window row: raw and O/E sums in column order (the orders of k_score_warp;
-// the full band holds nan0(pixel), so there is no NaN test).  prow -> pixel (row, column 0) as
-// bytes, T8 = column step in bytes, columns [c0, c0 + ncols); rp -> mirrored 1/(expected+1e-8) entry
-// of column c0 (the right part's expected is shifted by one bin, getStripe.py:696-698: SHIFT = 1).
+// The three column parts of one window row — left flank, centre, right flank — as raw and O/E sums
+// in column order per part (the orders of k_score_warp; the full band holds nan0(pixel), so there is
+// no NaN test).  The parts advance together, two columns each per iteration: six independent
+// accumulation chains and twelve loads in flight per lane.  prow -> pixel (row, column 0) as bytes,
+// T8 = column step in bytes; rp -> mirrored 1/(expected+1e-8) entry of column C0 (the right part's
+// expected is shifted by one bin, getStripe.py:696-698).
+// Every address is base + int * int, forced to ONE IMAD.WIDE through PTX (left to itself the compiler
+// merged the bases into the products and expanded full 64-bit multiplications: 10-14 instructions per cell).
+__device__ __forceinline__ const double* f_at(const void* base, int k, int step) {
+    unsigned long long r;
+    asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(r) : "r"(k), "r"(step), "l"(base));
+    return reinterpret_cast<const double*>(r);
+}
+
+template <bool WS>
+__device__ __forceinline__ void f_run(const char* __restrict__ prow, int T8, int c, const double* __restrict__ rp, int e,
+                                      int n, double& sraw, double& soe) {
+    const double* pe = f_at(rp, e, 8);
+#pragma unroll 1
+    for (; n >= 2; n -= 2, c += 2, pe += 2) {
+        const double v0 = __ldg(f_at(prow, c, T8)), v1 = __ldg(f_at(prow + T8, c, T8));
+        if (WS) {
+            const double e0 = __ldg(pe), e1 = __ldg(pe + 1);
+            soe += v0 * e0;
+            soe += v1 * e1;
+        }
+        sraw += v0;
+        sraw += v1;
+    }
+    if (n > 0) {
+        const double v0 = __ldg(f_at(prow, c, T8));
+        if (WS) soe += v0 * __ldg(pe);
+        sraw += v0;
+    }
+}
+
+template <bool WS>
+__device__ __forceinline__ void f_row(const char* __restrict__ prow, int T8, int C0, int xsi, int wc, int bs,
+                                      const double* __restrict__ rp, double& rl, double& ol, double& rc, double& oc,
+                                      double& rr, double& orr) {
+    const int m = bs < wc ? bs : wc;
+    // one counter, fixed bases
+    const char* l0 = reinterpret_cast<const char*>(f_at(prow, C0, T8));
+    const char* c0p = reinterpret_cast<const char*>(f_at(prow, xsi, T8));
+    const char* r0 = reinterpret_cast<const char*>(f_at(prow, xsi + wc, T8));
+    const char* l1 = l0 + T8;
+    const char* c1p = c0p + T8;
+    const char* r1 = r0 + T8;
+    const double* el = rp;
+    const double* ec = rp + bs;
+    const double* er = rp + (bs + wc + 1);
+    int k = 0;
+#pragma unroll 1
+    for (; k + 2 <= m; k += 2) {
+        const double a0 = __ldg(f_at(l0, k, T8)), a1 = __ldg(f_at(l1, k, T8));
+        const double c0 = __ldg(f_at(c0p, k, T8)), c1 = __ldg(f_at(c1p, k, T8));
+        const double b0 = __ldg(f_at(r0, k, T8)), b1 = __ldg(f_at(r1, k, T8));
+        if (WS) {
+            const double* qa = f_at(el, k, 8);
+            const double* qc = f_at(ec, k, 8);
+            const double* qb = f_at(er, k, 8);
+            const double ea0 = __ldg(qa), ea1 = __ldg(qa + 1);
+            const double ec0 = __ldg(qc), ec1 = __ldg(qc + 1);
+            const double eb0 = __ldg(qb), eb1 = __ldg(qb + 1);
+            ol += a0 * ea0;
+            oc += c0 * ec0;
+            orr += b0 * eb0;
+            ol += a1 * ea1;
+            oc += c1 * ec1;
+            orr += b1 * eb1;
+        }
+        rl += a0;
+        rc += c0;
+        rr += b0;
+        rl += a1;
+        rc += c1;
+        rr += b1;
+    }
+    f_run<WS>(prow, T8, C0 + k, rp, k, bs - k, rl, ol);
+    f_run<WS>(prow, T8, xsi + k, rp, bs + k, wc - k, rc, oc);
+    f_run<WS>(prow, T8, xsi + wc + k, rp, bs + wc + 1 + k, bs - k, rr, orr);
+}
+
+#ifdef SF_OLDROW
 template <int SHIFT, bool WS>
 __device__ __forceinline__ void f_part(const char* __restrict__ prow, int T8, int c0, const double* __restrict__ rp,
                                        int ncols, double& sraw, double& soe) {
     int k = 0;
-#define F_LD(c) __ldg(reinterpret_cast<const double*>(prow + (int64_t)(c) * (int64_t)T8))
+#define F_LD1(c) __ldg(reinterpret_cast<const double*>(prow + (int64_t)(c) * (int64_t)T8))
 #pragma unroll 1
     for (; k + 4 <= ncols; k += 4) {
         const int c = c0 + k;
-        const double v0 = F_LD(c), v1 = F_LD(c + 1), v2 = F_LD(c + 2), v3 = F_LD(c + 3);
+        const double v0 = F_LD1(c), v1 = F_LD1(c + 1), v2 = F_LD1(c + 2), v3 = F_LD1(c + 3);
         if (WS) {
             const double e0 = __ldg(rp + SHIFT), e1 = __ldg(rp + SHIFT + 1), e2 = __ldg(rp + SHIFT + 2),
                          e3 = __ldg(rp + SHIFT + 3);
@@ -78,13 +158,14 @@ __device__ __forceinline__ void f_part(const char* __restrict__ prow, int T8, in
     }
 #pragma unroll 1
     for (; k < ncols; ++k) {
-        const double v0 = F_LD(c0 + k);
+        const double v0 = F_LD1(c0 + k);
         if (WS) soe += v0 * __ldg(rp + SHIFT);
         rp += 1;
         sraw += v0;
     }
-#undef F_LD
+#undef F_LD1
 }
+#endif
 
 // np.median of a[0..n) (shared memory, n >= 1, no NaN) by quickselect: every round
 // takes a pivot from the remaining candidates, counts the candidates below / not above it with two
@@ -149,27 +230,61 @@ __device__ double f_median(const double* a, int n, int lane) {
     return (xlo + xhi) / 2.0;
 }
 
-template <int KC, bool WP, bool WS>
-__global__ void __launch_bounds__(SF_WARPS * 32) k_score_fast(const ChromDev* __restrict__ cds,
+// Runtime choice of the median's slot count (the register array must be compile-time)
+__device__ __forceinline__ double f_median_any(const double* a, int n, int lane) {
+    if (n <= 32) return f_median<1>(a, n, lane);
+    if (n <= 64) return f_median<2>(a, n, lane);
+    if (n <= 128) return f_median<4>(a, n, lane);
+    return f_median<SF_HMAX / 32>(a, n, lane);
+}
+
+// ONE launch for every regular stripe of a call.  The host sorts the stripes tallest first and the
+// warps take them from an atomic counter, so the long stripes start first and the short ones fill
+// the tail (per-class launches with a static split left the >128-row class at 11-19 % of the
+// warps resident, 425-680 us for 8 % of the stripes: profiles/r02x).  Row results of stripes up to
+// SF_HSM rows live in shared memory (4 KB per warp), taller stripes use the warp's slice of `tall`.
+template <bool WP, bool WS>
+__global__ void __launch_bounds__(SF_WARPS * 32, SF_MINB) k_score_fast(const ChromDev* __restrict__ cds,
                                                             const FastRec* __restrict__ recs, int n,
+                                                            int* __restrict__ next,
                                                             const double* __restrict__ bg,
                                                             const int32_t* __restrict__ bg_valid,
                                                             const double* __restrict__ bg_rcp, int bg_ncol,
                                                             int bg_half, double pmin, int bs,
+                                                            double* __restrict__ tall,
                                                             double* __restrict__ out) {
-    constexpr int HCAP = KC * 32;
+    constexpr int KC = SF_HMAX / 32;
     extern __shared__ double sh[];
     double* rcp = sh;                                  // rcp[k] = 1 / k, k <= 64
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double* pv = sh + 72 + (size_t)warp * 4 * HCAP;    // per-row p-values, later the compacted centre means
-    double* scA = pv + HCAP;                           // O/E row sums -> row means: centre
-    double* slA = scA + HCAP;                          //                            left
-    double* srA = slA + HCAP;                          //                            right
+    double* piv = sh + 72;                             // first search steps of the hot background rows
+    constexpr int PIVN = WP ? 4 * SF_PIVD * SF_PNODE : 0;
+    double* const sm_rows = sh + 72 + PIVN + (size_t)warp * 4 * SF_HSM;
+    double* const gl_rows = tall + ((size_t)blockIdx.x * SF_WARPS + warp) * 4 * SF_HMAX;
     if (threadIdx.x <= 64) rcp[threadIdx.x] = 1.0 / (double)threadIdx.x;
+    const bool use_piv = SF_PIVD > 0 && WP && (bg_half >> SF_PLEV) >= 1;
+    if (use_piv) {
+        // piv[(t * SF_PIVD + d) * SF_PNODE + (2^l - 1) + m] = entry probed at step l after the path m:
+        // position (2m + 1) * (bg_half >> l), +inf past the row (never taken)
+        for (int t = threadIdx.x; t < PIVN; t += blockDim.x) {
+            const int node = t % SF_PNODE, rd = t / SF_PNODE;
+            const int row = (rd / (SF_PIVD > 0 ? SF_PIVD : 1)) * SNN_NDIST + rd % (SF_PIVD > 0 ? SF_PIVD : 1);
+            int l = 0;
+            while ((2 << l) - 1 <= node) ++l;
+            const int m = node - ((1 << l) - 1);
+            const int posn = (2 * m + 1) * (bg_half >> l);
+            piv[t] = posn <= bg_ncol ? __ldg(bg + (int64_t)row * bg_ncol + posn - 1)
+                                     : __longlong_as_double(0x7ff0000000000000LL);
+        }
+    }
     __syncthreads();
     const double ybs = rcp[bs], dbs = (double)bs;
 
-    for (int it = blockIdx.x * SF_WARPS + warp; it < n; it += gridDim.x * SF_WARPS) {
+    for (;;) {
+        int it = 0;
+        if (lane == 0) it = atomicAdd(next, 1);
+        it = __shfl_sync(FULL, it, 0);
+        if (it >= n) break;
         const int4 g0 = __ldg(reinterpret_cast<const int4*>(recs + it));
         const int4 g1 = __ldg(reinterpret_cast<const int4*>(recs + it) + 1);
         const int xsi = g0.x, wc = g0.y, R0 = g0.z, h = g0.w;
@@ -183,6 +298,11 @@ __global__ void __launch_bounds__(SF_WARPS * 32) k_score_fast(const ChromDev* __
         const double* __restrict__ rexm = cd->rexm;
         const int C0 = xsi - bs;
         const double ywc = rcp[wc], dwc = (double)wc;
+        const int cap = h <= SF_HSM ? SF_HSM : SF_HMAX;
+        double* pv = h <= SF_HSM ? sm_rows : gl_rows;   // per-row p-values, later the compacted centre means
+        double* scA = pv + cap;                          // O/E row sums -> row means: centre
+        double* slA = scA + cap;                         //                            left
+        double* srA = slA + cap;                         //                            right
         double res0 = f_qnan(), res1 = f_qnan(), res2 = f_qnan(), res3 = f_qnan(), res4 = f_qnan(), res5 = f_qnan();
         double tot_obs = 0.0;
         int pnan = 0;
@@ -196,9 +316,13 @@ __global__ void __launch_bounds__(SF_WARPS * 32) k_score_fast(const ChromDev* __
             const char* prow = reinterpret_cast<const char*>(fb + row);
             const double* rp = WS ? rexm + (C0 - row) : nullptr;
             double rl = 0.0, ol = 0.0, rc = 0.0, oc = 0.0, rr = 0.0, orr = 0.0;
+#ifdef SF_OLDROW
             f_part<0, WS>(prow, T8, C0, rp, bs, rl, ol);
             f_part<0, WS>(prow, T8, xsi, rp + bs, wc, rc, oc);
             f_part<1, WS>(prow, T8, xsi + wc, rp + bs + wc, bs, rr, orr);
+#else
+            f_row<WS>(prow, T8, C0, xsi, wc, bs, rp, rl, ol, rc, oc, rr, orr);
+#endif
 
             if (WP) {
                 const double mc = f_div(rc, dwc, ywc), ml = f_div(rl, dbs, ybs), mr = f_div(rr, dbs, ybs);
@@ -216,18 +340,34 @@ __global__ void __launch_bounds__(SF_WARPS * 32) k_score_fast(const ChromDev* __
                 const int rowl = (table == 0 ? 0 : 2) * SNN_NDIST + dq, rowr = rowl + SNN_NDIST;
                 const int nl = __ldg(bg_valid + rowl), nr = __ldg(bg_valid + rowr);
                 const double yl = __ldg(bg_rcp + rowl), yr = __ldg(bg_rcp + rowr);
-                const double* __restrict__ ra = bg + (int64_t)rowl * bg_ncol - 1;
-                const double* __restrict__ rb = bg + (int64_t)rowr * bg_ncol - 1;
-                // lower bounds: #(row < v); entries past the valid ones are +inf (k_bg_sort)
-                int pa = 0, pb = 0;
+                // lower bounds #(row < v) by halving steps: probe position pa + step, never past the
+                // row (entries past the valid ones are +inf, k_bg_sort).  The first SF_PLEV steps of
+                // the rows with d < SF_PIVD come from the CTA's shared-memory copy of those pivots —
+                // scattered global loads cost the L1 one sector per lane each (ncu r02v: 58 % of the
+                // kernel's L1 sectors were these searches)
+                const int basel = rowl * bg_ncol - 1, baser = rowr * bg_ncol - 1;
+                int pa = 0, pb = 0, step = bg_half;
+                if (use_piv && __all_sync(FULL, ok && d < SF_PIVD)) {
+                    const double* __restrict__ qa = piv + ((table == 0 ? 0 : 2) * SF_PIVD + dq) * SF_PNODE;
+                    const double* __restrict__ qb = qa + SF_PIVD * SF_PNODE;
+                    int ma = 0, mb = 0;
+#pragma unroll
+                    for (int l = 0; l < SF_PLEV; ++l) {
+                        const double xa = qa[(1 << l) - 1 + ma], xb = qb[(1 << l) - 1 + mb];
+                        ma = 2 * ma + (xa < dl ? 1 : 0);
+                        mb = 2 * mb + (xb < dr ? 1 : 0);
+                    }
+                    step = bg_half >> SF_PLEV;
+                    pa = ma * (2 * step);
+                    pb = mb * (2 * step);
+                }
 #pragma unroll 1
-                for (int step = bg_half; step > 0; step >>= 1) {
+                for (; step > 0; step >>= 1) {
                     const int ia = pa + step, ib = pb + step;
-                    const bool ga = ia <= bg_ncol, gb = ib <= bg_ncol;
-                    const double xa = ga ? __ldg(ra + ia) : dl;
-                    const double xb = gb ? __ldg(rb + ib) : dr;
-                    if (xa < dl) pa = ia;
-                    if (xb < dr) pb = ib;
+                    const double xa = __ldg(bg + (basel + min(ia, bg_ncol)));
+                    const double xb = __ldg(bg + (baser + min(ib, bg_ncol)));
+                    if (ia <= bg_ncol && xa < dl) pa = ia;
+                    if (ib <= bg_ncol && xb < dr) pb = ib;
                 }
                 const int cl = (dl == dl) ? nl - pa : 0, cr = (dr == dr) ? nr - pb : 0;
                 const double a = f_div((double)cl, (double)nl, yl);
@@ -251,7 +391,7 @@ __global__ void __launch_bounds__(SF_WARPS * 32) k_score_fast(const ChromDev* __
         __syncwarp();
 
         // ================================ p-value: np.median over the rows ==========================
-        if (WP) res0 = __any_sync(FULL, pnan) ? f_qnan() : f_median<KC>(pv, h, lane);
+        if (WP) res0 = __any_sync(FULL, pnan) ? f_qnan() : f_median_any(pv, h, lane);
 
         if (WS) {
             // ---- dead columns (all-NaN inside the stripe's rows) and the finite-cell count, from the
@@ -379,7 +519,7 @@ __global__ void __launch_bounds__(SF_WARPS * 32) k_score_fast(const ChromDev* __
                     nm += __popc(b);
                 }
                 __syncwarp();
-                const double med = nm ? f_median<KC>(pv, nm, lane) : f_qnan();
+                const double med = nm ? f_median_any(pv, nm, lane) : f_qnan();
                 res1 = med * avgdiff;
             }
             // getMean (getStripe.py:501-534)
@@ -395,29 +535,22 @@ __global__ void __launch_bounds__(SF_WARPS * 32) k_score_fast(const ChromDev* __
     }
 }
 
-template <int KC>
-static int launch_kc(snn_ctx* ctx, const ChromDev* cds, const FastRec* recs, int n, int bs, int want_p, int want_s,
-                     double* out) {
-    const size_t smem = (72 + (size_t)SF_WARPS * 4 * KC * 32) * sizeof(double);
+int snn_launch_score_fast(snn_ctx* ctx, const ChromDev* cds, const FastRec* recs, int n, int bs, int want_p, int want_s,
+                          int* next, double* tall, int grid, double* out) {
+    if (n <= 0) return SNN_OK;
+    const size_t smem = (72 + (want_p ? 4 * SF_PIVD * SF_PNODE : 0) + (size_t)SF_WARPS * 4 * SF_HSM) * sizeof(double);
     int bg_half = 1;
     while (bg_half * 2 <= ctx->bg_ncol) bg_half <<= 1;     // largest power of two <= ncol: positions up to 2*half - 1 >= ncol
     const double pmin = ctx->bg_ncol > 0 ? 1.0 / (double)ctx->bg_ncol : 0.0;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int per_sm = (int)((size_t)(220 * 1024) / (smem + 1024));
-    if (per_sm > 8) per_sm = 8;
-    if (per_sm < 1) per_sm = 1;
-    int grid = (n + SF_WARPS - 1) / SF_WARPS;
-    if (grid > sms * per_sm) grid = sms * per_sm;
+    SNN_CUDA(cudaMemsetAsync(next, 0, sizeof(int), ctx->stream));
 #define SF_LAUNCH(WP, WS)                                                                                          \
     do {                                                                                                           \
-        SNN_CUDA(cudaFuncSetAttribute(k_score_fast<KC, WP, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+        SNN_CUDA(cudaFuncSetAttribute(k_score_fast<WP, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
                                       (int)smem));                                                                 \
-        k_score_fast<KC, WP, WS><<<grid, SF_WARPS * 32, smem, ctx->stream>>>(cds, recs, n, ctx->bg_sorted,         \
-                                                                             ctx->bg_valid, ctx->bg_rcp,           \
-                                                                             (int)ctx->bg_ncol, bg_half, pmin, bs, \
-                                                                             out);                                 \
+        k_score_fast<WP, WS><<<grid, SF_WARPS * 32, smem, ctx->stream>>>(cds, recs, n, next, ctx->bg_sorted,       \
+                                                                         ctx->bg_valid, ctx->bg_rcp,               \
+                                                                         (int)ctx->bg_ncol, bg_half, pmin, bs,     \
+                                                                         tall, out);                               \
     } while (0)
     if (want_p && want_s) SF_LAUNCH(true, true);
     else if (want_p) SF_LAUNCH(true, false);
@@ -427,14 +560,12 @@ static int launch_kc(snn_ctx* ctx, const ChromDev* cds, const FastRec* recs, int
     return SNN_OK;
 }
 
-int snn_launch_score_fast(snn_ctx* ctx, const ChromDev* cds, const FastRec* recs, int n, int bs, int hcap, int want_p,
-                          int want_s, double* out) {
-    if (n <= 0) return SNN_OK;
-    switch (hcap) {
-        case 32: return launch_kc<1>(ctx, cds, recs, n, bs, want_p, want_s, out);
-        case 64: return launch_kc<2>(ctx, cds, recs, n, bs, want_p, want_s, out);
-        case 128: return launch_kc<4>(ctx, cds, recs, n, bs, want_p, want_s, out);
-        case 320: return launch_kc<10>(ctx, cds, recs, n, bs, want_p, want_s, out);
-        default: return snn_fail(ctx, SNN_EINVAL, "snn_launch_score_fast: height class %d", hcap);
-    }
+// CTAs of the persistent grid (the host sizes the `tall` scratch from it)
+int snn_score_fast_grid(int n) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int grid = (n + SF_WARPS - 1) / SF_WARPS;
+    if (grid > sms * SF_MINB) grid = sms * SF_MINB;
+    return grid < 1 ? 1 : grid;
 }

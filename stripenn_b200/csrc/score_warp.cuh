@@ -30,7 +30,16 @@ struct ChromDev {
 // ---- fast kernel: "regular" stripes (the geometry StripeSearch emits away from the chromosome ends:
 // pos2 and pos4 on bin boundaries, full flanks) whose window lies inside the band -----------------------
 #define SF_WARPS 8
+#ifndef SF_MINB
+#define SF_MINB 4          // CTAs per SM the register allocation aims at (64 registers)
+#endif
 #define SF_RM 1024         // half-width of the mirrored 1/(expected+1e-8) table
+#define SF_PLEV 4          // search steps served from shared memory ...
+#define SF_PNODE 15         // ... = 2^SF_PLEV - 1 pivots per background row ...
+#ifndef SF_PIVD
+#define SF_PIVD 0      // 0: off.  Measured neutral on the whole-genome table (profiles/r02y): the default
+#endif
+//         // ... for the rows of distance < SF_PIVD of the four tables (30 KB per CTA)
 #define SF_EXSTRIDE 4096   // doubles per chromosome slot: expected[512] | rex[512] | pad | rexm[2*SF_RM] from 2048
 struct FastRec {           // host-side geometry of one stripe, all in bins
     int32_t xsi;           // first centre column = int(pos1 / r)
@@ -43,8 +52,11 @@ struct FastRec {           // host-side geometry of one stripe, all in bins
     int32_t slot;          // chromosome slot
     int32_t idx;           // output row
 };
-int snn_launch_score_fast(snn_ctx* ctx, const ChromDev* cds, const FastRec* recs, int n, int bs, int hcap, int want_p,
-                          int want_s, double* out);
+#define SF_HMAX 320         // tallest stripe the fast kernel takes
+#define SF_HSM 128          // row results of stripes up to this height stay in shared memory
+int snn_launch_score_fast(snn_ctx* ctx, const ChromDev* cds, const FastRec* recs, int n, int bs, int want_p, int want_s,
+                          int* next, double* tall, int grid, double* out);
+int snn_score_fast_grid(int n);
 
 int snn_launch_score_warp(snn_ctx* ctx, const ChromDev* cds, const int32_t* cslot, const int64_t* pos,
                           const int32_t* stale, const int32_t* order, int n, int64_t binsize, int bs, int hcap,

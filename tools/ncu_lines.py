@@ -43,7 +43,12 @@ def main():
     ii, si = hdr.index("Instructions Executed"), hdr.index("# Samples")
     agg = {}
     tot = tots = 0
-    body = [r for r in rows[start:] if len(r) == len(hdr)]
+    body = []
+    for r in rows[start:]:          # newer ncu versions repeat the table (second view): stop at its header
+        if "Instructions Executed" in r:
+            break
+        if len(r) == len(hdr):
+            body.append(r)
     if len(body) != len(lines_of):
         print("warning: %d SASS rows in the report, %d in the disassembly" % (len(body), len(lines_of)))
     for k, r in enumerate(body):
