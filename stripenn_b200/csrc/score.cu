@@ -472,12 +472,31 @@ int snn_score_multi_impl(snn_ctx* ctx, const std::vector<ScoreSlot>& slots, int6
     static const Cls cls[3] = {{128, 4096}, {512, 12288}, {4800, 0}};
     std::vector<int32_t> worder[3];
     std::vector<std::vector<int32_t>> gorder((size_t)nslot * 3);
-    // fast kernel (score_fast.cu): regular stripes by height class; SNN_SCORE_FAST=0 switches it off
-    // (read per call: the tests compare the kernels)
+    // fast kernel (score_fast.cu): the regular stripes.  SNN_SCORE_FAST (read per call: the tests
+    // compare the kernels) = 0 off, 1 always, unset = when it pays: the kernel needs the column-major
+    // full band of every chromosome it touches, and building one moves ~8 B * nbins * 2 bw + 64 B per
+    // stored pixel through HBM — about what the warp kernel loses on 1 stripe per 150 KB.  A `score`
+    // call over 100k stripes builds the bands (and later calls find them resident); the few hundred
+    // stripes per chromosome of a `compute` step stay with the warp kernel.
     std::vector<FastRec> frec;
     const char* fenv = getenv("SNN_SCORE_FAST");
-    const bool fast_on = !(fenv && fenv[0] == '0') && !ctx->force_generic && bs >= 1 && bs <= 64 &&
-                         (!want_p || ctx->bg_ncol >= 1);
+    bool fast_on = !(fenv && fenv[0] == '0') && !ctx->force_generic && bs >= 1 && bs <= 64 &&
+                   (!want_p || ctx->bg_ncol >= 1);
+    if (fast_on && !(fenv && fenv[0] == '1')) {
+        std::vector<int64_t> cand((size_t)nslot, 0);
+        for (int64_t i = 0; i < n; ++i) {
+            const int sl = slot_of ? slot_of[i] : 0;
+            if (sl >= 0 && sl < nslot && pos[i * 4 + 1] % r == 0 && pos[i * 4 + 3] % r == 0) ++cand[sl];
+        }
+        double build_bytes = 0.0, ncand = 0.0;
+        for (int sl = 0; sl < nslot; ++sl) {
+            const SnnChrom* c = slots[sl].c;
+            if (!cand[sl]) continue;
+            ncand += (double)cand[sl];
+            if (c->fband_state == 0) build_bytes += 16.0 * (double)c->nbins * (double)c->bw + 64.0 * (double)c->nnz;
+        }
+        fast_on = ncand * 150000.0 >= build_bytes;
+    }
     std::vector<char> slot_fast((size_t)nslot, 1), slot_used((size_t)nslot, 0);
     for (int sl = 0; sl < nslot; ++sl) {
         const SnnChrom* c = slots[sl].c;

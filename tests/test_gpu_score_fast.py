@@ -3,7 +3,7 @@
 `k_score_fast` takes the REGULAR stripes (pos2 / pos4 on bin boundaries, complete flanks, window
 inside the band); `k_score_warp` / `k_score` keep the rest and are pinned to the oracle and the
 reference goldens by the other GPU tests.  Here the same stripes go through both families
-(`SNN_SCORE_FAST=0` switches the fast kernel off) and must agree: p-value, Stripiness, O/E mean and
+(`SNN_SCORE_FAST=0` switches the fast kernel off, `=1` forces it) and must agree: p-value, Stripiness, O/E mean and
 O/E total bit for bit (same operations in the same order); observed mean / sum to 1e-13 (the fast
 kernel adds row sums, the warp kernel accumulates per lane across rows).  Routing is checked through
 `snn_score_routing`, so a silent fall-back to the old kernels fails the test."""
@@ -56,7 +56,7 @@ def _both(dev, ids, index, pos, exs, want_pvalue=True, expected=True, stale=None
     dev.score_routing()
     old = dev.score_multi(ids, index, pos, exs if expected else None, want_pvalue, stale=stale)
     r_old = dev.score_routing()
-    os.environ.pop("SNN_SCORE_FAST")
+    os.environ["SNN_SCORE_FAST"] = "1"
     new = dev.score_multi(ids, index, pos, exs if expected else None, want_pvalue, stale=stale)
     r_new = dev.score_routing()
     assert r_old[0] == 0
@@ -173,3 +173,21 @@ def test_fast_one_kb_wide_flanks(dev):
     old, new, routed = _both(dev, ids, index, pos, exs)
     assert routed[0] == len(pos), routed
     _compare(old, new)
+
+
+def test_fast_auto_rule(dev):
+    """Unset SNN_SCORE_FAST: a small table does not pay for the full band (warp kernel), a large one
+    does; once the bands are resident the small table uses them too."""
+    cm = _kr_map()
+    names, ids, exs = _setup(dev, cm, "KR")
+    small_pos, small_index = _table(cm, names, 300, seed=5)
+    big_pos, big_index = _table(cm, names, 30000, seed=6)
+    os.environ.pop("SNN_SCORE_FAST", None)
+    dev.score_routing()
+    a = dev.score_multi(ids, small_index, small_pos, exs, True)
+    assert dev.score_routing()[0] == 0
+    dev.score_multi(ids, big_index, big_pos, exs, True)
+    assert dev.score_routing()[0] == len(big_pos)
+    b = dev.score_multi(ids, small_index, small_pos, exs, True)
+    assert dev.score_routing()[0] == len(small_pos)
+    _compare(a, b)
