@@ -206,6 +206,7 @@ void snn_destroy(snn_ctx* ctx) {
     cudaFree(ctx->bg_sorted);
     cudaFree(ctx->bg_valid);
     cudaFree(ctx->bg_rcp);
+    cudaFree(ctx->bg_tree);
     cudaFree(ctx->scratch);
     if (ctx->sync_event) cudaEventDestroy(ctx->sync_event);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);

@@ -112,7 +112,8 @@ int snn_background_dev_impl(snn_ctx* ctx, SnnChrom* c, int64_t nsamp, const int3
 // slots = null: in[row][col] (the host tables); else sample-major in[slots[col]][row]
 __global__ void __launch_bounds__(512) k_bg_sort(const double* __restrict__ in, int64_t ncol, int npow2,
                                                  double* __restrict__ out, int32_t* __restrict__ nvalid,
-                                                 double* __restrict__ nrcp,
+                                                 double* __restrict__ nrcp, float4* __restrict__ tree,
+                                                 int levels,
                                                  const int32_t* __restrict__ slots, int use_slots) {
     extern __shared__ double s[];
     const int64_t row = blockIdx.x;
@@ -152,6 +153,31 @@ __global__ void __launch_bounds__(512) k_bg_sort(const double* __restrict__ in, 
         nvalid[row] = total;
         nrcp[row] = 1.0 / (double)total;
     }
+    // 5-ary search tree for the fast scoring kernel: node q of level l holds the keys of the sorted
+    // positions (5q + r + 1) * 5^(levels-1-l) - 1, r = 0..3, as float32 rounded toward -inf (so that
+    // key < RU(v) whenever entry < v), +inf past the row.  Descending with q' = 5q + #(key < RU(v)) ends
+    // at q = #(key < RU(v)) over the whole row, an upper bound of #(entry < v) that is exact unless an
+    // entry lies within one float32 ulp above v (score_fast.cu checks one float64 entry).
+    if (tree) {
+        int nodes = 1, total_nodes = 0;
+        for (int l = 0; l < levels; ++l) { total_nodes += nodes; nodes *= 5; }
+        float4* trow = tree + row * total_nodes;
+        int base = 0, cnt = 1, stride = nodes / 5;          // stride of level 0 = 5^(levels-1)
+        for (int l = 0; l < levels; ++l) {
+            for (int q = threadIdx.x; q < cnt; q += blockDim.x) {
+                float k[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int64_t posn = (int64_t)(5 * q + r + 1) * stride - 1;
+                    k[r] = posn < ncol ? __double2float_rd(s[posn]) : __int_as_float(0x7f800000);
+                }
+                trow[base + q] = make_float4(k[0], k[1], k[2], k[3]);
+            }
+            base += cnt;
+            cnt *= 5;
+            stride /= 5;
+        }
+    }
 }
 
 // tables != null: host tables [4][400][ncol]; else sample-major device buffer d_buf with the host
@@ -162,6 +188,9 @@ static int set_background_run(snn_ctx* ctx, int64_t ncol, const double* tables, 
         cudaFree(ctx->bg_sorted);
         cudaFree(ctx->bg_valid);
         cudaFree(ctx->bg_rcp);
+        cudaFree(ctx->bg_tree);
+        ctx->bg_tree = nullptr;
+        ctx->bg_tree_levels = 0;
         ctx->bg_sorted = nullptr;
         ctx->bg_valid = nullptr;
         ctx->bg_rcp = nullptr;
@@ -182,6 +211,13 @@ static int set_background_run(snn_ctx* ctx, int64_t ncol, const double* tables, 
         SNN_CUDA(cudaMalloc(&ctx->bg_sorted, bytes));
         SNN_CUDA(cudaMalloc(&ctx->bg_valid, rows * sizeof(int32_t)));
         SNN_CUDA(cudaMalloc(&ctx->bg_rcp, rows * sizeof(double)));
+        int levels = 1;
+        int64_t reach = 5;                                   // 5^levels positions
+        while (reach < ncol + 1) { reach *= 5; ++levels; }
+        if (levels <= 5) {                                   // rows up to 3124 entries: 12.5 KB of keys per row
+            SNN_CUDA(cudaMalloc(&ctx->bg_tree, (size_t)rows * (size_t)((reach - 1) / 4) * sizeof(float4)));
+            ctx->bg_tree_levels = levels;
+        }
     }
     const double* src = d_buf;
     const int32_t* dslots = nullptr;
@@ -197,7 +233,8 @@ static int set_background_run(snn_ctx* ctx, int64_t ncol, const double* tables, 
     SNN_CUDA(cudaFuncSetAttribute(k_bg_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     {
         SnnScope scope(ctx, ST_BGSORT, 1);
-        k_bg_sort<<<(unsigned)rows, 512, smem, ctx->stream>>>(src, ncol, npow2, ctx->bg_sorted, ctx->bg_valid, ctx->bg_rcp, dslots,
+        k_bg_sort<<<(unsigned)rows, 512, smem, ctx->stream>>>(src, ncol, npow2, ctx->bg_sorted, ctx->bg_valid, ctx->bg_rcp, ctx->bg_tree,
+                                                              ctx->bg_tree_levels, dslots,
                                                               tables ? 0 : 1);
         SNN_LAUNCH_CHECK("k_bg_sort");
     }

@@ -25,6 +25,8 @@
 //
 // Roofline: HBM/L2 (window bytes are requested exactly once, sector-aligned runs of h doubles).
 // Algorithmic bytes per stripe: 8 * h * (w + 2*bs) + 48.
+#include <stdlib.h>
+
 #include "score_warp.cuh"
 
 #define FULL 0xffffffffu
@@ -250,7 +252,9 @@ __global__ void __launch_bounds__(SF_WARPS * 32, SF_MINB) k_score_fast(const Chr
                                                             const double* __restrict__ bg,
                                                             const int32_t* __restrict__ bg_valid,
                                                             const double* __restrict__ bg_rcp, int bg_ncol,
-                                                            int bg_half, double pmin, int bs,
+                                                            int bg_half, const float4* __restrict__ bg_tree,
+                                                            int tree_levels, int tree_nodes, int tree_dbg, double pmin,
+                                                            int bs,
                                                             double* __restrict__ tall,
                                                             double* __restrict__ out) {
     constexpr int KC = SF_HMAX / 32;
@@ -347,7 +351,36 @@ __global__ void __launch_bounds__(SF_WARPS * 32, SF_MINB) k_score_fast(const Chr
                 // kernel's L1 sectors were these searches)
                 const int basel = rowl * bg_ncol - 1, baser = rowr * bg_ncol - 1;
                 int pa = 0, pb = 0, step = bg_half;
-                if (use_piv && __all_sync(FULL, ok && d < SF_PIVD)) {
+                if (bg_tree) {
+                    // 5-ary descent over float32 keys rounded down, against the thresholds rounded up:
+                    // one 16-byte load per level and search instead of one 8-byte load per halving
+                    // step (10 -> 5 scattered loads for 1000 columns), then ONE float64 entry confirms
+                    // the position; a lane whose entry is not below its threshold (an entry within a
+                    // float32 ulp above it) repeats the search on the float64 row
+                    // tree_dbg (SNN_SCORE_TREE=2, tests): thresholds of +inf send every lane through the repeat
+                    const float ul = tree_dbg ? __int_as_float(0x7f800000) : __double2float_ru(dl);
+                    const float ur = tree_dbg ? __int_as_float(0x7f800000) : __double2float_ru(dr);
+                    const float4* __restrict__ ta = bg_tree + (int64_t)rowl * tree_nodes;
+                    const float4* __restrict__ tb = bg_tree + (int64_t)rowr * tree_nodes;
+                    int base = 0, cnt = 1;
+#pragma unroll 1
+                    for (int l = 0; l < tree_levels; ++l) {
+                        const float4 ka = __ldg(ta + (base + pa)), kb = __ldg(tb + (base + pb));
+                        pa = 5 * pa + (ka.x < ul) + (ka.y < ul) + (ka.z < ul) + (ka.w < ul);
+                        pb = 5 * pb + (kb.x < ur) + (kb.y < ur) + (kb.z < ur) + (kb.w < ur);
+                        base += cnt;
+                        cnt *= 5;
+                    }
+                    const double xa = __ldg(bg + (basel + max(pa, 1))), xb = __ldg(bg + (baser + max(pb, 1)));
+                    const bool bad = (pa > 0 && !(xa < dl)) || (pb > 0 && !(xb < dr));
+                    step = 0;
+                    if (__any_sync(FULL, bad)) {
+                        step = bg_half;
+                        if (bad) { pa = 0; pb = 0; }
+                        else step = 0;
+                    }
+                }
+                if (SF_PIVD > 0 && use_piv && step == bg_half && !bg_tree && __all_sync(FULL, ok && d < SF_PIVD)) {
                     const double* __restrict__ qa = piv + ((table == 0 ? 0 : 2) * SF_PIVD + dq) * SF_PNODE;
                     const double* __restrict__ qb = qa + SF_PIVD * SF_PNODE;
                     int ma = 0, mb = 0;
@@ -542,12 +575,19 @@ int snn_launch_score_fast(snn_ctx* ctx, const ChromDev* cds, const FastRec* recs
     int bg_half = 1;
     while (bg_half * 2 <= ctx->bg_ncol) bg_half <<= 1;     // largest power of two <= ncol: positions up to 2*half - 1 >= ncol
     const double pmin = ctx->bg_ncol > 0 ? 1.0 / (double)ctx->bg_ncol : 0.0;
+    const char* tenv = getenv("SNN_SCORE_TREE");          // A/B switch and test hook: 0 = float64 rows only
+    const float4* tree = (tenv && tenv[0] == '0') ? nullptr : ctx->bg_tree;
+    const int tree_dbg = (tenv && tenv[0] == '2') ? 1 : 0;
+    int tree_nodes = 0;
+    for (int l = 0, c = 1; l < ctx->bg_tree_levels; ++l, c *= 5) tree_nodes += c;
 #define SF_LAUNCH(WP, WS)                                                                                          \
     do {                                                                                                           \
         k_score_fast<WP, WS><<<grid, SF_WARPS * 32, smem, ctx->stream>>>(cds, recs, n, next, ctx->bg_sorted,       \
                                                                          ctx->bg_valid, ctx->bg_rcp,               \
-                                                                         (int)ctx->bg_ncol, bg_half, pmin, bs,     \
-                                                                         tall, out);                               \
+                                                                         (int)ctx->bg_ncol, bg_half, tree,         \
+                                                                         ctx->bg_tree_levels, tree_nodes,          \
+                                                                         tree_dbg, pmin,                           \
+                                                                         bs, tall, out);                           \
     } while (0)
     if (want_p && want_s) SF_LAUNCH(true, true);
     else if (want_p) SF_LAUNCH(true, false);

@@ -104,6 +104,11 @@ struct snn_ctx {
     double* bg_sorted = nullptr;
     int32_t* bg_valid = nullptr;
     double* bg_rcp = nullptr;      // 1 / bg_valid[row] (correctly rounded; inf for an empty row)
+    // 5-ary search tree over each sorted row with float32 keys rounded DOWN (background.cu: k_bg_sort):
+    // bg_tree_levels levels, (5^levels - 1) / 4 nodes of four keys per row; null when the rows are too
+    // long for five levels (the fast scoring kernel then searches the float64 rows directly)
+    float4* bg_tree = nullptr;
+    int bg_tree_levels = 0;
     int64_t bg_ncol = 0;
     // --mask of scoringstripes (snn_set_mask): chromosome id (< 0: none), start/end in bp
     int mask_chrom = -1;

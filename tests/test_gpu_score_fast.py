@@ -191,3 +191,23 @@ def test_fast_auto_rule(dev):
     b = dev.score_multi(ids, small_index, small_pos, exs, True)
     assert dev.score_routing()[0] == len(small_pos)
     _compare(a, b)
+
+
+def test_fast_tree_search_equals_row_search(dev):
+    """The 5-ary float32 key tree over the sorted background rows against the float64 halving search
+    (SNN_SCORE_TREE=0), and with every lane forced through the tree's repeat path (=2)."""
+    cm = _kr_map()
+    names, ids, exs = _setup(dev, cm, "KR")
+    pos, index = _table(cm, names, 8000, seed=8)
+    os.environ["SNN_SCORE_FAST"] = "1"
+    try:
+        os.environ["SNN_SCORE_TREE"] = "0"
+        plain = dev.score_multi(ids, index, pos, exs, True)
+        os.environ["SNN_SCORE_TREE"] = "2"
+        forced = dev.score_multi(ids, index, pos, exs, True)
+        os.environ.pop("SNN_SCORE_TREE")
+        tree = dev.score_multi(ids, index, pos, exs, True)
+    finally:
+        os.environ.pop("SNN_SCORE_TREE", None)
+    _compare(plain, tree, keys_exact=KEYS_EXACT + KEYS_CLOSE, keys_close=())
+    _compare(plain, forced, keys_exact=KEYS_EXACT + KEYS_CLOSE, keys_close=())
