@@ -154,7 +154,8 @@ CONFIG_TEXT = {"cfg1": "synthetic chr16-sized map at 5 kb", "cfg2": "synthetic m
                "cfg4": "synthetic human chr1 at 1 kb"}
 NCU_FAMILY = {"gaussian": ("k_gauss_vm", "k_gauss_hm"), "sobel_nms": ("k_sobel_nms",), "gray": ("k_gray6",),
               "search": ("k_search",), "score": ("k_score_warp",), "background": ("k_background",),
-              "quantile_select": ("k_radix_hist",), "k_gray_gv": ("k_gray_gv",), "k_gh_nms": ("k_gh_nms",)}
+              "quantile_select": ("k_radix_hist",), "k_gray_gv": ("k_gray_gv",), "k_gh_nms": ("k_gh_nms",),
+              "k_score_fast": ("k_score_fast",)}
 # FP64 operations of the REFERENCE per pass pixel (one pixel of one (window, maxpixel, brightness) image),
 # counted from its literal operation sequence: what `roofline.achieved` credits.
 #   k_gray_gv: saturate 4 (255*(M-D)/M/255) + brightness 1 + cv.filter2D 3x3 (9 mul + 9 add) = 23,
@@ -419,6 +420,7 @@ def score_bench(devs, cm, stream, torch, n_stripes=100000):
         run()
     for d in devs:
         d.reset_stage_times()
+        d.score_routing()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     reps = 3
@@ -431,16 +433,26 @@ def score_bench(devs, cm, stream, torch, n_stripes=100000):
     sts = [d.stage_times()["score"] for d in devs]
     st = {"ms": sum(x["ms"] for x in sts), "launches": sum(x["launches"] for x in sts)}
     kms = st["ms"] / reps
+    routed = [sum(v) // reps for v in zip(*[d.score_routing() for d in devs])]
     peak, src = measured_peaks()
     ach = alg_bytes / 1e9 / (kms / 1e3)
+    tr = ncu_traffic("k_score_fast")
     return {"workload": "config-5-like: %d synthetic stripes (h ~ lognormal(55), w 3..12, +-%d flank bins) on the "
                         "resident %d-bp genome, p-value + stripiness + O/E + observed mean" % (len(pos), bs, r),
             "stripes_per_s_e2e": len(pos) / (ms / 1e3), "ms_e2e": ms, "kernel_ms": kms,
             "kernel_launches": st["launches"] // reps,
             "window_mpixels_per_s": float(np.sum(h * (w + 2 * bs))) / 1e6 / (kms / 1e3),
             "nan_outputs": int(np.isnan(out).sum()),
-            "roofline": {"kernel": "k_score", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": ach / peak, "algorithmic_bytes": alg_bytes, "peak_source": src}}
+            "stripes_routed": {"k_score_fast": routed[0], "k_score_warp": routed[1], "k_score": routed[2]},
+            "kernel_ms_is": "CUDA events around the scoring kernels of a call (the copies of the stripe table and of "
+                            "the results are outside; ms_e2e has them)",
+            "roofline": {"kernel": "k_score_fast" if routed[0] >= max(routed[1], routed[2]) else "k_score_warp",
+                         "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                         "frac": ach / peak, "algorithmic_bytes": alg_bytes,
+                         "algorithmic": "8 B x h x (w + 2 x flank) window bytes + 48 B of results per stripe (DESIGN.md 3) "
+                                        "+ the background tables once",
+                         "traffic": tr[0] if tr else None, "traffic_source": tr[1] if tr else None,
+                         "peak_source": src}}
 
 
 # ------------------------------------------------------------------------------------------ B200 arm
