@@ -131,10 +131,13 @@ def test_raw_candidates_cfg4_sampled(dev):
     _check_sampled_windows(dev, synth.make_config("cfg4"), "chr1", "None", 8, (1, 4), 4)
 
 
-def test_cfg5_shape_scores_match_oracle(dev):
+@pytest.mark.parametrize("fast", ["0", "1"])
+def test_cfg5_shape_scores_match_oracle(dev, fast, monkeypatch):
     """`stripenn score` on 5,000 stripes drawn like the bench's config-5 table (h ~ lognormal(55),
     w 3..12, both directions) over three KR-balanced config-3 chromosomes: p-value, Stripiness,
     O/E mean and total, observed mean and sum against the oracle."""
+    monkeypatch.setenv("SNN_SCORE_FAST", fast)      # k_score_warp / k_score_fast, both against the oracle
+    dev.score_routing()
     chroms, binsize, _ = synth.config_chroms("cfg3")
     keep = ("chr20", "chr21", "chr22")
     cm = synth.make_map([c for c in chroms if c[0] in keep], binsize, balanced=True)
@@ -147,3 +150,6 @@ def test_cfg5_shape_scores_match_oracle(dev):
         np.testing.assert_allclose(got[k].to_numpy(dtype=float), np.array(want[k], dtype=float), rtol=RTOL, atol=0,
                                    equal_nan=True, err_msg=k)
     assert np.isfinite(got["pvalue_added"].to_numpy(dtype=float)).all()
+    routed = dev.score_routing()
+    # score_table makes one call per output group: every stripe of the table is regular
+    assert (routed[0] > 0 and routed[1] + routed[2] == 0) if fast == "1" else routed[0] == 0, routed

@@ -256,7 +256,13 @@ def test_compute_subset_of_chromosomes(dev, tiny2_cm):
         np.testing.assert_allclose(unf[k].to_numpy(dtype=float), np.array(ounf[k], float), rtol=RTOL, equal_nan=True)
 
 
-def test_score_matches_reference(dev, tiny2_cm, golden_dir):
+@pytest.mark.parametrize("fast", ["auto", "1"])
+def test_score_matches_reference(dev, tiny2_cm, golden_dir, fast, monkeypatch):
+    """`stripenn score` against the unmodified reference's own output; fast = "1" sends the regular
+    stripes through k_score_fast (a table this small stays with the warp kernel otherwise)."""
+    if fast == "1":
+        monkeypatch.setenv("SNN_SCORE_FAST", "1")
+    dev.score_routing()
     g = np.load(os.path.join(golden_dir, "tiny2_score.npz"))
     df = pd.DataFrame({"chr": g["chr"], "pos1": g["pos1"], "pos2": g["pos2"], "chr2": g["chr2"],
                        "pos3": g["pos3"], "pos4": g["pos4"]})
@@ -264,6 +270,8 @@ def test_score_matches_reference(dev, tiny2_cm, golden_dir):
     for k in ("pvalue_added", "Stripiness_added", "O_Mean_added", "O_Sum_added", "O/E_Mean_added", "O/E_Total_added"):
         np.testing.assert_allclose(res[k].to_numpy(dtype=float), g[k.replace("/", "_")], rtol=RTOL, atol=0,
                                    equal_nan=True)
+    routed = dev.score_routing()
+    assert (routed[0] > 0) == (fast == "1"), routed
 
 
 def test_small_and_empty_windows(dev):
