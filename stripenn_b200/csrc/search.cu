@@ -5,6 +5,9 @@
 //   C  current: high mask, grown to the connected components of E that contain a high pixel
 //   V  vert   : ImageProcessing.verticalLine(edges, 60, 120)            (ImageProcessing.py:61-83)
 //   T  testmat: painted candidate segments, refined per row               (getStripe.py:945-978)
+// C is dead once the hysteresis has converged (E := C), so T lives in C's storage: three masks =
+// 62.4 KB of dynamic shared memory, 11 KB static, 48 registers x 416 threads -> 3 CTAs per SM
+// (four masks and 28-byte pending records were 99 KB: 2 CTAs per SM, 26 warps, issue 40 %: profiles/r01p).
 // All of this is integer / bit work; the only floating point is the count-weighted mean
 // column of the grouping step (float64, sequential, round-half-even).
 #include <string.h>
@@ -150,7 +153,21 @@ struct SearchParams {
     int raw_cap;
 };
 
-__global__ void __launch_bounds__(NTHR) k_search(const uint32_t* __restrict__ low_all,
+// candidate kept in shared memory until the pass is flushed: 16 bytes (x, right, k fit 16 bits; y and hi
+// may hold the 'no row hit' sentinels 1 << 30 and -1)
+struct PendCand {
+    int y, hi;
+    short x, right, k;
+    unsigned char ud, pad;
+};
+
+#ifdef SEARCH_FOUR_MASKS          // A/B build switch: the 4-mask layout, 2 CTAs per SM
+#define SEARCH_MINB 2
+#else
+#define SEARCH_MINB 3
+#endif
+
+__global__ void __launch_bounds__(NTHR, SEARCH_MINB) k_search(const uint32_t* __restrict__ low_all,
                                                  const uint32_t* __restrict__ high_all,
                                                  const FrameInfo* __restrict__ info, SearchParams P,
                                                  int* __restrict__ counter, RawCand* __restrict__ raw,
@@ -159,7 +176,11 @@ __global__ void __launch_bounds__(NTHR) k_search(const uint32_t* __restrict__ lo
     uint32_t* E = smem;
     uint32_t* C = E + SNN_SMAX * SNN_WPR;
     uint32_t* V = C + SNN_SMAX * SNN_WPR;
+#ifdef SEARCH_FOUR_MASKS
     uint32_t* T = V + SNN_SMAX * SNN_WPR;
+#else
+    uint32_t* T = C;                    // C's storage, after the hysteresis
+#endif
     __shared__ uint32_t colV[SNN_WPR], colT[SNN_WPR], colOK[SNN_WPR];   // per-column any-bit / >= 3 ones masks
     __shared__ short cEnd[SNN_SMAX];
     __shared__ unsigned char cUd[SNN_SMAX];
@@ -167,7 +188,7 @@ __global__ void __launch_bounds__(NTHR) k_search(const uint32_t* __restrict__ lo
     __shared__ int X[SNN_SMAX + 8];
     __shared__ int nX;
     __shared__ int rmin, rmax;
-    __shared__ RawCand pend[SNN_SMAX];
+    __shared__ PendCand pend[SNN_SMAX];
     __shared__ int npend;
     __shared__ int base_sh;
     __shared__ unsigned char dirty[2][SNN_SMAX + 2];   // row r at index r + 1
@@ -496,10 +517,10 @@ __global__ void __launch_bounds__(NTHR) k_search(const uint32_t* __restrict__ lo
                 int lo = rmin, hi = rmax;
                 if (ud == 1) hi = right; else lo = n;
                 if (npend < SNN_SMAX) {
-                    RawCand rc;
-                    rc.pass = pass; rc.ud = ud; rc.k = kout;
-                    rc.x = n; rc.y = lo; rc.right = right; rc.hi = hi;
-                    pend[npend++] = rc;
+                    PendCand pc;
+                    pc.ud = (unsigned char)ud; pc.pad = 0; pc.k = (short)kout;
+                    pc.x = (short)n; pc.y = lo; pc.right = (short)right; pc.hi = hi;
+                    pend[npend++] = pc;
                 }
             }
             ++kout;
@@ -512,8 +533,13 @@ __global__ void __launch_bounds__(NTHR) k_search(const uint32_t* __restrict__ lo
     __syncthreads();
     const int base = base_sh;
     for (int t = tid; t < npend; t += NTHR) {
-        if (base + t < P.raw_cap) raw[base + t] = pend[t];
-        else counter[1] = 1;
+        if (base + t < P.raw_cap) {
+            const PendCand pc = pend[t];
+            RawCand rc;
+            rc.pass = pass; rc.ud = pc.ud; rc.k = pc.k;
+            rc.x = pc.x; rc.y = pc.y; rc.right = pc.right; rc.hi = pc.hi;
+            raw[base + t] = rc;
+        } else counter[1] = 1;
     }
 }
 
@@ -667,7 +693,11 @@ static int make_plan(snn_ctx* ctx, ExtractPlan* pl, int nq, const double* mp, co
     return SNN_OK;
 }
 
+#ifdef SEARCH_FOUR_MASKS
 static const size_t kSearchSmem = 4 * (size_t)SNN_SMAX * SNN_WPR * sizeof(uint32_t);
+#else
+static const size_t kSearchSmem = 3 * (size_t)SNN_SMAX * SNN_WPR * sizeof(uint32_t);
+#endif
 
 // Enqueue one batch of windows: image chain, search (appends raw candidates), finish (turns the
 // batch's raw candidates into records while its compacted windows are still in the scratch
