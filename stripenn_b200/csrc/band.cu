@@ -190,7 +190,17 @@ int snn_fband_build(snn_ctx* ctx, SnnChrom* c) {
         }
     }
     const int64_t total = c->nbins * (2 * (int64_t)c->bw - 1);
-    SNN_CUDA(cudaMallocAsync(&c->fband, (size_t)total * sizeof(double), ctx->stream));
+    {
+        // an optional layout: when HBM cannot hold it the chromosome simply stays with the warp kernel
+        const cudaError_t e = cudaMallocAsync(&c->fband, (size_t)total * sizeof(double), ctx->stream);
+        if (e == cudaErrorMemoryAllocation) {
+            cudaGetLastError();
+            c->fband = nullptr;
+            c->fband_state = 2;
+            return SNN_OK;
+        }
+        if (e != cudaSuccess) return snn_cuda_fail(ctx, e, "cudaMallocAsync(fband)");
+    }
     SnnScope scope(ctx, ST_BAND, 1);
     const int threads = 256;
     SNN_CUDA(cudaMemsetAsync(c->fband, 0, (size_t)total * sizeof(double), ctx->stream));
