@@ -142,41 +142,6 @@ __device__ __forceinline__ void f_row(const char* __restrict__ prow, int T8, int
     f_run<WS>(prow, T8, xsi + wc + k, rp, bs + wc + 1 + k, bs - k, rr, orr);
 }
 
-#ifdef SF_OLDROW
-template <int SHIFT, bool WS>
-__device__ __forceinline__ void f_part(const char* __restrict__ prow, int T8, int c0, const double* __restrict__ rp,
-                                       int ncols, double& sraw, double& soe) {
-    int k = 0;
-#define F_LD1(c) __ldg(reinterpret_cast<const double*>(prow + (int64_t)(c) * (int64_t)T8))
-#pragma unroll 1
-    for (; k + 4 <= ncols; k += 4) {
-        const int c = c0 + k;
-        const double v0 = F_LD1(c), v1 = F_LD1(c + 1), v2 = F_LD1(c + 2), v3 = F_LD1(c + 3);
-        if (WS) {
-            const double e0 = __ldg(rp + SHIFT), e1 = __ldg(rp + SHIFT + 1), e2 = __ldg(rp + SHIFT + 2),
-                         e3 = __ldg(rp + SHIFT + 3);
-            soe += v0 * e0;
-            soe += v1 * e1;
-            soe += v2 * e2;
-            soe += v3 * e3;
-        }
-        rp += 4;
-        sraw += v0;
-        sraw += v1;
-        sraw += v2;
-        sraw += v3;
-    }
-#pragma unroll 1
-    for (; k < ncols; ++k) {
-        const double v0 = F_LD1(c0 + k);
-        if (WS) soe += v0 * __ldg(rp + SHIFT);
-        rp += 1;
-        sraw += v0;
-    }
-#undef F_LD1
-}
-#endif
-
 // np.median of a[0..n) (shared memory, n >= 1, no NaN) by quickselect: every round
 // takes a pivot from the remaining candidates, counts the candidates below / not above it with two
 // redux.sync and keeps one side.  KC = 32-value slots per lane (n <= 32 * KC).
@@ -269,26 +234,9 @@ __global__ void __launch_bounds__(SF_WARPS * 32, SF_MINB) k_score_fast(const Chr
     extern __shared__ double sh[];
     double* rcp = sh;                                  // rcp[k] = 1 / k, k <= 64
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double* piv = sh + 72;                             // first search steps of the hot background rows
-    constexpr int PIVN = WP ? 4 * SF_PIVD * SF_PNODE : 0;
-    double* const sm_rows = sh + 72 + PIVN + (size_t)warp * 4 * SF_HSM;
+    double* const sm_rows = sh + 72 + (size_t)warp * 4 * SF_HSM;
     double* const gl_rows = tall + ((size_t)blockIdx.x * SF_WARPS + warp) * 4 * SF_HMAX;
     if (threadIdx.x <= 64) rcp[threadIdx.x] = 1.0 / (double)threadIdx.x;
-    const bool use_piv = SF_PIVD > 0 && WP && (bg_half >> SF_PLEV) >= 1;
-    if (use_piv) {
-        // piv[(t * SF_PIVD + d) * SF_PNODE + (2^l - 1) + m] = entry probed at step l after the path m:
-        // position (2m + 1) * (bg_half >> l), +inf past the row (never taken)
-        for (int t = threadIdx.x; t < PIVN; t += blockDim.x) {
-            const int node = t % SF_PNODE, rd = t / SF_PNODE;
-            const int row = (rd / (SF_PIVD > 0 ? SF_PIVD : 1)) * SNN_NDIST + rd % (SF_PIVD > 0 ? SF_PIVD : 1);
-            int l = 0;
-            while ((2 << l) - 1 <= node) ++l;
-            const int m = node - ((1 << l) - 1);
-            const int posn = (2 * m + 1) * (bg_half >> l);
-            piv[t] = posn <= bg_ncol ? __ldg(bg + (int64_t)row * bg_ncol + posn - 1)
-                                     : __longlong_as_double(0x7ff0000000000000LL);
-        }
-    }
     __syncthreads();
     const double ybs = rcp[bs], dbs = (double)bs;
 
@@ -328,13 +276,7 @@ __global__ void __launch_bounds__(SF_WARPS * 32, SF_MINB) k_score_fast(const Chr
             const char* prow = reinterpret_cast<const char*>(fb + row);
             const double* rp = WS ? rexm + (C0 - row) : nullptr;
             double rl = 0.0, ol = 0.0, rc = 0.0, oc = 0.0, rr = 0.0, orr = 0.0;
-#ifdef SF_OLDROW
-            f_part<0, WS>(prow, T8, C0, rp, bs, rl, ol);
-            f_part<0, WS>(prow, T8, xsi, rp + bs, wc, rc, oc);
-            f_part<1, WS>(prow, T8, xsi + wc, rp + bs + wc, bs, rr, orr);
-#else
             f_row<WS>(prow, T8, C0, xsi, wc, bs, rp, rl, ol, rc, oc, rr, orr);
-#endif
 
             if (WP) {
                 const double mc = f_div(rc, dwc, ywc), ml = f_div(rl, dbs, ybs), mr = f_div(rr, dbs, ybs);
@@ -352,11 +294,12 @@ __global__ void __launch_bounds__(SF_WARPS * 32, SF_MINB) k_score_fast(const Chr
                 const int rowl = (table == 0 ? 0 : 2) * SNN_NDIST + dq, rowr = rowl + SNN_NDIST;
                 const int nl = __ldg(bg_valid + rowl), nr = __ldg(bg_valid + rowr);
                 const double yl = __ldg(bg_rcp + rowl), yr = __ldg(bg_rcp + rowr);
-                // lower bounds #(row < v) by halving steps: probe position pa + step, never past the
-                // row (entries past the valid ones are +inf, k_bg_sort).  The first SF_PLEV steps of
-                // the rows with d < SF_PIVD come from the CTA's shared-memory copy of those pivots —
-                // scattered global loads cost the L1 one sector per lane each (ncu r02v: 58 % of the
-                // kernel's L1 sectors were these searches)
+                // lower bounds #(row < v).  Scattered loads cost the L1 one sector per lane each (ncu r02v:
+                // 58 % of the kernel's L1 sectors were these searches when they were ten halving steps on
+                // the float64 row), hence the key tree; the halving steps (probe position pa + step, never
+                // past the row; entries past the valid ones are +inf, k_bg_sort) remain as its repeat path
+                // and for rows too long for a tree.  Shared-memory copies of the first steps of the hot
+                // rows were measured neutral (profiles/r02y) and are gone.
                 const int basel = rowl * bg_ncol - 1, baser = rowr * bg_ncol - 1;
                 int pa = 0, pb = 0, step = bg_half;
                 if (bg_tree) {
@@ -387,20 +330,6 @@ __global__ void __launch_bounds__(SF_WARPS * 32, SF_MINB) k_score_fast(const Chr
                         if (bad) { pa = 0; pb = 0; }
                         else step = 0;
                     }
-                }
-                if (SF_PIVD > 0 && use_piv && step == bg_half && !bg_tree && __all_sync(FULL, ok && d < SF_PIVD)) {
-                    const double* __restrict__ qa = piv + ((table == 0 ? 0 : 2) * SF_PIVD + dq) * SF_PNODE;
-                    const double* __restrict__ qb = qa + SF_PIVD * SF_PNODE;
-                    int ma = 0, mb = 0;
-#pragma unroll
-                    for (int l = 0; l < SF_PLEV; ++l) {
-                        const double xa = qa[(1 << l) - 1 + ma], xb = qb[(1 << l) - 1 + mb];
-                        ma = 2 * ma + (xa < dl ? 1 : 0);
-                        mb = 2 * mb + (xb < dr ? 1 : 0);
-                    }
-                    step = bg_half >> SF_PLEV;
-                    pa = ma * (2 * step);
-                    pb = mb * (2 * step);
                 }
 #pragma unroll 1
                 for (; step > 0; step >>= 1) {
@@ -579,7 +508,7 @@ __global__ void __launch_bounds__(SF_WARPS * 32, SF_MINB) k_score_fast(const Chr
 int snn_launch_score_fast(snn_ctx* ctx, const ChromDev* cds, const FastRec* recs, int n, int bs, int want_p, int want_s,
                           int* next, double* tall, int grid, double* out) {
     if (n <= 0) return SNN_OK;
-    const size_t smem = (72 + (want_p ? 4 * SF_PIVD * SF_PNODE : 0) + (size_t)SF_WARPS * 4 * SF_HSM) * sizeof(double);
+    const size_t smem = (72 + (size_t)SF_WARPS * 4 * SF_HSM) * sizeof(double);
     int bg_half = 1;
     while (bg_half * 2 <= ctx->bg_ncol) bg_half <<= 1;     // largest power of two <= ncol: positions up to 2*half - 1 >= ncol
     const double pmin = ctx->bg_ncol > 0 ? 1.0 / (double)ctx->bg_ncol : 0.0;
@@ -608,7 +537,7 @@ int snn_launch_score_fast(snn_ctx* ctx, const ChromDev* cds, const FastRec* recs
 // Host-side preparation kept out of the timed scope: the work counter and the shared-memory opt-in
 // (one constant value per kernel: contexts on several host threads share the functions)
 int snn_prepare_score_fast(snn_ctx* ctx, int* next) {
-    const int smem = (int)((72 + 4 * SF_PIVD * SF_PNODE + (size_t)SF_WARPS * 4 * SF_HSM) * sizeof(double));
+    const int smem = (int)((72 + (size_t)SF_WARPS * 4 * SF_HSM) * sizeof(double));
     SNN_CUDA(cudaFuncSetAttribute(k_score_fast<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     SNN_CUDA(cudaFuncSetAttribute(k_score_fast<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     SNN_CUDA(cudaFuncSetAttribute(k_score_fast<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

@@ -34,12 +34,6 @@ struct ChromDev {
 #define SF_MINB 4          // CTAs per SM the register allocation aims at (64 registers)
 #endif
 #define SF_RM 1024         // half-width of the mirrored 1/(expected+1e-8) table
-#define SF_PLEV 4          // search steps served from shared memory ...
-#define SF_PNODE 15         // ... = 2^SF_PLEV - 1 pivots per background row ...
-#ifndef SF_PIVD
-#define SF_PIVD 0      // 0: off.  Measured neutral on the whole-genome table (profiles/r02y): the default
-#endif
-//         // ... for the rows of distance < SF_PIVD of the four tables (30 KB per CTA)
 #define SF_EXSTRIDE 4096   // doubles per chromosome slot: expected[512] | rex[512] | pad | rexm[2*SF_RM] from 2048
 struct FastRec {           // host-side geometry of one stripe, all in bins
     int32_t xsi;           // first centre column = int(pos1 / r)
