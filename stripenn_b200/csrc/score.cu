@@ -497,7 +497,7 @@ int snn_score_multi_impl(snn_ctx* ctx, const std::vector<ScoreSlot>& slots, int6
         }
         fast_on = ncand * 150000.0 >= build_bytes;
     }
-    std::vector<char> slot_fast((size_t)nslot, 1), slot_used((size_t)nslot, 0);
+    std::vector<char> slot_fast((size_t)nslot, 1);
     for (int sl = 0; sl < nslot; ++sl) {
         const SnnChrom* c = slots[sl].c;
         bool ok = fast_on && c->nbins < (1ll << 30) && c->bw < SF_RM;
@@ -557,7 +557,6 @@ int snn_score_multi_impl(snn_ctx* ctx, const std::vector<ScoreSlot>& slots, int6
                 fr.slot = sl;
                 fr.idx = (int32_t)i;
                 frec.push_back(fr);
-                slot_used[sl] = 1;
                 continue;
             }
         }
