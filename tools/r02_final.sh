@@ -1,7 +1,7 @@
 #!/bin/bash
 # Run under gpurun: closing pass of a session — whole GPU suite, score-mode lines (fast / warp kernels),
 # one --set full capture of k_score_fast on the whole-genome table, the default bench line.
-TAG=${TAG:-r02B}
+TAG=${TAG:-r02zb}
 mkdir -p gpurun_out
 python -m pytest tests -x -q -m gpu > gpurun_out/${TAG}_tests.log 2>&1; tail -3 gpurun_out/${TAG}_tests.log
 python tools/score_bench.py --config cfg3 --stripes 100000 --reps 5 --tag ${TAG}_fast > gpurun_out/${TAG}_score_fast.json 2> gpurun_out/${TAG}_score.err

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Run under gpurun: closing pass after the k_gh_nms ring — whole GPU suite, the default bench line,
 # one --set full capture of k_gh_nms on a full 51-window launch (cfg1).
-TAG=${TAG:-r02D}
+TAG=${TAG:-r02zd}
 mkdir -p gpurun_out
 python -m pytest tests -x -q -m gpu > gpurun_out/${TAG}_tests.log 2>&1; tail -2 gpurun_out/${TAG}_tests.log
 python bench.py > gpurun_out/${TAG}_bench_n1.json 2> gpurun_out/${TAG}_bench_n1.err
