@@ -395,6 +395,32 @@ def run_pipeline(obj, cm, qs, chromnames, pvalue, mask, slow, comm=None, say=lam
         EV = {c: f_ev[c].result() for c in my_sel}
         # ---- search -> prune -> p-values (grouped) -> prune by p-value -> stripiness
         kept, pend, f_pv = [], [], []      # kept: (chrom, records, positions)
+        final, f_st, all_pv = [], [], []
+        # p-values in groups of `group` chromosomes, but never so large that a rank with few search
+        # units computes all of them after its last search: with 8 GPUs x 2 host threads a thread owns
+        # one or two chromosomes, and the chain last search -> p-values -> RemoveRedundant ->
+        # stripiness -> tables is the serial tail of the whole step
+        group = max(1, min(group, (len(my_units) + 2) // 3))
+        pv_next = [0]
+
+        def consume_pvalues(block):
+            """RemoveRedundant(pvalue) and the stripiness call of every p-value group that has
+            finished (`block`: of every group), in submission order."""
+            while pv_next[0] < len(f_pv) and (block or f_pv[pv_next[0]][1].done()):
+                grp, f = f_pv[pv_next[0]]
+                pv_next[0] += 1
+                pv = f.result()
+                off = 0
+                rows = []
+                for c, cand, pos in grp:
+                    p = pv[off:off + len(cand)]
+                    off += len(cand)
+                    all_pv.append(p)
+                    keep = gs.remove_redundant_mask(np.zeros(len(cand), np.int32), cand["frame"].astype(np.int64),
+                                                    pos, cand["h"].astype(np.float64), cand["w"].astype(np.float64),
+                                                    np.ascontiguousarray(p, dtype=np.float64), "pvalue")
+                    rows.append((c, cand[keep], pos[keep], p[keep]))
+                f_st.append((rows, dq.submit(obj.stripiness_of, [(c, pos) for c, _, pos, _ in rows], EV, mask)))
 
         def flush_group():
             if pend:
@@ -421,6 +447,7 @@ def run_pipeline(obj, cm, qs, chromnames, pvalue, mask, slow, comm=None, say=lam
                 rec = np.empty(len(raw), dtype=PIECE_DTYPE)
                 rec["ck"], rec["piece"], rec["rec"] = cidx[u["chrom"]], u["piece"], raw
                 pieces.append(rec)
+            consume_pvalues(False)         # earlier groups: prune and queue their stripiness behind the next search
         if split_chroms:
             # exchange 3 (only when a chromosome was cut): the window ranges of a chromosome meet
             # at its primary, in window order, before the cross-window pruning
@@ -435,20 +462,7 @@ def run_pipeline(obj, cm, qs, chromnames, pvalue, mask, slow, comm=None, say=lam
         flush_group()
         f_bg.result()
         clock.lap('search+prune')
-        final, f_st, all_pv = [], [], []
-        for grp, f in f_pv:
-            pv = f.result()
-            off = 0
-            rows = []
-            for c, cand, pos in grp:
-                p = pv[off:off + len(cand)]
-                off += len(cand)
-                all_pv.append(p)
-                keep = gs.remove_redundant_mask(np.zeros(len(cand), np.int32), cand["frame"].astype(np.int64), pos,
-                                                cand["h"].astype(np.float64), cand["w"].astype(np.float64),
-                                                np.ascontiguousarray(p, dtype=np.float64), "pvalue")
-                rows.append((c, cand[keep], pos[keep], p[keep]))
-            f_st.append((rows, dq.submit(obj.stripiness_of, [(c, pos) for c, _, pos, _ in rows], EV, mask)))
+        consume_pvalues(True)
         clock.lap('pvalue+dedup')
         say('5. Stripiness calculation ...')
         for rows, f in f_st:
