@@ -261,7 +261,7 @@ def filtered_sorted(table, pvals, stripiness, pcut):
 
 
 def run_pipeline(obj, cm, qs, chromnames, pvalue, mask, slow, comm=None, say=lambda *a, **k: None,
-                 return_stages=False, group=5, ahead=2):
+                 return_stages=False, group=5, ahead=2, adapt_group=True):
     """Stages 1-5 of compute (stripenn.py:120-152) for the units this (virtual) rank owns
     (plan_units: whole chromosomes, window ranges of over-sized ones).  `obj` is a getStripe-shaped
     object, `comm` a communicator of stripenn_b200.comm.
@@ -400,7 +400,8 @@ def run_pipeline(obj, cm, qs, chromnames, pvalue, mask, slow, comm=None, say=lam
         # units computes all of them after its last search: with 8 GPUs x 2 host threads a thread owns
         # one or two chromosomes, and the chain last search -> p-values -> RemoveRedundant ->
         # stripiness -> tables is the serial tail of the whole step
-        group = max(1, min(group, (len(my_units) + 2) // 3))
+        if adapt_group:
+            group = max(1, min(group, (len(my_units) + 2) // 3))
         pv_next = [0]
 
         def consume_pvalues(block):

@@ -216,3 +216,28 @@ def test_filtered_sorted_equals_the_pandas_expression():
         want = t[t["pvalue"] < cut].sort_values(by=["Stripiness"], ascending=False)
         got = cp.filtered_sorted(t, pv, s, cut)
         pd.testing.assert_frame_equal(got, want)
+
+
+@pytest.mark.parametrize("group", [1, 2])
+def test_pvalue_grouping_does_not_change_the_tables(tiny2_cm, group):
+    """run_pipeline computes the p-values in groups of chromosomes and prunes / scores every group as
+    soon as it has finished (the tail of a sharded step): one chromosome per group, both in one group
+    and everything in a single group after the last search give the same rows."""
+    cm = tiny2_cm
+    bal = cp.resolve_norm(cm, "KR", "compute", False)
+    all_names, all_sizes, names, sizes = cp.compute_chromosomes(cm, ["all"])
+    out = []
+    for g in (group, 50):
+        dev = FakeDevice(cm, bal)
+        o = cp.make_object(cm, bal, dev, all_names, all_sizes, names, sizes, 10, 8, 2.0, 1, 3, 123456789, 0)
+        out.append(cp.run_pipeline(o, cm, [0.95, 0.99], names, 0.1, '0', False, None, return_stages=True, group=g,
+                                   adapt_group=False))
+    (unf, fil, st), (unf0, fil0, st0) = out
+    assert len(unf) == len(unf0) > 0
+    for k in unf.columns:
+        a, b = unf[k].to_numpy(), unf0[k].to_numpy()
+        assert (a == b).all() or np.allclose(a.astype(float), b.astype(float), rtol=0, atol=0, equal_nan=True), k
+    assert list(fil.index) == list(fil0.index)
+    for ta, tb in zip(st["per_q"], st0["per_q"]):
+        assert ta["pos1"].tolist() == tb["pos1"].tolist()
+        np.testing.assert_array_equal(ta["pvalue"].to_numpy(float), tb["pvalue"].to_numpy(float))
