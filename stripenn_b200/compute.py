@@ -498,20 +498,27 @@ def run_pipeline(obj, cm, qs, chromnames, pvalue, mask, slow, comm=None, say=lam
                                  ['pvalue', 'Stripiness'])
             return empty, empty[empty['pvalue'] < pvalue]
         # reference row order: maxpixel-major, then chromosomes in -k order, then emission order
-        # (rows of one chromosome come from one rank, already in emission order)
-        m = m[np.lexsort((np.arange(len(m)), m["ck"], m["q"]))]
+        # (rows of one chromosome come from one rank, already in emission order): ONE stable sort of a
+        # small integer key (16-bit keys take numpy's radix sort), and every column is taken through the
+        # order from its field — re-ordering the 86-byte records first and pulling the fields out of the
+        # copy was a third of the table time (3.5 -> 2.6 ms for the 6,353 rows of a cfg3 genome)
+        nck = max(len(chromnames), 1)
+        key = m["q"].astype(np.int64) * nck + m["ck"]
+        order = np.argsort(key.astype(np.int16) if key.max(initial=0) < 32000 else key, kind="stable")
+        col = lambda k: m[k][order]
+        q, ck = col("q"), col("ck")
         # string columns: take from a small typed array (pandas would convert an object array
         # element by element); same dtype as a DataFrame built from Python strings
         sdt = pd.Series(np.array(["x"], dtype=object)).dtype
-        chrs = pd.array([str(c) for c in chromnames], dtype=sdt).take(m["ck"])
+        chrs = pd.array([str(c) for c in chromnames], dtype=sdt).take(ck)
+        p1, p2, p3, p4 = col("pos1"), col("pos2"), col("pos3"), col("pos4")
         with np.errstate(divide="ignore", invalid="ignore"):
-            mean = m["total"] / m["h"] / m["w"]                     # getStripe.py:1097
-        pv, st = np.ascontiguousarray(m["pvalue"]), np.ascontiguousarray(m["s"])
+            mean = col("total") / col("h") / col("w")                # getStripe.py:1097
+        pv, st = col("pvalue"), col("s")
         table = pd.DataFrame({
-            'chr': chrs, 'pos1': np.ascontiguousarray(m["pos1"]), 'pos2': np.ascontiguousarray(m["pos2"]),
-            'chr2': chrs, 'pos3': np.ascontiguousarray(m["pos3"]), 'pos4': np.ascontiguousarray(m["pos4"]),
-            'length': m["pos4"] - m["pos3"] + 1, 'width': m["pos2"] - m["pos1"] + 1, 'Mean': mean,
-            'maxpixel': pd.array(list(labels), dtype=sdt).take(m["q"]), 'pvalue': pv,
+            'chr': chrs, 'pos1': p1, 'pos2': p2, 'chr2': chrs, 'pos3': p3, 'pos4': p4,
+            'length': p4 - p3 + 1, 'width': p2 - p1 + 1, 'Mean': mean,
+            'maxpixel': pd.array(list(labels), dtype=sdt).take(q), 'pvalue': pv,
             'Stripiness': st}, copy=False)
         return table, filtered_sorted(table, pv, st, pvalue)
     result_table, res_filter = comm.once(build)
